@@ -1,0 +1,122 @@
+"""Pins the CPU oracle (oracle/) and the host-side fold against outputs of the reference itself.
+
+The golden files under tests/golden/ were produced by tools/gen_golden.py, which imports the
+reference from /root/reference and runs: the streaming composition of scripts/export_onnx.py:48-58,
+the offline Model.forward (model.py:728-735) and ONNXModel.forward (model.py:677-710).
+Tolerance: the north-star bar is 1e-4 RMS on the waveform; the oracle is held to 1e-6 (it is fp32
+arithmetic in a different summation order).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import rms
+from fastenhancer_b200.config import PRESETS
+from fastenhancer_b200.schema import synthetic_state_dict, canonical_size, state_dict_schema
+from fastenhancer_b200.synth import synthetic_noisy
+from oracle.oracle import Oracle, oracle_fold, tap_schema
+
+ALL = sorted(PRESETS)
+N_HOPS, TAP_HOP = 24, 5
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_fold_matches_reference(name, golden, canonical):
+    """fastenhancer_b200.fold and oracle_fold vs the reference's remove_weight_reparameterizations."""
+    cfg, g = PRESETS[name], golden(name)
+    mine = canonical(name)
+    assert mine.size == canonical_size(cfg)
+    np.testing.assert_allclose(mine[:4096], g["canonical_head"], rtol=0, atol=2e-7)
+    theirs = oracle_fold(cfg, synthetic_state_dict(cfg, 0))
+    np.testing.assert_allclose(mine, theirs, rtol=0, atol=3e-7)
+    # the float32 restatement reproduces the reference's folded bits on most presets; when it does
+    # the sha matches too -- informative only, the allclose above is the assertion.
+    _ = hashlib.sha256(theirs.tobytes()).digest() == bytes(g["canonical_sha"])
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_param_count_matches_readme(name):
+    """Folded parameter counts published in the reference README."""
+    want = {"16k_t": 21774, "16k_b": 91430, "16k_s": 194418, "16k_m": 491594, "16k_l": 1104610}
+    cfg = PRESETS[name]
+    n = canonical_size(cfg)
+    if (cfg.pre_post_init or "").endswith("_fixed"):
+        n -= 2 * cfg.f1 * cfg.rf_freq          # fixed filterbanks are buffers, not parameters
+    n -= 3 * cfg.rf_channels * cfg.rf_blocks   # canonical carries a (zero) qkv bias
+    if name in want:
+        assert n == want[name]
+    assert len(state_dict_schema(cfg)) > 0
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_streaming_wav2wav(name, golden, canonical):
+    cfg, g = PRESETS[name], golden(name)
+    o = Oracle(cfg, canonical(name))
+    x = synthetic_noisy(2, N_HOPS * cfg.hop_size, cfg.sample_rate)
+    state = o.new_state(2)
+    y, taps = o.stream(state, x, taps=True)
+    assert y.shape == g["stream_out"].shape
+    assert rms(y - g["stream_out"]) < 1e-6
+    assert np.abs(state - g["stream_state"]).max() < 5e-6
+    names = dict(tap_schema(cfg))
+    for key in g.files:
+        if key.startswith("tap.") and key[4:] in names:
+            ref = g[key]
+            assert np.abs(taps[key[4:]][TAP_HOP] - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), key
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_streaming_is_chunk_invariant(name, canonical):
+    """hop-by-hop == all hops in one call (state round trip), bit for bit."""
+    cfg = PRESETS[name]
+    o = Oracle(cfg, canonical(name))
+    H = cfg.hop_size
+    x = synthetic_noisy(1, 6 * H, cfg.sample_rate)
+    s1, s2 = o.new_state(1), o.new_state(1)
+    y1 = o.stream(s1, x)
+    y2 = np.concatenate([o.stream(s2, x[:, i * H:(i + 1) * H]) for i in range(6)], axis=1)
+    assert np.array_equal(y1, y2) and np.array_equal(s1, s2)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_offline(name, golden, canonical):
+    cfg, g = PRESETS[name], golden(name)
+    o = Oracle(cfg, canonical(name))
+    L = int(g["offline_len"])
+    wav, spec = o.offline(synthetic_noisy(2, L, cfg.sample_rate))
+    assert wav.shape == g["offline_wav"].shape == (2, cfg.hop_size * (L // cfg.hop_size))
+    assert spec.shape == (2, cfg.f_in, 1 + L // cfg.hop_size, 2)
+    assert rms(wav - g["offline_wav"]) < 1e-6
+    if "offline_spec_frames" in g.files:
+        spec = spec[:, :, g["offline_spec_frames"]]
+    assert np.abs(spec - g["offline_spec"]).max() < 1e-4 * max(1.0, np.abs(g["offline_spec"]).max())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_spec2spec(name, golden, canonical):
+    cfg, g = PRESETS[name], golden(name)
+    o = Oracle(cfg, canonical(name))
+    h = np.zeros((2, cfg.rf_blocks, cfg.rf_freq, cfg.rf_channels), np.float32)
+    out = np.concatenate([o.spec(h, g["spec_in"][:, :, :3]), o.spec(h, g["spec_in"][:, :, 3:6])], axis=2)
+    scale = np.abs(g["spec_out"]).max()
+    assert np.abs(out - g["spec_out"]).max() < 1e-5 * scale
+    assert np.abs(h - g["spec_h"]).max() < 5e-6
+    assert np.all(out[:, -1] == 0)              # Nyquist bin padded with zeros (model.py:709)
+
+
+def test_streaming_equals_offline_interior(canonical):
+    """For hop = N/2 the streaming output (delayed by N-H) equals the offline output away from the
+    edges (SURVEY.md section 7 'two framings'); bit-exact frame indexing is what this pins."""
+    cfg = PRESETS["16k_b"]
+    o = Oracle(cfg, canonical("16k_b"))
+    H, N = cfg.hop_size, cfg.n_fft
+    L = 30 * H
+    x = synthetic_noisy(1, L, cfg.sample_rate)
+    off, _ = o.offline(x)
+    xs = np.concatenate([x, np.zeros((1, N), np.float32)], axis=1)
+    n_hops = (L + N - H + H - 1) // H
+    ys = o.stream(o.new_state(1), xs[:, :n_hops * H])
+    ys = ys[:, N - H:N - H + L]
+    # the GRU state differs at t=0 (offline sees a reflected first frame), so compare late frames
+    assert rms(ys[:, 20 * H:28 * H] - off[:, 20 * H:28 * H]) < 5e-3 * rms(off)
