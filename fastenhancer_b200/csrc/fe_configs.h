@@ -1,0 +1,41 @@
+// fe_configs.h -- the shipped FastEnhancer configurations and the (config, streams-per-CTA)
+// variants the engine instantiates.  Shapes: configs/fastenhancer/{t,b,s,m,l}.yaml:1-29 and
+// configs/fastenhancer_48khz/{t,b,s,m,l}.yaml:1-29 of the reference.
+#pragma once
+#include "fe_plan.h"
+
+namespace fe {
+//                 N_FFT HOP  C1  E  C2  F2  K
+using C16T = Cfg<  512, 256,  24, 2, 20, 16, 2>;
+using C16B = Cfg<  512, 256,  48, 2, 36, 24, 3>;
+using C16S = Cfg<  512, 256,  64, 3, 48, 36, 3>;
+using C16M = Cfg<  512, 160,  96, 3, 72, 48, 4>;
+using C16L = Cfg<  512, 100, 128, 4, 96, 64, 5>;
+using C48T = Cfg< 1024, 512,  24, 2, 20, 24, 2>;
+using C48B = Cfg< 1024, 512,  48, 2, 36, 36, 3>;
+using C48S = Cfg< 1024, 512,  64, 3, 48, 48, 3>;
+using C48M = Cfg< 1024, 320,  96, 3, 72, 72, 4>;
+using C48L = Cfg< 1024, 200, 128, 4, 96, 96, 5>;
+}  // namespace fe
+
+// X(config id, Cfg type, S)
+#define FE_VARIANTS_16T(X) X(0, C16T, 1) X(0, C16T, 2) X(0, C16T, 4)
+#define FE_VARIANTS_16B(X) X(1, C16B, 1) X(1, C16B, 2)
+#define FE_VARIANTS_16S(X) X(2, C16S, 1)
+#define FE_VARIANTS_16M(X) X(3, C16M, 1)
+#define FE_VARIANTS_16L(X) X(4, C16L, 1)
+#define FE_VARIANTS_48T(X) X(5, C48T, 1) X(5, C48T, 2)
+#define FE_VARIANTS_48B(X) X(6, C48B, 1)
+#define FE_VARIANTS_48S(X) X(7, C48S, 1)
+#define FE_VARIANTS_48M(X) X(8, C48M, 1)
+#define FE_VARIANTS_48L(X) X(9, C48L, 1)
+#define FE_ALL_VARIANTS(X) FE_VARIANTS_16T(X) FE_VARIANTS_16B(X) FE_VARIANTS_16S(X) FE_VARIANTS_16M(X) FE_VARIANTS_16L(X) \
+    FE_VARIANTS_48T(X) FE_VARIANTS_48B(X) FE_VARIANTS_48S(X) FE_VARIANTS_48M(X) FE_VARIANTS_48L(X)
+
+namespace fe {
+struct ShapeKey { int n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads; };
+template <class C> constexpr bool shape_matches(const ShapeKey& k) {
+    return k.n_fft == C::N_FFT && k.hop == C::HOP && k.c1 == C::C1 && k.n_enc == C::E && k.c2 == C::C2 && k.f2 == C::F2 &&
+           k.n_blocks == C::K && k.n_heads == C::NH;
+}
+}  // namespace fe

@@ -1,0 +1,3 @@
+// fused-kernel instantiations for the 48T configuration (one translation unit per config so they build in parallel)
+#include "fe_inst.cuh"
+FE_DEFINE_VARIANTS(variants_48t, FE_VARIANTS_48T)

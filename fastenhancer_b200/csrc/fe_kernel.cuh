@@ -1,0 +1,782 @@
+// fe_kernel.cuh -- the fused per-hop FastEnhancer kernel body.
+//
+// One CTA owns S streams for every hop of the launch: window + rFFT, power-law compression, the
+// Conv1d encoder, the RNNFormer blocks (shared-weight sub-band GRU step + MHSA across frequency),
+// the skip-connected decoder with its transposed-conv complex-mask head, mask * spectrum,
+// decompression and irFFT + overlap-add all happen in shared memory; recurrent / overlap state
+// stays on chip across hops.  Weights stream through a shared-memory ring filled by a dedicated
+// producer warp with bulk async copies (cp.async.bulk + mbarrier), one pass per hop in execution
+// order, so the next layer's weights are already in flight while the current layer computes.
+//
+// What each stage restates (reference = /root/reference):
+//   front end      functional/audio_modules.py:243-257 (ONNXSTFT.forward), :70-90 (offline framing)
+//   compression    models/fastenhancer/default/model.py:684-690
+//   encoder        model.py:436-456, :628-642          rf_pre   model.py:459-465, :646-650
+//   RNNFormer      model.py:266-291 (GRU :187-190, attention :129-152)
+//   rf_post        model.py:486-490, :654-658          decoder  model.py:493-521, :661-671
+//   mask / decomp  model.py:694-709 (streaming), :732-733 (offline)
+//   back end       functional/audio_modules.py:259-303 (ONNXSTFT.inverse), :108-121 (offline)
+//
+// The body is written as a sequence of barrier-separated *phases*, each a function of the thread
+// id only.  On the GPU a phase is `f(tid); bar.sync`.  The test-only CPU emulation
+// (tests/emu/fe_emu.cpp, -DFE_EMU) runs `for tid: f(tid)` instead, which lets the whole index /
+// layout / packing logic be checked against the oracle without a GPU.
+#pragma once
+#include "fe_plan.h"
+
+#ifdef FE_EMU
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#define FE_DEV inline
+namespace fe {
+struct f4 { float x, y, z, w; };
+struct f2 { float x, y; };
+inline f4 ld4(const float* p) { f4 v; std::memcpy(&v, p, 16); return v; }
+inline f2 ld2(const float* p) { f2 v; std::memcpy(&v, p, 8); return v; }
+inline void st4(float* p, f4 v) { std::memcpy(p, &v, 16); }
+inline void st2(float* p, f2 v) { std::memcpy(p, &v, 8); }
+inline float ldg(const float* p) { return *p; }
+inline f2 ldg2(const float* p) { return ld2(p); }
+inline float fe_exp(float x) { return expf(x); }
+inline float fe_div(float a, float b) { return a / b; }
+}  // namespace fe
+#else
+#define FE_DEV __device__ __forceinline__
+namespace fe {
+using f4 = float4;
+using f2 = float2;
+FE_DEV f4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+FE_DEV f2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+FE_DEV void st4(float* p, f4 v) { *reinterpret_cast<float4*>(p) = v; }
+FE_DEV void st2(float* p, f2 v) { *reinterpret_cast<float2*>(p) = v; }
+FE_DEV float ldg(const float* p) { return __ldg(p); }
+FE_DEV f2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+FE_DEV float fe_exp(float x) { return __expf(x); }
+FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
+}  // namespace fe
+#endif
+
+namespace fe {
+
+FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
+FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
+FE_DEV float silu(float x) { return fe_div(x, 1.0f + fe_exp(-x)); }
+FE_DEV float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int PT> FE_DEV void load_pt(const float* p, float* v) {
+    if constexpr (PT == 4) { f4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (PT == 2) { f2 t = ld2(p); v[0] = t.x; v[1] = t.y; }
+    else { for (int j = 0; j < PT; ++j) v[j] = p[j]; }
+}
+template <int PT> FE_DEV void store_pt(float* p, const float* v) {
+    if constexpr (PT == 4) st4(p, mk4(v[0], v[1], v[2], v[3]));
+    else if constexpr (PT == 2) st2(p, mk2(v[0], v[1]));
+    else { for (int j = 0; j < PT; ++j) p[j] = v[j]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Thread geometry of a PosGemm tile.
+// ---------------------------------------------------------------------------------------------
+template <class L> struct PosGeo {
+    int lane, pl, cl, pg, cgp, s, f, xoff;
+    bool pvalid;
+    FE_DEV PosGeo(int tid, int stream_pitch, int data_off) {
+        int warp = tid >> 5;
+        lane = tid & 31;
+        pl = lane % L::PL; cl = lane / L::PL;
+        pg = warp % L::NPG; cgp = warp / L::NPG;
+        int p0 = (pg * L::PL + pl) * L::PT;
+        pvalid = p0 < L::NPOS;
+        if (!pvalid) p0 = 0;
+        s = p0 / L::F; f = p0 % L::F;
+        xoff = s * stream_pitch + f + data_off;
+    }
+    FE_DEV int co0(int pass) const { return ((pass * L::NCGP + cgp) * L::CL + cl) * L::CT; }
+};
+
+// acc[i][j] += sum_k sum_t W[co0+i][k][t] * X[k][p0 + j + t - TAPS/2] over the chunks of one pass.
+template <class L, class X, class XRow>
+FE_DEV void pos_accumulate(X& x, int ci0, XRow xrow, const PosGeo<L>& g, bool active, float (&acc)[L::CT][L::PT]) {
+    constexpr int CT = L::CT, PT = L::PT, TAPS = L::TAPS, RW = L::RW;
+    static_assert(L::SETS == 1, "use gru_layer for the fused GRU tile");
+    for (int c = 0; c < L::NCHUNK_PASS; ++c) {
+        const float* w = x.acquire(ci0 + c, (c == L::NCHUNK_PASS - 1 ? L::K - c * L::KC : L::KC) * L::ROW);
+        if (active) {
+            const float* wl = w + (g.cgp * L::CL + g.cl) * RW;
+            const int k0 = c * L::KC;
+            const int rows = (c == L::NCHUNK_PASS - 1) ? L::K - k0 : L::KC;
+#pragma unroll 2
+            for (int kk = 0; kk < rows; ++kk) {
+                const float* xr = xrow(k0 + kk) + g.xoff;
+                float xv[PT + TAPS - 1];
+                if constexpr (TAPS == 3) {
+                    xv[0] = xr[-1];
+                    load_pt<PT>(xr, xv + 1);
+                    xv[PT + 1] = xr[PT];
+                } else {
+                    load_pt<PT>(xr, xv);
+                }
+                float wv[RW];
+#pragma unroll
+                for (int e = 0; e < RW; e += 4) { f4 t = ld4(wl + kk * L::ROW + e); wv[e] = t.x; wv[e + 1] = t.y; wv[e + 2] = t.z; wv[e + 3] = t.w; }
+#pragma unroll
+                for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+                    for (int i = 0; i < CT; ++i)
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) acc[i][j] = fmaf(wv[t * CT + i], xv[j + t], acc[i][j]);
+            }
+        }
+        x.release(ci0 + c);
+    }
+}
+
+// Full layer: every pass accumulates and hands its rows to epi(co, s, f, values[PT]).
+template <class L, class X, class XRow, class Epi>
+FE_DEV void pos_gemm(X& x, int tid, int ci0, XRow xrow, int stream_pitch, int data_off, Epi epi) {
+    PosGeo<L> g(tid, stream_pitch, data_off);
+    for (int pass = 0; pass < L::NPASS; ++pass) {
+        float acc[L::CT][L::PT];
+#pragma unroll
+        for (int i = 0; i < L::CT; ++i)
+#pragma unroll
+            for (int j = 0; j < L::PT; ++j) acc[i][j] = 0.f;
+        const int co0 = g.co0(pass);
+        const bool active = g.pvalid && co0 < L::COUT;
+        pos_accumulate<L>(x, ci0 + pass * L::NCHUNK_PASS, xrow, g, active, acc);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < L::CT; ++i)
+                if (co0 + i < L::COUT) epi(co0 + i, g.s, g.f, acc[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row GEMM (frequency-axis linears).  epi(row, o0, values[NO]).
+// ---------------------------------------------------------------------------------------------
+template <class L, class X, class Epi>
+FE_DEV void row_gemm(X& x, int tid, int ci0, const float* xbase, int row_pitch, Epi epi) {
+    constexpr int RT = L::RT, NO = L::NO;
+    const int og = tid >> 5, lane = tid & 31;
+    const bool active = og < L::NOG;
+    float acc[RT][NO];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < NO; ++j) acc[i][j] = 0.f;
+    const float* xr[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) { int r = lane + 32 * i; xr[i] = xbase + (r < L::NROWS ? r : 0) * row_pitch; }
+    for (int c = 0; c < L::NCHUNK; ++c) {
+        const int rows = (c == L::NCHUNK - 1) ? L::K4 - c * L::KC : L::KC;
+        const float* w = x.acquire(ci0 + c, rows * L::ROW);
+        if (active) {
+            const float* wl = w + og * NO * 4;
+#pragma unroll 2
+            for (int kk = 0; kk < rows; ++kk) {
+                const int k4 = c * L::KC + kk;
+                f4 xv[RT];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) xv[i] = ld4(xr[i] + 4 * k4);
+#pragma unroll
+                for (int j = 0; j < NO; ++j) {
+                    f4 wv = ld4(wl + kk * L::ROW + j * 4);
+#pragma unroll
+                    for (int i = 0; i < RT; ++i)
+                        acc[i][j] = fmaf(wv.w, xv[i].w, fmaf(wv.z, xv[i].z, fmaf(wv.y, xv[i].y, fmaf(wv.x, xv[i].x, acc[i][j]))));
+                }
+            }
+        }
+        x.release(ci0 + c);
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = lane + 32 * i;
+            if (r < L::NROWS) epi(r, og * NO, acc[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The frame.
+// ---------------------------------------------------------------------------------------------
+template <class P> struct Frame {
+    using C = typename P::Cf;
+    static constexpr int S = P::S, NT = P::NT, N = C::N_FFT, H = C::HOP, M = C::M, FIN = C::FIN;
+    static constexpr int C1 = C::C1, C2 = C::C2, F1 = C::F1, F2 = C::F2, E = C::E, HD = C::HD;
+    static constexpr int P1 = P::P1, CP1 = P::CP1, ACT = P::ACT, F2P = P::F2P, PR = P::PR;
+    static constexpr int NMASK = N - 1;
+    static constexpr int LOG2M = (M == 128) ? 7 : (M == 256) ? 8 : (M == 512) ? 9 : (M == 1024) ? 10 : -1;
+    static_assert(LOG2M > 0, "unsupported n_fft");
+
+    // oracle tap layout (oracle/fe_oracle.c::core)
+    static constexpr int TAP_SPEC = 0;
+    static constexpr int TAP_ENC = 2 * FIN;                                // E+1 tensors [C1][F1]
+    static constexpr int TAP_RFPRE = TAP_ENC + (E + 1) * C1 * F1;
+    static constexpr int TAP_BLK = TAP_RFPRE + F2 * C2;                    // per block: mid, out, h
+    static constexpr int TAP_RFPOST = TAP_BLK + C::K * 3 * F2 * C2;
+    static constexpr int TAP_DEC = TAP_RFPOST + C1 * F1;
+    static constexpr int TAP_MASK = TAP_DEC + E * C1 * F1;
+    static constexpr int TAP_SPECHAT = TAP_MASK + 2 * FIN;
+    static constexpr int TAP_TOTAL = TAP_SPECHAT + 2 * FIN;
+
+    struct PwAcc { float v[P::PwCat::CT][P::PwCat::PT]; };
+
+    // Geo1 output row: bias (+SiLU), data columns, the 4 zero pad columns and the buffer tail.
+    struct EpiGeo1 {
+        float* dst; const float* bias; float* gdst; bool act;
+        FE_DEV void operator()(int co, int s, int f, const float* v) const {
+            const float b = ldg(bias + co);
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float t = v[j] + b; o[j] = act ? silu(t) : t; }
+            float* row = dst + co * CP1 + s * P1;
+            st4(row + 4 + f, mk4(o[0], o[1], o[2], o[3]));
+            if (f == 0) {
+                st4(row, mk4(0.f, 0.f, 0.f, 0.f));
+                if (co == C1 - 1 && s == S - 1) st4(dst + ACT - 4, mk4(0.f, 0.f, 0.f, 0.f));
+            }
+            if (gdst) st4(gdst + co * CP1 + s * P1 + 4 + f, mk4(o[0], o[1], o[2], o[3]));
+        }
+    };
+
+    template <class X> FE_DEV static void run(X& x) {
+        const KParams& prm = x.prm;
+        float* sm = x.sm;
+        // ---- one-time init: zero the activation area, load overlap state ----
+        x.phase([&](int tid) {
+            for (int i = tid * 4; i < P::SM_RING; i += NT * 4) st4(sm + i, mk4(0.f, 0.f, 0.f, 0.f));
+        });
+        if (prm.mode == MODE_STREAM) {
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * C::CL; idx += NT) {
+                    int s = idx / C::CL, i = idx % C::CL;
+                    int gs = x.s0 + s;
+                    float a = 0.f, b = 0.f;
+                    if (gs < prm.n_streams) {
+                        const float* st = prm.state + (size_t)gs * C::STATE;
+                        a = st[i]; b = st[C::CL + i];
+                    }
+                    sm[P::SM_TIN + s * N + ((H + i) & NMASK)] = a;
+                    sm[P::SM_OLA + s * N + i] = b;
+                }
+            });
+        }
+        for (int hop = 0; hop < prm.n_hops; ++hop) {
+            frame(x, hop);
+            x.next_frame();
+        }
+        if (prm.mode == MODE_STREAM) {
+            const int n = prm.n_hops;
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * C::CL; idx += NT) {
+                    int s = idx / C::CL, i = idx % C::CL;
+                    int gs = x.s0 + s;
+                    if (gs < prm.n_streams) {
+                        float* st = prm.state + (size_t)gs * C::STATE;
+                        st[i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
+                        st[C::CL + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
+                    }
+                }
+            });
+        }
+    }
+
+    // complex M-point Stockham radix-2 FFT over S streams; returns the buffer holding the result
+    template <class X> FE_DEV static float* fft(X& x, float* src, float* dst, bool inverse) {
+        const float* tw = x.blob + P::make_aux().tw;
+        int st = 1;
+        for (int stage = 0; stage < LOG2M; ++stage, st <<= 1) {
+            const int lst = stage;
+            x.phase([&](int tid) {
+                for (int j = tid; j < S * (M / 2); j += NT) {
+                    const int s = j / (M / 2), jj = j % (M / 2);
+                    const int p = jj >> lst, q = jj & (st - 1);
+                    const float* sp = src + s * N;
+                    float* dp = dst + s * N;
+                    f2 a = ld2(sp + 2 * (q + st * p));
+                    f2 b = ld2(sp + 2 * (q + st * (p + (M >> (lst + 1)))));
+                    f2 w = ldg2(tw + 2 * (p * st));
+                    if (inverse) w.y = -w.y;
+                    float dr = a.x - b.x, di = a.y - b.y;
+                    st2(dp + 2 * (q + st * 2 * p), mk2(a.x + b.x, a.y + b.y));
+                    st2(dp + 2 * (q + st * (2 * p + 1)), mk2(dr * w.x - di * w.y, dr * w.y + di * w.x));
+                }
+            });
+            float* t = src; src = dst; dst = t;
+        }
+        return src;
+    }
+
+    template <class X> FE_DEV static float* skip_dst(X& x, int i) {
+        if (i < P::SKIP_SMEM) return x.sm + P::SM_SK + i * ACT;
+        return x.sm + P::SM_W + (((E - i + 1) & 1) ? ACT : 0);
+    }
+    template <class X> FE_DEV static float* skip_gdst(X& x, int i) {
+        return (i < P::SKIP_SMEM) ? nullptr : x.gs + (size_t)(i - P::SKIP_SMEM) * ACT;
+    }
+
+    template <class X> FE_DEV static void frame(X& x, int hop) {
+        const KParams& prm = x.prm;
+        constexpr auto A = P::make_aux();
+        const float* aux = x.blob;
+        float* sm = x.sm;
+        float* W0 = sm + P::SM_W;
+        float* W1 = W0 + ACT;
+        float* AB = W0;
+        float* SPEC = sm + P::SM_SPEC;
+        float* TIN = sm + P::SM_TIN;
+        float* OLA = sm + P::SM_OLA;
+        const int mode = prm.mode;
+        const bool dbg = prm.dbg != nullptr && hop == prm.dbg_hop && x.cta == 0;
+        const int T = prm.n_hops;
+        const float comp_e = prm.compression - 1.0f, decomp_e = 1.0f / prm.compression - 1.0f;
+        int ci = 0;    // chunk index within the frame
+
+        // ================= front end =================
+        if (mode != MODE_SPEC) {
+            const int wpos = (hop * H) & NMASK;
+            if (mode == MODE_STREAM) {
+                x.phase([&](int tid) {
+                    for (int idx = tid; idx < S * H; idx += NT) {
+                        int s = idx / H, j = idx % H, gs = x.s0 + s;
+                        float v = 0.f;
+                        if (gs < prm.n_streams) v = prm.in[(size_t)gs * prm.ld_in + (size_t)hop * H + j];
+                        TIN[s * N + ((wpos + j) & NMASK)] = v;
+                    }
+                });
+            }
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * M; idx += NT) {
+                    int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
+                    float a, b;
+                    if (mode == MODE_STREAM) {
+                        a = TIN[s * N + ((wpos + H + n2) & NMASK)];
+                        b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
+                    } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
+                        a = b = 0.f;
+                        if (gs < prm.n_streams) {
+                            const float* w = prm.in + (size_t)gs * prm.L;
+                            long j0 = (long)hop * H + n2 - N / 2, j1 = j0 + 1;
+                            if (j0 < 0) j0 = -j0;
+                            if (j0 >= prm.L) j0 = 2L * (prm.L - 1) - j0;
+                            if (j1 < 0) j1 = -j1;
+                            if (j1 >= prm.L) j1 = 2L * (prm.L - 1) - j1;
+                            a = w[j0]; b = w[j1];
+                        }
+                    }
+                    st2(W0 + s * N + n2, mk2(a * ldg(aux + A.window + n2), b * ldg(aux + A.window + n2 + 1)));
+                }
+            });
+            float* Z = fft(x, W0, W1, false);
+            // unpack the packed real FFT, drop Nyquist, compress, scatter to the 8 virtual channels
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * M; idx += NT) {
+                    int s = idx / M, k = idx % M;
+                    f2 zk = ld2(Z + s * N + 2 * k), zm = ld2(Z + s * N + 2 * ((M - k) & (M - 1)));
+                    float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+                    float dr = 0.5f * (zk.x - zm.x), di = 0.5f * (zk.y + zm.y);
+                    float orr = di, oi = -dr;                                // O = -i * D
+                    f2 w = ldg2(aux + A.twn + 2 * k);
+                    float re = er + (w.x * orr - w.y * oi), im = ei + (w.x * oi + w.y * orr);
+                    float mag = sqrtf(re * re + im * im);
+                    mag = mag < 1.0e-5f ? 1.0e-5f : mag;
+                    float g = powf(mag, comp_e);
+                    int q = k & 3, m = k >> 2;
+                    SPEC[q * CP1 + s * P1 + 4 + m] = re * g;
+                    SPEC[(4 + q) * CP1 + s * P1 + 4 + m] = im * g;
+                }
+            });
+        } else {
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * M; idx += NT) {
+                    int s = idx / M, k = idx % M, gs = x.s0 + s;
+                    float re = 0.f, im = 0.f;
+                    if (gs < prm.n_streams) {
+                        f2 v = ld2(prm.in + (((size_t)gs * C::NB + k) * T + hop) * 2);
+                        re = v.x; im = v.y;
+                    }
+                    float mag = sqrtf(re * re + im * im);
+                    mag = mag < 1.0e-5f ? 1.0e-5f : mag;
+                    float g = powf(mag, comp_e);
+                    int q = k & 3, m = k >> 2;
+                    SPEC[q * CP1 + s * P1 + 4 + m] = re * g;
+                    SPEC[(4 + q) * CP1 + s * P1 + 4 + m] = im * g;
+                }
+            });
+        }
+        auto dump_spec = [&](const float* buf, int off) {
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < 2 * FIN; idx += NT) {
+                    int c = idx / FIN, k = idx % FIN;
+                    prm.dbg[off + idx] = buf[(c * 4 + (k & 3)) * CP1 + 4 + (k >> 2)];
+                }
+            });
+        };
+        auto dump_geo1 = [&](const float* buf, int off) {
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = buf[(idx / F1) * CP1 + 4 + idx % F1];
+            });
+        };
+        auto dump_rf = [&](const float* buf, int off) {
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < F2 * C2; idx += NT) prm.dbg[off + idx] = buf[(idx % C2) * PR + idx / C2];
+            });
+        };
+        if (dbg) dump_spec(SPEC, TAP_SPEC);
+
+        // ================= encoder =================
+        const float* src = SPEC;
+        for (int i = 0; i <= E; ++i) {
+            float* dst = skip_dst(x, i);
+            EpiGeo1 epi{dst, aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1)), skip_gdst(x, i), true};
+            if (i == 0) {
+                x.phase([&](int tid) {
+                    pos_gemm<typename P::EncPre>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
+                });
+                ci += P::EncPre::NCHUNK;
+            } else {
+                x.phase([&](int tid) {
+                    pos_gemm<typename P::Conv3>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
+                });
+                ci += P::Conv3::NCHUNK;
+            }
+            if (dbg) dump_geo1(dst, TAP_ENC + i * C1 * F1);
+            src = dst;
+        }
+
+        // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
+        float* Y1 = AB + P::O_Y1;
+        float* XR = AB + P::O_XR;
+        x.phase([&](int tid) {
+            row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
+#pragma unroll
+                for (int j = 0; j < P::LinPre::NO; j += 4)
+                    if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            });
+        });
+        ci += P::LinPre::NCHUNK;
+        x.phase([&](int tid) {
+            pos_gemm<typename P::RfPre>(x, tid, ci, [&](int k) { return Y1 + k * PR; }, F2P, 0,
+                                        [&](int co, int s, int f, const float* v) {
+                                            const float b = ldg(aux + A.rf_pre_b + co);
+                                            st4(XR + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                        });
+        });
+        ci += P::RfPre::NCHUNK;
+        if (dbg) dump_rf(XR, TAP_RFPRE);
+
+        // ================= RNNFormer blocks =================
+        float* HB = AB + P::O_HB;
+        float* G = AB + P::O_G;
+        float* QKV = AB + P::O_QKV;
+        float* ATT = AB + P::O_ATT;
+        for (int k = 0; k < C::K; ++k) {
+            const auto ab = A.blk(k);
+            // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
+            x.phase([&](int tid) {
+                for (int idx = tid; idx < S * C2 * F2; idx += NT) {
+                    int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
+                    float v = 0.f;
+                    if (gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + r];
+                    HB[c * PR + s * F2P + f] = v;
+                }
+            });
+            // fused GRU step (PyTorch gate order r, z, n; b_hn inside the r * (.) term)
+            x.phase([&](int tid) {
+                using L = typename P::Gru;
+                constexpr int CT = L::CT, PT = L::PT, RW = L::RW;
+                PosGeo<L> g(tid, F2P, 0);
+                for (int pass = 0; pass < L::NPASS; ++pass) {
+                    float ar[CT][PT], az[CT][PT], anx[CT][PT], anh[CT][PT];
+#pragma unroll
+                    for (int i = 0; i < CT; ++i)
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) ar[i][j] = az[i][j] = anx[i][j] = anh[i][j] = 0.f;
+                    const int co0 = g.co0(pass);
+                    const bool active = g.pvalid && co0 < C2;
+                    for (int c = 0; c < L::NCHUNK_PASS; ++c) {
+                        const int rows = (c == L::NCHUNK_PASS - 1) ? L::K - c * L::KC : L::KC;
+                        const float* w = x.acquire(ci + pass * L::NCHUNK_PASS + c, rows * L::ROW);
+                        if (active) {
+                            const float* wl = w + (g.cgp * L::CL + g.cl) * RW;
+#pragma unroll 2
+                            for (int kk = 0; kk < rows; ++kk) {
+                                const int kx = c * L::KC + kk;
+                                float xv[PT], hv[PT], wv[RW];
+                                load_pt<PT>(XR + kx * PR + g.xoff, xv);
+                                load_pt<PT>(HB + kx * PR + g.xoff, hv);
+#pragma unroll
+                                for (int e = 0; e < RW; e += 4) { f4 t = ld4(wl + kk * L::ROW + e); wv[e] = t.x; wv[e + 1] = t.y; wv[e + 2] = t.z; wv[e + 3] = t.w; }
+#pragma unroll
+                                for (int i = 0; i < CT; ++i)
+#pragma unroll
+                                    for (int j = 0; j < PT; ++j) {
+                                        ar[i][j] = fmaf(wv[3 * CT + i], hv[j], fmaf(wv[0 * CT + i], xv[j], ar[i][j]));
+                                        az[i][j] = fmaf(wv[4 * CT + i], hv[j], fmaf(wv[1 * CT + i], xv[j], az[i][j]));
+                                        anx[i][j] = fmaf(wv[2 * CT + i], xv[j], anx[i][j]);
+                                        anh[i][j] = fmaf(wv[5 * CT + i], hv[j], anh[i][j]);
+                                    }
+                            }
+                        }
+                        x.release(ci + pass * L::NCHUNK_PASS + c);
+                    }
+                    if (active) {
+                        const int gs = x.s0 + g.s;
+#pragma unroll
+                        for (int i = 0; i < CT; ++i) {
+                            const int c = co0 + i;
+                            if (c < C2) {
+                                const float br = ldg(aux + ab.b_r + c), bz = ldg(aux + ab.b_z + c);
+                                const float bin = ldg(aux + ab.b_in + c), bhn = ldg(aux + ab.b_hn + c);
+                                float hn[PT], ho[PT];
+                                load_pt<PT>(HB + c * PR + g.xoff, ho);
+#pragma unroll
+                                for (int j = 0; j < PT; ++j) {
+                                    float r = sigmoid_acc(ar[i][j] + br);
+                                    float z = sigmoid_acc(az[i][j] + bz);
+                                    float nn = tanhf(anx[i][j] + bin + r * (anh[i][j] + bhn));
+                                    hn[j] = (1.0f - z) * nn + z * ho[j];
+                                }
+                                store_pt<PT>(G + c * PR + g.xoff, hn);
+                                if (gs < prm.n_streams)
+                                    store_pt<PT>(prm.state + (size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + c * F2 + g.f, hn);
+                            }
+                        }
+                    }
+                }
+            });
+            ci += P::Gru::NCHUNK;
+            // rnn_fc (+ folded BN) + residual (+ positional embedding in block 0)
+            x.phase([&](int tid) {
+                pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return G + kk * PR; }, F2P, 0,
+                                         [&](int co, int s, int f, const float* v) {
+                                             const float b = ldg(aux + ab.fc_b + co);
+                                             float* p = XR + co * PR + s * F2P + f;
+                                             f4 o = ld4(p);
+                                             o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
+                                             if (k == 0) {
+                                                 const float* pe = aux + ab.pe + co * F2 + f;
+                                                 o.x += ldg(pe); o.y += ldg(pe + 1); o.z += ldg(pe + 2); o.w += ldg(pe + 3);
+                                             }
+                                             st4(p, o);
+                                         });
+            });
+            ci += P::Fc::NCHUNK;
+            if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
+            // attention over the F2 tokens of the frame, HG heads per round
+            for (int hg = 0; hg < P::NQG; ++hg) {
+                x.phase([&](int tid) {
+                    pos_gemm<typename P::Qkv>(x, tid, ci, [&](int kk) { return XR + kk * PR; }, F2P, 0,
+                                              [&](int co, int s, int f, const float* v) {
+                                                  const float b = ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + co);
+                                                  st4(QKV + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                              });
+                });
+                ci += P::Qkv::NCHUNK;
+                x.phase([&](int tid) {
+                    const float scale = 1.0f / sqrtf((float)HD);
+                    for (int it = tid; it < S * P::HG * F2; it += NT) {
+                        const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
+                        const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
+                        float q[HD], o[HD];
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
+                        float mx = -INFINITY;
+                        for (int j = 0; j < F2; ++j) {
+                            float sc = 0.f;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                            mx = fmaxf(mx, sc);
+                        }
+                        float den = 0.f;
+                        for (int j = 0; j < F2; ++j) {
+                            float sc = 0.f;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                            const float p = expf(sc - mx);
+                            den += p;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) o[d] = fmaf(p, qb[(2 * HD + d) * PR + j], o[d]);
+                        }
+                        const float inv = 1.0f / den;
+                        float* ob = ATT + ((hg * P::HG + hh) * HD) * PR + s * F2P + i;
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) ob[d * PR] = o[d] * inv;
+                    }
+                });
+            }
+            x.phase([&](int tid) {
+                pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return ATT + kk * PR; }, F2P, 0,
+                                         [&](int co, int s, int f, const float* v) {
+                                             const float b = ldg(aux + ab.afc_b + co);
+                                             float* p = XR + co * PR + s * F2P + f;
+                                             f4 o = ld4(p);
+                                             o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
+                                             st4(p, o);
+                                         });
+            });
+            ci += P::Fc::NCHUNK;
+            if (dbg) {
+                dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
+                x.phase([&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
+                    for (int idx = tid; idx < F2 * C2; idx += NT)
+                        prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
+                            prm.state[(size_t)x.s0 * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + (idx % C2) * F2 + idx / C2];
+                });
+            }
+        }
+
+        // ================= rf_post: Linear(F2->F1), 1x1 conv =================
+        float* Zb = AB + P::O_Z;
+        x.phase([&](int tid) {
+            row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
+#pragma unroll
+                for (int j = 0; j < P::LinPost::NO; j += 4)
+                    if (o0 + j < F1) st4(Zb + r * P1 + 4 + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            });
+        });
+        ci += P::LinPost::NCHUNK;
+        {
+            EpiGeo1 epi{W1, aux + A.rf_post_b, nullptr, false};
+            x.phase([&](int tid) {
+                pos_gemm<typename P::RfPost>(x, tid, ci, [&](int kk) { return Zb + kk * CP1; }, P1, 4, epi);
+            });
+            ci += P::RfPost::NCHUNK;
+        }
+        if (dbg) dump_geo1(W1, TAP_RFPOST);
+
+        // ================= decoder + dec_post =================
+        for (int i = 0; i <= E; ++i) {
+            const int sk = E - i;                       // skip tensor consumed by this stage (deepest first)
+            const float* skip;
+            if (sk < P::SKIP_SMEM) {
+                skip = sm + P::SM_SK + sk * ACT;
+            } else {
+                const float* gsrc = x.gs + (size_t)(sk - P::SKIP_SMEM) * ACT;
+                x.phase([&](int tid) {
+                    for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(W0 + idx, ld4(gsrc + idx));
+                });
+                skip = W0;
+            }
+            // 1x1 conv over cat([x, skip]) + SiLU; stored to W0 after a barrier (W0 may hold the skip)
+            {
+                using L = typename P::PwCat;
+                EpiGeo1 epi{W0, aux + (i < E ? A.dec1_b(i) : A.dp_b), nullptr, true};
+                auto xrow = [&](int kk) { return kk < C1 ? W1 + kk * CP1 : skip + (kk - C1) * CP1; };
+                x.template phase2<PwAcc>(
+                    [&](int tid, PwAcc& a) {
+                        PosGeo<L> g(tid, P1, 4);
+#pragma unroll
+                        for (int ii = 0; ii < L::CT; ++ii)
+#pragma unroll
+                            for (int j = 0; j < L::PT; ++j) a.v[ii][j] = 0.f;
+                        pos_accumulate<L>(x, ci, xrow, g, g.pvalid && g.co0(0) < C1, a.v);
+                    },
+                    [&](int tid, PwAcc& a) {
+                        PosGeo<L> g(tid, P1, 4);
+                        const int co0 = g.co0(0);
+                        if (g.pvalid && co0 < C1) {
+#pragma unroll
+                            for (int ii = 0; ii < L::CT; ++ii)
+                                if (co0 + ii < C1) epi(co0 + ii, g.s, g.f, a.v[ii]);
+                        }
+                    });
+                ci += L::NCHUNK;
+            }
+            if (i < E) {
+                EpiGeo1 epi{W1, aux + A.dec2_b(i), nullptr, true};
+                x.phase([&](int tid) {
+                    pos_gemm<typename P::Conv3>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4, epi);
+                });
+                ci += P::Conv3::NCHUNK;
+                if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
+            }
+        }
+        // transposed conv as a 3-tap conv to 8 virtual channels (o*4 + q) -> MASK (in W1)
+        float* MASK = W1;
+        x.phase([&](int tid) {
+            pos_gemm<typename P::ConvT>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4,
+                                        [&](int vo, int s, int f, const float* v) {
+                                            const float b = ldg(aux + A.convt_b + vo);
+                                            st4(MASK + vo * CP1 + s * P1 + 4 + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                        });
+        });
+        ci += P::ConvT::NCHUNK;
+        x.check_frame(ci);
+        if (dbg) dump_spec(MASK, TAP_MASK);
+
+        // ================= mask * spectrum, decompression =================
+        x.phase([&](int tid) {
+            for (int idx = tid; idx < S * M; idx += NT) {
+                const int s = idx / M, k = idx % M, q = k & 3, m = k >> 2, gs = x.s0 + s;
+                const int o = q * CP1 + s * P1 + 4 + m;
+                const float xr = SPEC[o], xi = SPEC[o + 4 * CP1], mr = MASK[o], mi = MASK[o + 4 * CP1];
+                const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
+                if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + k] = yr; prm.dbg[TAP_SPECHAT + FIN + k] = yi; }
+                const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);
+                if (mode == MODE_SPEC) {
+                    if (gs < prm.n_streams) {
+                        st2(prm.out + (((size_t)gs * C::NB + k) * T + hop) * 2, mk2(yr * g, yi * g));
+                        if (k == 0) st2(prm.out + (((size_t)gs * C::NB + FIN) * T + hop) * 2, mk2(0.f, 0.f));
+                    }
+                } else {
+                    if (mode == MODE_OFFLINE && prm.spec_out != nullptr && gs < prm.n_streams)
+                        st2(prm.spec_out + (((size_t)gs * FIN + k) * T + hop) * 2, mk2(yr, yi));
+                    st2(W0 + s * N + 2 * k, mk2(yr * g, yi * g));
+                }
+            }
+        });
+        if (mode == MODE_SPEC) return;
+
+        // ================= irFFT (packed), window, overlap-add =================
+        x.phase([&](int tid) {
+            for (int idx = tid; idx < S * M; idx += NT) {
+                const int s = idx / M, k = idx % M;
+                f2 yk = ld2(W0 + s * N + 2 * k), ym;
+                if (k == 0) { yk.y = 0.f; ym = mk2(0.f, 0.f); }        // imag of DC ignored, Nyquist bin is zero
+                else ym = ld2(W0 + s * N + 2 * (M - k));
+                const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
+                const float dr = 0.5f * (yk.x - ym.x), di = 0.5f * (yk.y + ym.y);
+                f2 w = ldg2(aux + A.twn + 2 * k);                        // O = D * conj(w)
+                const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+                st2(W1 + s * N + 2 * k, mk2(er - oi, ei + orr));         // Z = E + i O
+            }
+        });
+        const float* Y = fft(x, W1, W0, true);
+        const int base = (hop * H) & NMASK;
+        x.phase([&](int tid) {
+            const float invM = 1.0f / (float)M;
+            for (int idx = tid; idx < S * N; idx += NT) {
+                const int s = idx / N, i = idx % N, gs = x.s0 + s;
+                const int slot = s * N + ((base + i) & NMASK);
+                float y = Y[s * N + i] * invM;
+                if (mode == MODE_STREAM) {
+                    float v = y * ldg(aux + A.window_istft + i) + (i < C::CL ? OLA[slot] : 0.f);
+                    OLA[slot] = v;
+                    if (i < H && gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = v;
+                } else {          // torch.istft(center=True): window, overlap-add, / sum of window^2, trim N/2
+                    float v = y * ldg(aux + A.window + i) + (i < C::CL ? OLA[slot] : 0.f);
+                    OLA[slot] = v;
+                    const long npad = (long)hop * H + i, n = npad - N / 2;
+                    // samples [hop*H, hop*H + H) are final after this frame; the last frame also flushes its tail
+                    if ((i < H || hop == T - 1) && gs < prm.n_streams && n >= 0 && n < (long)H * (T - 1)) {
+                        long t0 = (npad - N + H) / H;                     // ceil((npad - N + 1) / H) for npad >= N - 1
+                        if (npad < N) t0 = 0;
+                        long t1 = npad / H;
+                        if (t1 > T - 1) t1 = T - 1;
+                        float env = 0.f;
+                        for (long t = t0; t <= t1; ++t) env += ldg(aux + A.window_sq + (int)(npad - t * H));
+                        prm.out[(size_t)gs * H * (T - 1) + n] = v / env;
+                    }
+                }
+            }
+        });
+    }
+};
+
+}  // namespace fe

@@ -1,0 +1,190 @@
+// fe_pack.h -- host-side packer: canonical folded weights -> the blob the fused kernel consumes.
+//
+// The canonical array (include/fastenhancer_b200.h, fastenhancer_b200/schema.py::canonical_schema)
+// is what the reference's remove_weight_reparameterizations leaves behind
+// (models/fastenhancer/default/model.py:532-608).  The blob is
+//     [ aux: windows, FFT twiddles, biases, positional embedding | chunk table | ring section ]
+// where the ring section is every layer's weights in execution order, laid out as the rows the
+// PosGemm / RowGemm tiles of fe_plan.h read (one contiguous slice per ring chunk).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "fe_plan.h"
+
+namespace fe {
+
+template <class C> struct Canon {
+    struct Blk { const float *w_ih, *w_hh, *b_ih, *b_hh, *fc_w, *fc_b, *pe, *qkv_w, *qkv_b, *afc_w, *afc_b; };
+    const float *enc_pre_w, *enc_pre_b, *enc_w[8], *enc_b[8], *rf_pre_lin, *rf_pre_w, *rf_pre_b;
+    Blk blk[16];
+    const float *rf_post_lin, *rf_post_w, *rf_post_b, *dec_w1[8], *dec_b1[8], *dec_w2[8], *dec_b2[8];
+    const float *dp_w, *dp_b, *dp_wt, *dp_bt;
+    explicit Canon(const float* p) {
+        constexpr int C1 = C::C1, C2 = C::C2, F1 = C::F1, F2 = C::F2;
+        auto take = [&p](long n) { const float* r = p; p += n; return r; };
+        enc_pre_w = take(C1 * 16); enc_pre_b = take(C1);
+        for (int i = 0; i < C::E; ++i) { enc_w[i] = take(C1 * C1 * 3); enc_b[i] = take(C1); }
+        rf_pre_lin = take(F2 * F1); rf_pre_w = take(C2 * C1); rf_pre_b = take(C2);
+        for (int k = 0; k < C::K; ++k) {
+            Blk& b = blk[k];
+            b.w_ih = take(3 * C2 * C2); b.w_hh = take(3 * C2 * C2); b.b_ih = take(3 * C2); b.b_hh = take(3 * C2);
+            b.fc_w = take(C2 * C2); b.fc_b = take(C2);
+            b.pe = (k == 0) ? take(F2 * C2) : nullptr;
+            b.qkv_w = take(3 * C2 * C2); b.qkv_b = take(3 * C2);
+            b.afc_w = take(C2 * C2); b.afc_b = take(C2);
+        }
+        rf_post_lin = take(F1 * F2); rf_post_w = take(C1 * C2); rf_post_b = take(C1);
+        for (int i = 0; i < C::E; ++i) {
+            dec_w1[i] = take(C1 * 2 * C1); dec_b1[i] = take(C1); dec_w2[i] = take(C1 * C1 * 3); dec_b2[i] = take(C1);
+        }
+        dp_w = take(C1 * 2 * C1); dp_b = take(C1); dp_wt = take(C1 * 16); dp_bt = take(2);
+    }
+};
+
+template <class P> class Packer {
+    using C = typename P::Cf;
+    std::vector<float>& blob_;
+    std::vector<int> table_;
+    long off_;
+
+    // w(set, co, k, tap)
+    template <class L, class W> void pos(W w) {
+        for (int pass = 0; pass < L::NPASS; ++pass) {
+            for (int c = 0; c < L::NCHUNK_PASS; ++c) {
+                int rows = cmin(L::KC, L::K - c * L::KC);
+                table_.push_back((int)(off_ + ((long)pass * L::K + (long)c * L::KC) * L::ROW));
+                table_.push_back(rows * L::ROW);
+            }
+            for (int k = 0; k < L::K; ++k)
+                for (int cgp = 0; cgp < L::NCGP; ++cgp)
+                    for (int cl = 0; cl < L::CL; ++cl) {
+                        float* d = &blob_[off_ + (((long)pass * L::K + k) * L::NCGP + cgp) * L::CL * L::RW + (long)cl * L::RW];
+                        for (int set = 0; set < L::SETS; ++set)
+                            for (int t = 0; t < L::TAPS; ++t)
+                                for (int i = 0; i < L::CT; ++i) {
+                                    int co = ((pass * L::NCGP + cgp) * L::CL + cl) * L::CT + i;
+                                    d[(set * L::TAPS + t) * L::CT + i] = co < L::COUT ? w(set, co, k, t) : 0.f;
+                                }
+                    }
+        }
+        off_ += L::FLOATS;
+    }
+    // w(o, k)
+    template <class L, class W> void row(W w) {
+        for (int c = 0; c < L::NCHUNK; ++c) {
+            int rows = cmin(L::KC, L::K4 - c * L::KC);
+            table_.push_back((int)(off_ + (long)c * L::KC * L::ROW));
+            table_.push_back(rows * L::ROW);
+        }
+        for (int k4 = 0; k4 < L::K4; ++k4)
+            for (int og = 0; og < L::NOG; ++og)
+                for (int j = 0; j < L::NO; ++j)
+                    for (int t = 0; t < 4; ++t) {
+                        int o = og * L::NO + j;
+                        blob_[off_ + ((long)k4 * L::NOG + og) * L::NO * 4 + j * 4 + t] = o < L::NOUT ? w(o, 4 * k4 + t) : 0.f;
+                    }
+        off_ += L::FLOATS;
+    }
+
+public:
+    explicit Packer(std::vector<float>& blob) : blob_(blob), off_(0) {}
+
+    void pack(const float* canonical) {
+        constexpr int C1 = C::C1, C2 = C::C2, F1 = C::F1, F2 = C::F2, N = C::N_FFT, H = C::HOP, M = C::M;
+        constexpr auto A = P::make_aux();
+        Canon<C> cw(canonical);
+        blob_.assign((size_t)A.total, 0.f);
+        // ---- tables (periodic Hann: functional/audio_modules.py:213-214; window_istft :221-234) ----
+        float* win = &blob_[A.window];
+        for (int i = 0; i < N; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / N));
+        for (int i = 0; i < N; ++i) {
+            float s = 0.f;
+            for (int j = i % H; j < N; j += H) s += win[j] * win[j];
+            blob_[A.window_istft + i] = win[i] / s;
+            blob_[A.window_sq + i] = win[i] * win[i];
+        }
+        for (int t = 0; t < M / 2; ++t) {
+            blob_[A.tw + 2 * t] = (float)std::cos(-2.0 * M_PI * t / M);
+            blob_[A.tw + 2 * t + 1] = (float)std::sin(-2.0 * M_PI * t / M);
+        }
+        for (int k = 0; k < M; ++k) {
+            blob_[A.twn + 2 * k] = (float)std::cos(-2.0 * M_PI * k / N);
+            blob_[A.twn + 2 * k + 1] = (float)std::sin(-2.0 * M_PI * k / N);
+        }
+        // ---- biases ----
+        auto cp = [&](int dst, const float* src, int n) { std::memcpy(&blob_[dst], src, n * sizeof(float)); };
+        cp(A.enc_pre_b, cw.enc_pre_b, C1);
+        for (int i = 0; i < C::E; ++i) cp(A.enc_b(i), cw.enc_b[i], C1);
+        cp(A.rf_pre_b, cw.rf_pre_b, C2);
+        for (int k = 0; k < C::K; ++k) {
+            const auto& b = cw.blk[k];
+            const auto q = A.blk(k);
+            for (int c = 0; c < C2; ++c) {
+                blob_[q.b_r + c] = b.b_ih[c] + b.b_hh[c];
+                blob_[q.b_z + c] = b.b_ih[C2 + c] + b.b_hh[C2 + c];
+                blob_[q.b_in + c] = b.b_ih[2 * C2 + c];
+                blob_[q.b_hn + c] = b.b_hh[2 * C2 + c];
+            }
+            cp(q.fc_b, b.fc_b, C2);
+            if (b.pe)
+                for (int f = 0; f < F2; ++f)
+                    for (int c = 0; c < C2; ++c) blob_[q.pe + c * F2 + f] = b.pe[f * C2 + c];
+            cp(q.qkv_b, b.qkv_b, 3 * C2);
+            cp(q.afc_b, b.afc_b, C2);
+        }
+        cp(A.rf_post_b, cw.rf_post_b, C1);
+        for (int i = 0; i < C::E; ++i) { cp(A.dec1_b(i), cw.dec_b1[i], C1); cp(A.dec2_b(i), cw.dec_b2[i], C1); }
+        cp(A.dp_b, cw.dp_b, C1);
+        for (int vo = 0; vo < 8; ++vo) blob_[A.convt_b + vo] = cw.dp_bt[vo / 4];
+
+        // ---- ring section, execution order (must match fe_kernel.cuh::frame) ----
+        off_ = A.ring;
+        table_.clear();
+        // enc_pre as a 3-tap conv over 8 virtual channels v = c*4 + q holding x[c][4m + q]:
+        // original tap k = 4*dj + q + 2 (model.py:15-59, weight index [co][(k%4)*2 + c][k/4])
+        pos<typename P::EncPre>([&](int, int co, int v, int t) {
+            int c = v / 4, q = v % 4, k = 4 * (t - 1) + q + 2;
+            return (k >= 0 && k < 8) ? cw.enc_pre_w[(co * 8 + (k % 4) * 2 + c) * 2 + k / 4] : 0.f;
+        });
+        for (int i = 0; i < C::E; ++i)
+            pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
+        row<typename P::LinPre>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
+        pos<typename P::RfPre>([&](int, int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
+        for (int k = 0; k < C::K; ++k) {
+            const auto& b = cw.blk[k];
+            pos<typename P::Gru>([&](int set, int c, int ci, int) {
+                return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
+            });
+            pos<typename P::Fc>([&](int, int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
+            for (int g = 0; g < P::NQG; ++g)
+                pos<typename P::Qkv>([&](int, int co, int ci, int) { return b.qkv_w[(g * 3 * C::HD * P::HG + co) * C2 + ci]; });
+            pos<typename P::Fc>([&](int, int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
+        }
+        row<typename P::LinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+        pos<typename P::RfPost>([&](int, int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
+        for (int i = 0; i < C::E; ++i) {
+            pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });
+            pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; });
+        }
+        pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; });
+        // transposed conv as a 3-tap conv to 8 virtual output channels vo = o*4 + q (bin 4m + q):
+        // original tap k = -4*dj + q + 2 (model.py:62-95)
+        pos<typename P::ConvT>([&](int, int vo, int ci, int t) {
+            int o = vo / 4, q = vo % 4, k = -4 * (t - 1) + q + 2;
+            return (k >= 0 && k < 8) ? cw.dp_wt[(ci * 2 + o) * 8 + k] : 0.f;
+        });
+        if (off_ != A.total || (int)table_.size() != 2 * P::NCHUNK_FRAME) throw std::runtime_error("fe_pack: schedule mismatch");
+        std::memcpy(&blob_[A.table], table_.data(), table_.size() * sizeof(int));
+    }
+};
+
+template <class P> std::vector<float> pack_blob(const float* canonical) {
+    std::vector<float> blob;
+    Packer<P>(blob).pack(canonical);
+    return blob;
+}
+
+}  // namespace fe

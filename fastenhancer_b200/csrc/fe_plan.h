@@ -1,0 +1,271 @@
+// fe_plan.h -- compile-time shape, tile, shared-memory and weight-stream plan of the fused per-hop kernel.
+//
+// One `Cfg` per shipped FastEnhancer configuration (reference YAMLs:
+// configs/fastenhancer/{t,b,s,m,l}.yaml:1-29, configs/fastenhancer_48khz/*.yaml:1-29) and one
+// `Plan<Cfg, S>` per (configuration, streams-per-CTA).  The device kernel (fe_kernel.cuh), the
+// host-side weight packer (fe_pack.h) and the CPU emulation build used by the tests
+// (tests/emu/fe_emu.cpp) are all instantiated from the same Plan, so the packed layout has a single
+// source of truth.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FE_HD __host__ __device__
+#else
+#define FE_HD
+#endif
+
+namespace fe {
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+constexpr int pow2ceil(int a) { int p = 1; while (p < a) p <<= 1; return p; }
+
+// ----------------------------------------------------------------------------------------------
+// Model shape (SURVEY.md section 8 notation).  kernel_size = [8, 3 x E], stride 4, 4 heads, SiLU.
+// ----------------------------------------------------------------------------------------------
+template <int N_FFT_, int HOP_, int C1_, int E_, int C2_, int F2_, int K_, int NH_ = 4>
+struct Cfg {
+    static constexpr int N_FFT = N_FFT_, HOP = HOP_, C1 = C1_, E = E_, C2 = C2_, F2 = F2_, K = K_, NH = NH_;
+    static constexpr int FIN = N_FFT / 2;      // bins kept (Nyquist dropped)
+    static constexpr int NB = FIN + 1;         // bins of the rFFT
+    static constexpr int F1 = FIN / 4;         // encoder frequency positions
+    static constexpr int HD = C2 / NH;         // attention head dim
+    static constexpr int CL = N_FFT - HOP;     // overlap / cache length
+    static constexpr int M = N_FFT / 2;        // complex FFT size of the packed real FFT
+    static constexpr int HS = K * F2 * C2;     // floats of GRU state per stream
+    static constexpr int STATE = 2 * CL + HS;  // floats of state per stream
+    static_assert(C2 % NH == 0, "heads");
+    static_assert((N_FFT & (N_FFT - 1)) == 0, "n_fft must be a power of two");
+    static_assert(F2 % 4 == 0 && F1 % 4 == 0, "frequency axes must be multiples of 4");
+};
+
+// Number of floats of the canonical folded weight array (include/fastenhancer_b200.h).
+template <class C> constexpr long canonical_floats() {
+    long n = 0;
+    n += C::C1 * 16 + C::C1;
+    n += (long)C::E * (C::C1 * C::C1 * 3 + C::C1);
+    n += C::F2 * C::F1 + C::C2 * C::C1 + C::C2;
+    n += (long)C::K * (2 * 3 * C::C2 * C::C2 + 2 * 3 * C::C2 + C::C2 * C::C2 + C::C2 + 3 * C::C2 * C::C2 + 3 * C::C2 + C::C2 * C::C2 + C::C2);
+    n += C::F2 * C::C2;
+    n += C::F1 * C::F2 + C::C1 * C::C2 + C::C1;
+    n += (long)C::E * (C::C1 * 2 * C::C1 + C::C1 + C::C1 * C::C1 * 3 + C::C1);
+    n += C::C1 * 2 * C::C1 + C::C1 + C::C1 * 16 + 2;
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------------
+// "Position GEMM": Y[co][p] = sum_{k, tap} W[co][k][tap] * X[k][p + tap - TAPS/2], activations
+// channel-major in shared memory with the positions contiguous.  A warp owns a tile of
+// (PL*PT positions) x (CL*CT output channels): lane = cl*PL + pl, each lane PT consecutive
+// positions x CT channels in registers.  Weights arrive through the shared-memory ring as rows
+//     row k of pass p : [cgp][cl][RW],  RW = round_up(SETS*TAPS*CT, 4),  entry [set][tap][i]
+// so a lane reads RW contiguous floats per k (float4 loads, broadcast across the pl lanes).
+// SETS = 6 is the fused GRU tile (W_ir, W_iz, W_in, W_hr, W_hz, W_hn).
+// If the layer has more tiles than warps it runs in NPASS passes; the stream is pass-major.
+// ----------------------------------------------------------------------------------------------
+template <int NPOS_, int F_, int COUT_, int K_, int TAPS_, int PT_, int CTMAX_, int NW_, int CHUNK_, int SETS_ = 1>
+struct PosGemm {
+    static constexpr int NPOS = NPOS_, F = F_, COUT = COUT_, K = K_, TAPS = TAPS_, PT = PT_, NW = NW_, SETS = SETS_;
+    static_assert(F % PT == 0, "a thread's positions must not straddle streams");
+    static constexpr int PL = cmin(32, pow2ceil(cdiv(NPOS, PT)));
+    static constexpr int CL = 32 / PL;
+    static constexpr int NPG = pow2ceil(cdiv(NPOS, PL * PT));
+    static_assert(NPG <= NW, "too many positions for one pass: lower S");
+    static constexpr int NCGP = NW / NPG;                       // channel groups per pass
+    static constexpr int CT = cmax(1, cmin(CTMAX_, cdiv(COUT, CL * NCGP)));
+    static constexpr int NCG = cdiv(COUT, CL * CT);
+    static constexpr int NPASS = cdiv(NCG, NCGP);
+    static constexpr int RW = round_up(SETS * TAPS * CT, 4);
+    static constexpr int ROW = NCGP * CL * RW;                  // floats per k row of one pass
+    static_assert(ROW <= CHUNK_, "one weight row must fit a ring chunk");
+    static constexpr int KC = cmax(1, cmin(K, CHUNK_ / ROW));   // rows per chunk
+    static constexpr int NCHUNK_PASS = cdiv(K, KC);
+    static constexpr int NCHUNK = NPASS * NCHUNK_PASS;
+    static constexpr int FLOATS = NPASS * K * ROW;
+};
+
+// ----------------------------------------------------------------------------------------------
+// "Row GEMM": Y[r][o] = sum_k W[o][k] * X[r][k] with k the contiguous axis of X (the two
+// frequency-axis linears rf_pre.0 / rf_post.0).  Lanes own rows (row pitch = 4*odd floats, so the
+// float4 loads of 8 consecutive lanes hit 8 distinct bank groups), a warp owns NO outputs.
+// Ring rows: one per 4 k's: [og][NO][4].
+// ----------------------------------------------------------------------------------------------
+template <int NROWS_, int K_, int NOUT_, int NW_, int CHUNK_>
+struct RowGemm {
+    static constexpr int NROWS = NROWS_, K = K_, NOUT = NOUT_, NW = NW_;
+    static_assert(K % 4 == 0, "contraction axis must be a multiple of 4");
+    static constexpr int RT = cdiv(NROWS, 32);
+    static constexpr int NO = round_up(cdiv(NOUT, NW), 4);
+    static constexpr int NOG = cdiv(NOUT, NO);
+    static_assert(NOG <= NW && RT * NO <= 64, "row gemm tile too large: lower S");
+    static constexpr int K4 = K / 4;
+    static constexpr int ROW = NOG * NO * 4;
+    static_assert(ROW <= CHUNK_, "one weight row must fit a ring chunk");
+    static constexpr int KC = cmax(1, cmin(K4, CHUNK_ / ROW));
+    static constexpr int NCHUNK = cdiv(K4, KC);
+    static constexpr int FLOATS = K4 * ROW;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Per-(config, S) tuning.  Primary template = generic heuristics; specialise to override.
+// ----------------------------------------------------------------------------------------------
+template <class C, int S> struct Tune {
+    static constexpr int NW = 8;                      // consumer warps (one more warp streams weights)
+    static constexpr int CHUNK = 4096;                // floats per ring chunk
+    static constexpr int STAGES = 3;
+    static constexpr int CT_CONV = 16;                // max output channels per lane, conv / 1x1 layers
+    static constexpr int CT_RF = 8;                   // ... RNNFormer linears
+    static constexpr int PT_GRU = 2, CT_GRU = 6;      // GRU tile: 4 accumulators per (channel, position)
+    // heads per attention round: the largest that fits the work region (see Plan static_asserts)
+    static constexpr int HG = (C::C1 >= 96) ? 1 : C::NH;
+    // upper bound on skip tensors kept in shared memory (the rest round-trip through L2);
+    // the Plan lowers it to what fits in 227 KB
+    static constexpr int SKIP_SMEM_MAX = C::E + 1;
+};
+
+template <class C, int S_>
+struct Plan {
+    using Cf = C;
+    static constexpr int S = S_;
+    using T = Tune<C, S_>;
+    static constexpr int NW = T::NW, NT = NW * 32, NTHREADS = NT + 32;
+    static constexpr int CHUNK = T::CHUNK, STAGES = T::STAGES;
+    // ---- conv geometry ("Geo1"): [C1][S][P1], data at column 4, zero columns 0..3; the 4 zero
+    //      columns of the next row are the right halo, +4 floats after the very last row ----
+    static constexpr int P1 = C::F1 + 4;
+    static constexpr int CP1 = S * P1;                 // channel pitch
+    static constexpr int ACT = C::C1 * CP1 + 4;
+    static constexpr int SPECF = 8 * CP1 + 4;          // compressed spectrum as 8 virtual channels (c*4+q)
+    // ---- RNNFormer geometry: [C2][S][F2P] channel-major, F2P = 4*odd ----
+    static constexpr int F2P = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
+    static constexpr int PR = S * F2P;
+    static constexpr int XRS = C::C2 * PR;
+    static constexpr int HG = T::HG, NQG = C::NH / HG;
+    static_assert(C::NH % HG == 0, "HG must divide NH");
+    static constexpr int QKVS = 3 * C::HD * HG * PR;
+    // work region AB = [W0 | W1 (| W2)]; RNNFormer: XR at the tail, ATT/HB at 0, G/QKV at XRS.
+    // W2 exists only when the RNNFormer scratch needs the room (16 kHz L).
+    static constexpr int NWORK = (2 * XRS + cmax(XRS, QKVS) > 2 * ACT) ? 3 : 2;
+    static constexpr int AB = NWORK * ACT;
+    static constexpr int O_XR = AB - XRS;
+    static constexpr int O_HB = 0, O_ATT = 0, O_G = XRS, O_QKV = XRS;
+    static constexpr int O_Y1 = 0;                     // rf_pre linear output [C1][PR]
+    static constexpr int O_Z = 0;                      // rf_post linear output [C2][S][P1]
+    static_assert(XRS + cmax(XRS, QKVS) <= O_XR, "RNNFormer scratch does not fit: lower Tune::HG");
+    static_assert(C::C1 * PR <= O_XR && C::C1 * PR <= ACT, "rf_pre scratch does not fit");
+    static_assert(C::C2 * CP1 <= O_XR, "rf_post scratch does not fit");
+    static_assert(S * C::N_FFT <= ACT, "FFT buffers do not fit");
+    // ---- shared memory map (float offsets) ----
+    static constexpr int NSK = C::E + 1;
+    static constexpr int SM_FIXED = AB + SPECF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES;
+    static_assert(SM_FIXED <= 227 * 256, "shared memory plan exceeds 227 KB even with every skip tensor spilled");
+    static constexpr int SKIP_SMEM = cmax(0, cmin(cmin(NSK, T::SKIP_SMEM_MAX), (227 * 256 - SM_FIXED) / ACT));
+    static constexpr int SM_SK = 0;
+    static constexpr int SM_W = SM_SK + SKIP_SMEM * ACT;
+    static constexpr int SM_SPEC = SM_W + AB;
+    static constexpr int SM_TIN = SM_SPEC + SPECF;             // last N input samples per stream (circular)
+    static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
+    static constexpr int SM_RING = SM_OLA + S * C::N_FFT;
+    static constexpr int SM_BAR = SM_RING + STAGES * CHUNK;    // 2*STAGES mbarriers (8 bytes each)
+    static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES;
+    static_assert(SM_RING % 4 == 0 && SM_BAR % 2 == 0, "alignment");
+    static constexpr int SMEM_BYTES = SM_TOTAL * 4;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
+    // global scratch per CTA: spilled skip tensors
+    static constexpr int GS_TOTAL = (NSK - SKIP_SMEM) * ACT + 4;
+
+    // ---- layers (weight-stream order) ----
+    using EncPre = PosGemm<S * C::F1, C::F1, C::C1, 8, 3, 4, T::CT_CONV, NW, CHUNK>;
+    using Conv3 = PosGemm<S * C::F1, C::F1, C::C1, C::C1, 3, 4, T::CT_CONV, NW, CHUNK>;
+    using PwCat = PosGemm<S * C::F1, C::F1, C::C1, 2 * C::C1, 1, 4, T::CT_CONV, NW, CHUNK>;
+    using ConvT = PosGemm<S * C::F1, C::F1, 8, C::C1, 3, 4, 1, NW, CHUNK>;
+    using LinPre = RowGemm<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
+    using RfPre = PosGemm<S * C::F2, C::F2, C::C2, C::C1, 1, 4, T::CT_RF, NW, CHUNK>;
+    using Gru = PosGemm<S * C::F2, C::F2, C::C2, C::C2, 1, T::PT_GRU, T::CT_GRU, NW, CHUNK, 6>;
+    using Fc = PosGemm<S * C::F2, C::F2, C::C2, C::C2, 1, 4, T::CT_RF, NW, CHUNK>;
+    using Qkv = PosGemm<S * C::F2, C::F2, 3 * C::HD * HG, C::C2, 1, 4, T::CT_RF, NW, CHUNK>;
+    using LinPost = RowGemm<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
+    using RfPost = PosGemm<S * C::F1, C::F1, C::C1, C::C2, 1, 4, T::CT_CONV, NW, CHUNK>;
+    static_assert(PwCat::NPASS == 1, "the concatenating 1x1 conv stores in place after a barrier: one pass only");
+
+    static constexpr int BLK_CHUNKS = Gru::NCHUNK + 2 * Fc::NCHUNK + NQG * Qkv::NCHUNK;
+    static constexpr int NCHUNK_FRAME = EncPre::NCHUNK + C::E * Conv3::NCHUNK + LinPre::NCHUNK + RfPre::NCHUNK +
+                                        C::K * BLK_CHUNKS + LinPost::NCHUNK + RfPost::NCHUNK +
+                                        C::E * (PwCat::NCHUNK + Conv3::NCHUNK) + PwCat::NCHUNK + ConvT::NCHUNK;
+    static constexpr long RING_FLOATS = (long)EncPre::FLOATS + (long)C::E * Conv3::FLOATS + LinPre::FLOATS + RfPre::FLOATS +
+                                        (long)C::K * (Gru::FLOATS + 2 * Fc::FLOATS + NQG * Qkv::FLOATS) + LinPost::FLOATS +
+                                        RfPost::FLOATS + (long)C::E * (PwCat::FLOATS + Conv3::FLOATS) + PwCat::FLOATS + ConvT::FLOATS;
+
+    // ---- blob layout (float offsets): [aux tables + biases | chunk table | ring section] ----
+    // Per-layer arrays are affine (base + index * stride) so that device code never indexes a
+    // constexpr array at run time (which would materialise the table on the stack).
+    struct Blk { int b_r, b_z, b_in, b_hn, fc_b, pe, qkv_b, afc_b; };
+    struct Aux {
+        int window, window_istft, window_sq;   // [N] each
+        int tw, twn;                           // float2[M/2] : exp(-2 pi i t / M) ; float2[M] : exp(-2 pi i k / N)
+        int enc_pre_b, enc_b0, enc_bs;         // encoder[i] bias at enc_b0 + i*enc_bs
+        int rf_pre_b;
+        int blk0, blks;                        // block k at blk0 + k*blks + rel.*
+        Blk rel;
+        int rf_post_b;
+        int dec_b0, dec_bs, dec2_rel;          // decoder[i]: 1x1 bias at dec_b0 + i*dec_bs, k=3 bias dec2_rel after it
+        int dp_b, convt_b;
+        int table;                             // int32[2*NCHUNK_FRAME] : (float offset from blob start, floats)
+        int ring;                              // start of the ring section
+        int total;
+        constexpr int enc_b(int i) const { return enc_b0 + i * enc_bs; }
+        constexpr int dec1_b(int i) const { return dec_b0 + i * dec_bs; }
+        constexpr int dec2_b(int i) const { return dec_b0 + i * dec_bs + dec2_rel; }
+        constexpr Blk blk(int k) const {
+            const int o = blk0 + k * blks;
+            return Blk{o + rel.b_r, o + rel.b_z, o + rel.b_in, o + rel.b_hn, o + rel.fc_b, o + rel.pe, o + rel.qkv_b, o + rel.afc_b};
+        }
+    };
+    static constexpr Aux make_aux() {
+        Aux a{};
+        int o = 0;
+        auto take = [&o](int n) { int r = o; o += round_up(n, 4); return r; };
+        a.window = take(C::N_FFT); a.window_istft = take(C::N_FFT); a.window_sq = take(C::N_FFT);
+        a.tw = take(C::M); a.twn = take(2 * C::M);
+        a.enc_pre_b = take(C::C1);
+        a.enc_bs = round_up(C::C1, 4); a.enc_b0 = take(C::E * a.enc_bs);
+        a.rf_pre_b = take(C::C2);
+        {
+            int r = 0;
+            auto rel = [&r](int n) { int q = r; r += round_up(n, 4); return q; };
+            a.rel.b_r = rel(C::C2); a.rel.b_z = rel(C::C2); a.rel.b_in = rel(C::C2); a.rel.b_hn = rel(C::C2);
+            a.rel.fc_b = rel(C::C2); a.rel.pe = rel(C::C2 * C::F2); a.rel.qkv_b = rel(3 * C::C2); a.rel.afc_b = rel(C::C2);
+            a.blks = r; a.blk0 = take(C::K * r);
+        }
+        a.rf_post_b = take(C::C1);
+        a.dec2_rel = round_up(C::C1, 4); a.dec_bs = 2 * a.dec2_rel; a.dec_b0 = take(C::E * a.dec_bs);
+        a.dp_b = take(C::C1); a.convt_b = take(8);
+        a.table = take(2 * NCHUNK_FRAME);
+        a.ring = o;
+        a.total = o + (int)RING_FLOATS;
+        return a;
+    }
+};
+
+// kernel parameters (plain data, passed by value)
+struct KParams {
+    const float* blob;        // packed weights + tables (device)
+    float* state;             // [n_streams][STATE] native layout: cache_stft | cache_istft | h[K][C2][F2]
+    const float* in;          // mode 0: wav [n_streams][ld_in]; mode 1: spec [B][NB][T][2]; mode 2: wav [B][L]
+    float* out;               // mode 0: wav [n_streams][ld_out]; mode 1: spec [B][NB][T][2]; mode 2: wav [B][H*(T-1)]
+    float* spec_out;          // mode 2 (optional): compressed masked spectrum [B][FIN][T][2]
+    float* scratch;           // global scratch [grid][GS_TOTAL]
+    float* dbg;               // optional tap dump of stream 0 (oracle tap layout), frame `dbg_hop`
+    long long ld_in, ld_out;
+    int n_streams, n_hops;    // n_hops = T frames in modes 1, 2
+    int mode, L, dbg_hop;
+    float compression;
+};
+
+enum { MODE_STREAM = 0, MODE_SPEC = 1, MODE_OFFLINE = 2 };
+
+}  // namespace fe

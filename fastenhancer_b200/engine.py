@@ -1,0 +1,242 @@
+"""ctypes binding of the C ABI (include/fastenhancer_b200.h) -- the only route to the CUDA engine.
+
+PyTorch is used for device memory and streams only (tensors are passed as raw device pointers).
+There is no CPU path: if the shared library cannot be loaded, or no B200 is visible, construction
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import typing as tp
+
+import numpy as np
+
+from .config import FEConfig
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfastenhancer_b200.so")
+_lib = None
+
+#: every symbol include/fastenhancer_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = (
+    "fe_last_error", "fe_weight_count", "fe_state_floats", "fe_create", "fe_destroy", "fe_state_create",
+    "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
+    "fe_spec", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
+    "fe_stream_taps",
+)
+
+
+class CConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("n_fft", "hop", "c1", "n_enc", "c2", "f2", "n_blocks", "n_heads")] + \
+        [("compression", ctypes.c_float)]
+
+    @classmethod
+    def from_cfg(cls, cfg: FEConfig) -> "CConfig":
+        return cls(cfg.n_fft, cfg.hop_size, cfg.channels, cfg.n_enc, cfg.rf_channels, cfg.rf_freq, cfg.rf_blocks,
+                   cfg.rf_heads, cfg.input_compression)
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen the in-tree engine library and declare the C ABI's signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{_LIB_PATH} is missing: run `python -m fastenhancer_b200.build`")
+        from .build import build
+        build()
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, ip, ll, fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p   # fp: raw float* (host or device)
+    cfgp = ctypes.POINTER(CConfig)
+    lib.fe_last_error.restype = ctypes.c_char_p
+    lib.fe_weight_count.restype = ctypes.c_size_t
+    lib.fe_weight_count.argtypes = [cfgp]
+    lib.fe_state_floats.restype = ctypes.c_size_t
+    lib.fe_state_floats.argtypes = [cfgp]
+    lib.fe_create.argtypes = [cfgp, fp, ctypes.c_size_t, ip, ctypes.POINTER(vp)]
+    lib.fe_destroy.argtypes = [vp]
+    lib.fe_destroy.restype = None
+    lib.fe_state_create.argtypes = [vp, ip, ctypes.POINTER(vp)]
+    lib.fe_state_destroy.argtypes = [vp]
+    lib.fe_state_destroy.restype = None
+    lib.fe_state_reset.argtypes = [vp, vp]
+    lib.fe_state_export.argtypes = [vp, fp, vp]
+    lib.fe_state_import.argtypes = [vp, fp, vp]
+    lib.fe_stream.argtypes = [vp, vp, fp, fp, ip, ll, ll, vp]
+    lib.fe_stream_host.argtypes = [vp, vp, fp, fp, ip, ll, ll, ip]
+    lib.fe_spec.argtypes = [vp, vp, fp, fp, ip, vp]
+    lib.fe_offline.argtypes = [vp, fp, ip, ip, fp, fp, vp]
+    lib.fe_streams_per_cta.argtypes = [vp, ip]
+    lib.fe_set_streams_per_cta.argtypes = [vp, ip]
+    lib.fe_kernel_launches.argtypes = [vp]
+    lib.fe_kernel_launches.restype = ll
+    lib.fe_tap_floats.argtypes = [vp]
+    lib.fe_stream_taps.argtypes = [vp, vp, fp, fp, ip, ll, ll, fp, ip, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().fe_last_error()
+        raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def _stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class State:
+    """Recurrent (GRU h per block) + overlap (STFT / iSTFT caches) state of ``n_streams`` streams, on device."""
+
+    def __init__(self, engine: "Engine", n_streams: int):
+        self.engine, self.n_streams = engine, int(n_streams)
+        h = ctypes.c_void_p()
+        _check(engine._lib.fe_state_create(engine._h, self.n_streams, ctypes.byref(h)), "fe_state_create")
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.engine._lib.fe_state_destroy(self._h)
+            self._h = None
+
+    def reset(self) -> None:
+        _check(self.engine._lib.fe_state_reset(self._h, _stream_ptr()), "fe_state_reset")
+
+    def export(self):
+        """-> float32 cuda tensor [n_streams, state_floats] in the reference cache layout
+        [cache_stft | cache_istft | h_0 [F2][C2] | ...]."""
+        import torch
+        out = torch.empty(self.n_streams, self.engine.state_floats, dtype=torch.float32, device=self.engine.device)
+        _check(self.engine._lib.fe_state_export(self._h, out.data_ptr(), _stream_ptr()), "fe_state_export")
+        return out
+
+    def load(self, t) -> None:
+        t = self.engine._dev(t, (self.n_streams, self.engine.state_floats))
+        _check(self.engine._lib.fe_state_import(self._h, t.data_ptr(), _stream_ptr()), "fe_state_import")
+
+
+class Engine:
+    """One folded FastEnhancer model resident on one B200."""
+
+    def __init__(self, cfg: FEConfig, canonical: np.ndarray, device: tp.Union[int, str, None] = None):
+        import torch
+        cfg.validate()
+        if not torch.cuda.is_available():
+            raise RuntimeError("fastenhancer_b200: no CUDA device visible; the engine has no CPU fallback")
+        self._lib = load_library()
+        self.cfg = cfg
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"fastenhancer_b200: device must be a CUDA device, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        canonical = np.ascontiguousarray(canonical, dtype=np.float32)
+        self._c = CConfig.from_cfg(cfg)
+        need = self._lib.fe_weight_count(ctypes.byref(self._c))
+        if canonical.size != need:
+            raise ValueError(f"canonical weights: got {canonical.size} floats, need {need}")
+        h = ctypes.c_void_p()
+        _check(self._lib.fe_create(ctypes.byref(self._c), canonical.ctypes.data, canonical.size, self.device.index,
+                                   ctypes.byref(h)), "fe_create")
+        self._h = h
+        self.state_floats = int(self._lib.fe_state_floats(ctypes.byref(self._c)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.fe_destroy(self._h)
+            self._h = None
+
+    # ---- helpers ----
+    def _dev(self, t, shape=None):
+        import torch
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def new_state(self, n_streams: int) -> State:
+        return State(self, n_streams)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.fe_kernel_launches(self._h))
+
+    def streams_per_cta(self, n_streams: int) -> int:
+        return int(self._lib.fe_streams_per_cta(self._h, int(n_streams)))
+
+    def set_streams_per_cta(self, s: int) -> None:
+        _check(self._lib.fe_set_streams_per_cta(self._h, int(s)), "fe_set_streams_per_cta")
+
+    # ---- the hot path ----
+    def stream(self, state: State, wav_in, out=None):
+        """``n_hops`` streaming steps for every stream: wav_in [B, n_hops*hop] (cuda) -> wav_out, one launch."""
+        import torch
+        x = self._dev(wav_in)
+        B, L = x.shape
+        H = self.cfg.hop_size
+        if B != state.n_streams or L % H:
+            raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty_like(x)
+        _check(self._lib.fe_stream(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), out.stride(0),
+                                   _stream_ptr()), "fe_stream")
+        return out
+
+    def stream_taps(self, state: State, wav_in, tap_hop: int):
+        import torch
+        x = self._dev(wav_in)
+        B, L = x.shape
+        H = self.cfg.hop_size
+        out = torch.empty_like(x)
+        taps = torch.zeros(int(self._lib.fe_tap_floats(self._h)), dtype=torch.float32, device=self.device)
+        _check(self._lib.fe_stream_taps(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), out.stride(0),
+                                        taps.data_ptr(), int(tap_hop), _stream_ptr()), "fe_stream_taps")
+        return out, taps
+
+    def stream_host(self, state: State, wav_in, out=None, hops_per_chunk: int = 0):
+        """Same as :meth:`stream` for HOST tensors (pinned preferred); copies are pipelined with the kernel."""
+        import torch
+        if wav_in.device.type != "cpu" or wav_in.dtype != torch.float32 or wav_in.stride(1) != 1:
+            raise ValueError("stream_host takes a float32 CPU tensor with contiguous rows")
+        B, L = wav_in.shape
+        H = self.cfg.hop_size
+        if B != state.n_streams or L % H:
+            raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(wav_in.shape)}")
+        if out is None:
+            out = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        _check(self._lib.fe_stream_host(self._h, state._h, wav_in.data_ptr(), out.data_ptr(), L // H, wav_in.stride(0),
+                                        out.stride(0), int(hops_per_chunk)), "fe_stream_host")
+        return out
+
+    def spec(self, state: State, spec_in, out=None):
+        """ONNXModel.forward on [B, n_fft/2+1, T, 2] spectra (GRU state in ``state``)."""
+        import torch
+        x = self._dev(spec_in)
+        B, NB, T, two = x.shape
+        if B != state.n_streams or NB != self.cfg.n_fft // 2 + 1 or two != 2:
+            raise ValueError(f"bad spectrum shape {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty_like(x)
+        _check(self._lib.fe_spec(self._h, state._h, x.data_ptr(), out.data_ptr(), T, _stream_ptr()), "fe_spec")
+        return out
+
+    def offline(self, wav, want_spec: bool = True):
+        """Model.forward: wav [B, L] -> (wav_hat [B, hop*(L//hop)], spec_hat [B, n_fft/2, 1+L//hop, 2] or None)."""
+        import torch
+        x = self._dev(wav)
+        B, L = x.shape
+        H = self.cfg.hop_size
+        T = 1 + L // H
+        out = torch.empty((B, H * (T - 1)), dtype=torch.float32, device=self.device)
+        spec = torch.empty((B, self.cfg.f_in, T, 2), dtype=torch.float32, device=self.device) if want_spec else None
+        _check(self._lib.fe_offline(self._h, x.data_ptr(), B, L, out.data_ptr(), spec.data_ptr() if want_spec else None,
+                                    _stream_ptr()), "fe_offline")
+        return out, spec

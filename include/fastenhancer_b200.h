@@ -1,0 +1,102 @@
+/*
+ * fastenhancer_b200.h -- C ABI of the B200-native FastEnhancer streaming engine.
+ *
+ * The reference (aask1357/fastenhancer) has no native ABI: its hot path is Python/PyTorch
+ * (models/fastenhancer/default/model.py, functional/audio_modules.py) and its streaming boundary is
+ * the ONNX graph of scripts/export_onnx.py:48-58 driven hop by hop from scripts/test_onnx.py:44-49.
+ * Each entry point below names the reference interface it replaces.  Plain pointers and sizes
+ * only; all `device` pointers are CUDA device memory of the engine's device, `cuda_stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Every function returns 0 on success and a negative code on failure; fe_last_error() returns a
+ * thread-local description.  One engine per device; calls on one engine are serialised per CUDA
+ * stream by the caller; distinct engines are independent (no global state).
+ */
+#ifndef FASTENHANCER_B200_H
+#define FASTENHANCER_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Shape of one FastEnhancer model: the `model_kwargs` block of the reference YAMLs
+ * (configs/fastenhancer/b.yaml:1-29) reduced to what the hot path needs. */
+typedef struct fe_config {
+    int n_fft, hop;         /* STFT: n_fft == win_size, hop_size */
+    int c1, n_enc;          /* encoder channels, number of k=3 encoder blocks (len(kernel_size) - 1) */
+    int c2, f2;             /* rnnformer channels / freq */
+    int n_blocks, n_heads;  /* rnnformer num_blocks / num_heads */
+    float compression;      /* input_compression (0.3) */
+} fe_config;
+
+typedef struct fe_engine fe_engine;   /* weights + kernels of one model on one device */
+typedef struct fe_state fe_state;     /* recurrent + overlap state of n_streams independent streams */
+
+enum {
+    FE_OK = 0,
+    FE_ERR_ARG = -1,          /* bad argument */
+    FE_ERR_UNSUPPORTED = -2,  /* model shape not among the shipped FastEnhancer configurations */
+    FE_ERR_CUDA = -3,         /* CUDA runtime error (see fe_last_error) */
+    FE_ERR_NO_DEVICE = -4     /* no CUDA device: there is no CPU fallback */
+};
+
+const char* fe_last_error(void);
+
+/* Number of floats of the canonical folded weight array / of the per-stream state for `cfg`.
+ * Canonical order = what ONNXModel.remove_weight_reparameterizations leaves behind
+ * (model.py:532-608), flattened as fastenhancer_b200/schema.py::canonical_schema lists it. */
+size_t fe_weight_count(const fe_config* cfg);
+size_t fe_state_floats(const fe_config* cfg);   /* 2*(n_fft-hop) + n_blocks*f2*c2 */
+
+/* Replaces: building ONNXModel(**model_kwargs) + load_state_dict + remove_weight_reparameterizations
+ * (scripts/export_onnx.py:60-78).  `canonical` is HOST memory, copied. */
+int fe_create(const fe_config* cfg, const float* canonical, size_t n_floats, int device, fe_engine** out);
+void fe_destroy(fe_engine* e);
+
+/* Replaces: ONNXSTFT.initialize_cache + ONNXModel.initialize_cache (audio_modules.py:238-241,
+ * model.py:614-618): zeroed cache_stft [n, n_fft-hop], cache_istft [n, n_fft-hop], h_k [n*f2, c2] x K. */
+int fe_state_create(fe_engine* e, int n_streams, fe_state** out);
+void fe_state_destroy(fe_state* s);
+int fe_state_reset(fe_state* s, void* cuda_stream);
+/* Reference cache layout per stream: [cache_stft | cache_istft | h_0 [f2][c2] | ... | h_{K-1}], so ORT-style
+ * callers that round-trip `cache_in_* / cache_out_*` tensors (scripts/test_onnx.py:34-49) still can. */
+int fe_state_export(fe_state* s, float* dst_device, void* cuda_stream);
+int fe_state_import(fe_state* s, const float* src_device, void* cuda_stream);
+
+/* Replaces: `n_hops` iterations of the streaming graph export_onnx.Model.forward
+ * (scripts/export_onnx.py:48-58; loop at scripts/test_onnx.py:44-49) for n_streams independent streams.
+ * wav_in / wav_out: device, [n_streams][ld] floats, the first n_hops*hop columns are read / written.
+ * Output sample n of hop i is input time i*hop + n - (n_fft - hop) (docs/docs/onnx.md:37-72).
+ * One persistent kernel launch; state stays on chip between the hops of the call. */
+int fe_stream(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops,
+              long long ld_in, long long ld_out, void* cuda_stream);
+
+/* Same, HOST buffers (pinned or pageable): host->device copy, kernel and device->host copy are pipelined in
+ * `hops_per_chunk`-hop pieces (0 = default).  This is the end-to-end path bench.py times as `e2e`. */
+int fe_stream_host(fe_engine* e, fe_state* s, const float* wav_in_host, float* wav_out_host, int n_hops,
+                   long long ld_in, long long ld_out, int hops_per_chunk);
+
+/* Replaces: ONNXModel.forward(spec_noisy, *h) (model.py:677-710; the spec2spec graph of
+ * scripts/export_onnx_spec.py:135-142).  spec_in / spec_out: device, [n_streams][n_fft/2+1][T][2]. */
+int fe_spec(fe_engine* e, fe_state* s, const float* spec_in, float* spec_out, int T, void* cuda_stream);
+
+/* Replaces: Model.forward(noisy) (model.py:728-735): wav [B][L] -> wav_out [B][hop*(L/hop)] and (optional)
+ * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
+int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
+
+/* Introspection used by the host wrapper, tests and bench. */
+int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
+int fe_set_streams_per_cta(fe_engine* e, int s);                /* force a variant (0 = automatic) */
+long long fe_kernel_launches(fe_engine* e);                     /* fused-kernel launches issued so far */
+int fe_tap_floats(fe_engine* e);
+/* Test hook: like fe_stream, additionally dumps the per-stage tensors of stream 0 at hop `tap_hop`
+ * (layout of oracle/fe_oracle.c::core) into taps_device [fe_tap_floats]. */
+int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops,
+                   long long ld_in, long long ld_out, float* taps_device, int tap_hop, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTENHANCER_B200_H */

@@ -1,0 +1,85 @@
+// fe_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host build (-DFE_EMU) of the fused kernel body: every barrier-separated phase of
+// fastenhancer_b200/csrc/fe_kernel.cuh runs as `for tid in 0..NT`, CTAs run one after another and
+// the weight ring is read straight from the packed blob.  It checks the packer, the tile / layout
+// index math and the buffer aliasing plan against the oracle on the build container (no GPU).
+// It is never linked into the product library.
+#define FE_EMU 1
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../fastenhancer_b200/csrc/fe_configs.h"
+#include "../../fastenhancer_b200/csrc/fe_kernel.cuh"
+#include "../../fastenhancer_b200/csrc/fe_pack.h"
+
+namespace fe {
+
+template <class P> struct EmuCtx {
+    float* sm; const float* blob; KParams prm; int s0; float* gs; int cta;
+    long frames_done = 0;
+    const int* table;
+    const float* acquire(int ci, int expect_floats) const {
+        if (ci < 0 || ci >= P::NCHUNK_FRAME) throw std::runtime_error("emu: chunk index out of range");
+        if (table[2 * ci + 1] != expect_floats) throw std::runtime_error("emu: chunk size mismatch at chunk " + std::to_string(ci));
+        return blob + table[2 * ci];
+    }
+    void release(int) const {}
+    template <class F> void phase(F&& f) { for (int t = 0; t < P::NT; ++t) f(t); }
+    template <class A, class F1, class F2> void phase2(F1&& f1, F2&& f2) {
+        std::vector<A> acc(P::NT);
+        for (int t = 0; t < P::NT; ++t) f1(t, acc[t]);
+        for (int t = 0; t < P::NT; ++t) f2(t, acc[t]);
+    }
+    void next_frame() { ++frames_done; }
+    void check_frame(int ci) const { if (ci != P::NCHUNK_FRAME) throw std::runtime_error("emu: frame consumed wrong number of chunks"); }
+};
+
+template <class P> int run_variant(const float* canonical, KParams prm) {
+    std::vector<float> blob = pack_blob<P>(canonical);
+    constexpr auto A = P::make_aux();
+    int grid = (prm.n_streams + P::S - 1) / P::S;
+    std::vector<float> sm(P::SM_TOTAL), gs((size_t)P::GS_TOTAL);
+    for (int cta = 0; cta < grid; ++cta) {
+        // poison shared memory so that reads of never-written locations show up
+        for (auto& v : sm) v = std::nanf("");
+        EmuCtx<P> x;
+        x.sm = sm.data(); x.blob = blob.data(); x.prm = prm; x.prm.blob = blob.data();
+        x.s0 = cta * P::S; x.gs = gs.data(); x.cta = cta;
+        x.table = reinterpret_cast<const int*>(blob.data() + A.table);
+        Frame<P>::run(x);
+    }
+    return 0;
+}
+
+}  // namespace fe
+
+extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S,
+                       const float* canonical, int mode, float* state, const float* in, float* out, float* spec_out,
+                       int n_streams, int n_hops, int L, long long ld_in, long long ld_out, float* dbg, int dbg_hop,
+                       float compression)
+{
+    fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
+    fe::KParams prm{};
+    prm.state = state; prm.in = in; prm.out = out; prm.spec_out = spec_out; prm.dbg = dbg;
+    prm.ld_in = ld_in; prm.ld_out = ld_out; prm.n_streams = n_streams; prm.n_hops = n_hops; prm.mode = mode; prm.L = L;
+    prm.dbg_hop = dbg_hop; prm.compression = compression;
+    try {
+#define X(id, CFG, SV) if (fe::shape_matches<fe::CFG>(key) && S == SV) return fe::run_variant<fe::Plan<fe::CFG, SV>>(canonical, prm);
+        FE_ALL_VARIANTS(X)
+#undef X
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "fee_run: %s\n", e.what());
+        return -2;
+    }
+    return -1;
+}
+
+extern "C" int fee_tap_total(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads)
+{
+    fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
+#define X(id, CFG, SV) if (fe::shape_matches<fe::CFG>(key)) return fe::Frame<fe::Plan<fe::CFG, SV>>::TAP_TOTAL;
+    FE_ALL_VARIANTS(X)
+#undef X
+    return -1;
+}
