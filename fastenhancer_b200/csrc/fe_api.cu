@@ -14,6 +14,7 @@
 
 #include "../../include/fastenhancer_b200.h"
 #include "fe_variant.h"
+#include "fe_kernel.cuh"
 
 namespace {
 
@@ -80,6 +81,7 @@ struct fe_engine {
     std::vector<float> canonical;
     std::vector<Variant> variants;       // same shape, ascending S
     int forced_s = 0;
+    long long* prof = nullptr;           // optional per-phase cycle counters (device)
     long long launches = 0;
     std::mutex mu;
     // offline-mode scratch state (zeroed before every call)
@@ -146,6 +148,7 @@ int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st) {
     prm.blob = v.blob;
     prm.scratch = scratch;
     prm.compression = e->cfg.compression;
+    prm.prof = e->prof;
     const int grid = (prm.n_streams + v.ops.S - 1) / v.ops.S;
     FE_CUDA(v.ops.launch(prm, grid, st));
     ++e->launches;
@@ -386,6 +389,12 @@ FE_API int fe_set_streams_per_cta(fe_engine* e, int s) {
         if (!ok) return fail(FE_ERR_UNSUPPORTED, "fe_set_streams_per_cta: no such variant for this model");
     }
     e->forced_s = s;
+    return FE_OK;
+}
+FE_API int fe_profile_slots(void) { return (int)fe::PH_COUNT; }
+FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
+    if (!e) return fail(FE_ERR_ARG, "fe_set_profile: null engine");
+    e->prof = counters_device;
     return FE_OK;
 }
 FE_API long long fe_kernel_launches(fe_engine* e) { return e ? e->launches : 0; }

@@ -56,13 +56,22 @@ template <class P> struct GpuCtx {
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
     }
-    template <class F> __device__ __forceinline__ void phase(F&& f) { f(tid); bar_consumers<P::NT>(); }
-    template <class A, class F1, class F2> __device__ __forceinline__ void phase2(F1&& f1, F2&& f2) {
+    long long t_last;
+    __device__ __forceinline__ void stamp(int id) {
+        if (prm.prof != nullptr && cta == 0 && tid == 0) {
+            const long long t = clock64();
+            prm.prof[id] += t - t_last;
+            t_last = t;
+        }
+    }
+    template <class F> __device__ __forceinline__ void phase(int id, F&& f) { f(tid); bar_consumers<P::NT>(); stamp(id); }
+    template <class A, class F1, class F2> __device__ __forceinline__ void phase2(int id, F1&& f1, F2&& f2) {
         A a;
         f1(tid, a);
         bar_consumers<P::NT>();
         f2(tid, a);
         bar_consumers<P::NT>();
+        stamp(id);
     }
     __device__ __forceinline__ void next_frame() { seq_base += P::NCHUNK_FRAME; }
     __device__ __forceinline__ void check_frame(int) const {}
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     GpuCtx<P> x;
     x.sm = sm; x.blob = prm.blob; x.prm = prm; x.cta = blockIdx.x; x.s0 = blockIdx.x * P::S;
     x.gs = prm.scratch + (size_t)blockIdx.x * P::GS_TOTAL;
-    x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars;
+    x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64();
     Frame<P>::run(x);
 }
 

@@ -60,6 +60,11 @@ FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
 
 namespace fe {
 
+// phase ids for the optional in-kernel profile (KParams::prof): cycles of CTA 0 accumulated per id
+enum PhaseId { PH_INIT = 0, PH_LOAD, PH_WINDOW, PH_FFT, PH_COMPRESS, PH_ENC_PRE, PH_ENC, PH_LIN_PRE, PH_RF_PRE, PH_HLOAD, PH_GRU,
+               PH_RNN_FC, PH_QKV, PH_ATTN, PH_ATTN_FC, PH_LIN_POST, PH_RF_POST, PH_SKIP_LOAD, PH_PWCAT, PH_DEC, PH_CONVT, PH_MASK,
+               PH_PRETW, PH_IFFT, PH_OLA, PH_DBG, PH_STATE, PH_COUNT };
+
 FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
 FE_DEV float silu(float x) { return fe_div(x, 1.0f + fe_exp(-x)); }
@@ -248,11 +253,11 @@ template <class P> struct Frame {
         const KParams& prm = x.prm;
         float* sm = x.sm;
         // ---- one-time init: zero the activation area, load overlap state ----
-        x.phase([&](int tid) {
+        x.phase(PH_INIT, [&](int tid) {
             for (int i = tid * 4; i < P::SM_RING; i += NT * 4) st4(sm + i, mk4(0.f, 0.f, 0.f, 0.f));
         });
         if (prm.mode == MODE_STREAM) {
-            x.phase([&](int tid) {
+            x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::CL; idx += NT) {
                     int s = idx / C::CL, i = idx % C::CL;
                     int gs = x.s0 + s;
@@ -272,7 +277,7 @@ template <class P> struct Frame {
         }
         if (prm.mode == MODE_STREAM) {
             const int n = prm.n_hops;
-            x.phase([&](int tid) {
+            x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::CL; idx += NT) {
                     int s = idx / C::CL, i = idx % C::CL;
                     int gs = x.s0 + s;
@@ -288,11 +293,12 @@ template <class P> struct Frame {
 
     // complex M-point Stockham radix-2 FFT over S streams; returns the buffer holding the result
     template <class X> FE_DEV static float* fft(X& x, float* src, float* dst, bool inverse) {
+        const int ph = inverse ? PH_IFFT : PH_FFT;
         const float* tw = x.blob + P::make_aux().tw;
         int st = 1;
         for (int stage = 0; stage < LOG2M; ++stage, st <<= 1) {
             const int lst = stage;
-            x.phase([&](int tid) {
+            x.phase(ph, [&](int tid) {
                 for (int j = tid; j < S * (M / 2); j += NT) {
                     const int s = j / (M / 2), jj = j % (M / 2);
                     const int p = jj >> lst, q = jj & (st - 1);
@@ -341,7 +347,7 @@ template <class P> struct Frame {
         if (mode != MODE_SPEC) {
             const int wpos = (hop * H) & NMASK;
             if (mode == MODE_STREAM) {
-                x.phase([&](int tid) {
+                x.phase(PH_LOAD, [&](int tid) {
                     for (int idx = tid; idx < S * H; idx += NT) {
                         int s = idx / H, j = idx % H, gs = x.s0 + s;
                         float v = 0.f;
@@ -350,7 +356,7 @@ template <class P> struct Frame {
                     }
                 });
             }
-            x.phase([&](int tid) {
+            x.phase(PH_WINDOW, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
                     float a, b;
@@ -374,7 +380,7 @@ template <class P> struct Frame {
             });
             float* Z = fft(x, W0, W1, false);
             // unpack the packed real FFT, drop Nyquist, compress, scatter to the 8 virtual channels
-            x.phase([&](int tid) {
+            x.phase(PH_COMPRESS, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, k = idx % M;
                     f2 zk = ld2(Z + s * N + 2 * k), zm = ld2(Z + s * N + 2 * ((M - k) & (M - 1)));
@@ -392,7 +398,7 @@ template <class P> struct Frame {
                 }
             });
         } else {
-            x.phase([&](int tid) {
+            x.phase(PH_COMPRESS, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, k = idx % M, gs = x.s0 + s;
                     float re = 0.f, im = 0.f;
@@ -410,7 +416,7 @@ template <class P> struct Frame {
             });
         }
         auto dump_spec = [&](const float* buf, int off) {
-            x.phase([&](int tid) {
+            x.phase(PH_DBG, [&](int tid) {
                 for (int idx = tid; idx < 2 * FIN; idx += NT) {
                     int c = idx / FIN, k = idx % FIN;
                     prm.dbg[off + idx] = buf[(c * 4 + (k & 3)) * CP1 + 4 + (k >> 2)];
@@ -418,12 +424,12 @@ template <class P> struct Frame {
             });
         };
         auto dump_geo1 = [&](const float* buf, int off) {
-            x.phase([&](int tid) {
+            x.phase(PH_DBG, [&](int tid) {
                 for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = buf[(idx / F1) * CP1 + 4 + idx % F1];
             });
         };
         auto dump_rf = [&](const float* buf, int off) {
-            x.phase([&](int tid) {
+            x.phase(PH_DBG, [&](int tid) {
                 for (int idx = tid; idx < F2 * C2; idx += NT) prm.dbg[off + idx] = buf[(idx % C2) * PR + idx / C2];
             });
         };
@@ -435,12 +441,12 @@ template <class P> struct Frame {
             float* dst = skip_dst(x, i);
             EpiGeo1 epi{dst, aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1)), skip_gdst(x, i), true};
             if (i == 0) {
-                x.phase([&](int tid) {
+                x.phase(PH_ENC_PRE, [&](int tid) {
                     pos_gemm<typename P::EncPre>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
                 });
                 ci += P::EncPre::NCHUNK;
             } else {
-                x.phase([&](int tid) {
+                x.phase(PH_ENC, [&](int tid) {
                     pos_gemm<typename P::Conv3>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
                 });
                 ci += P::Conv3::NCHUNK;
@@ -452,7 +458,7 @@ template <class P> struct Frame {
         // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
         float* Y1 = AB + P::O_Y1;
         float* XR = AB + P::O_XR;
-        x.phase([&](int tid) {
+        x.phase(PH_LIN_PRE, [&](int tid) {
             row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
 #pragma unroll
                 for (int j = 0; j < P::LinPre::NO; j += 4)
@@ -460,7 +466,7 @@ template <class P> struct Frame {
             });
         });
         ci += P::LinPre::NCHUNK;
-        x.phase([&](int tid) {
+        x.phase(PH_RF_PRE, [&](int tid) {
             pos_gemm<typename P::RfPre>(x, tid, ci, [&](int k) { return Y1 + k * PR; }, F2P, 0,
                                         [&](int co, int s, int f, const float* v) {
                                             const float b = ldg(aux + A.rf_pre_b + co);
@@ -478,7 +484,7 @@ template <class P> struct Frame {
         for (int k = 0; k < C::K; ++k) {
             const auto ab = A.blk(k);
             // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
-            x.phase([&](int tid) {
+            x.phase(PH_HLOAD, [&](int tid) {
                 for (int idx = tid; idx < S * C2 * F2; idx += NT) {
                     int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
                     float v = 0.f;
@@ -487,7 +493,7 @@ template <class P> struct Frame {
                 }
             });
             // fused GRU step (PyTorch gate order r, z, n; b_hn inside the r * (.) term)
-            x.phase([&](int tid) {
+            x.phase(PH_GRU, [&](int tid) {
                 using L = typename P::Gru;
                 constexpr int CT = L::CT, PT = L::PT, RW = L::RW;
                 PosGeo<L> g(tid, F2P, 0);
@@ -552,7 +558,7 @@ template <class P> struct Frame {
             });
             ci += P::Gru::NCHUNK;
             // rnn_fc (+ folded BN) + residual (+ positional embedding in block 0)
-            x.phase([&](int tid) {
+            x.phase(PH_RNN_FC, [&](int tid) {
                 pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return G + kk * PR; }, F2P, 0,
                                          [&](int co, int s, int f, const float* v) {
                                              const float b = ldg(aux + ab.fc_b + co);
@@ -570,7 +576,7 @@ template <class P> struct Frame {
             if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
             // attention over the F2 tokens of the frame, HG heads per round
             for (int hg = 0; hg < P::NQG; ++hg) {
-                x.phase([&](int tid) {
+                x.phase(PH_QKV, [&](int tid) {
                     pos_gemm<typename P::Qkv>(x, tid, ci, [&](int kk) { return XR + kk * PR; }, F2P, 0,
                                               [&](int co, int s, int f, const float* v) {
                                                   const float b = ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + co);
@@ -578,7 +584,7 @@ template <class P> struct Frame {
                                               });
                 });
                 ci += P::Qkv::NCHUNK;
-                x.phase([&](int tid) {
+                x.phase(PH_ATTN, [&](int tid) {
                     const float scale = 1.0f / sqrtf((float)HD);
                     for (int it = tid; it < S * P::HG * F2; it += NT) {
                         const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
@@ -610,7 +616,7 @@ template <class P> struct Frame {
                     }
                 });
             }
-            x.phase([&](int tid) {
+            x.phase(PH_ATTN_FC, [&](int tid) {
                 pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return ATT + kk * PR; }, F2P, 0,
                                          [&](int co, int s, int f, const float* v) {
                                              const float b = ldg(aux + ab.afc_b + co);
@@ -623,7 +629,7 @@ template <class P> struct Frame {
             ci += P::Fc::NCHUNK;
             if (dbg) {
                 dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
-                x.phase([&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
+                x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
                     for (int idx = tid; idx < F2 * C2; idx += NT)
                         prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
                             prm.state[(size_t)x.s0 * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + (idx % C2) * F2 + idx / C2];
@@ -633,7 +639,7 @@ template <class P> struct Frame {
 
         // ================= rf_post: Linear(F2->F1), 1x1 conv =================
         float* Zb = AB + P::O_Z;
-        x.phase([&](int tid) {
+        x.phase(PH_LIN_POST, [&](int tid) {
             row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
 #pragma unroll
                 for (int j = 0; j < P::LinPost::NO; j += 4)
@@ -643,7 +649,7 @@ template <class P> struct Frame {
         ci += P::LinPost::NCHUNK;
         {
             EpiGeo1 epi{W1, aux + A.rf_post_b, nullptr, false};
-            x.phase([&](int tid) {
+            x.phase(PH_RF_POST, [&](int tid) {
                 pos_gemm<typename P::RfPost>(x, tid, ci, [&](int kk) { return Zb + kk * CP1; }, P1, 4, epi);
             });
             ci += P::RfPost::NCHUNK;
@@ -658,7 +664,7 @@ template <class P> struct Frame {
                 skip = sm + P::SM_SK + sk * ACT;
             } else {
                 const float* gsrc = x.gs + (size_t)(sk - P::SKIP_SMEM) * ACT;
-                x.phase([&](int tid) {
+                x.phase(PH_SKIP_LOAD, [&](int tid) {
                     for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(W0 + idx, ld4(gsrc + idx));
                 });
                 skip = W0;
@@ -668,7 +674,7 @@ template <class P> struct Frame {
                 using L = typename P::PwCat;
                 EpiGeo1 epi{W0, aux + (i < E ? A.dec1_b(i) : A.dp_b), nullptr, true};
                 auto xrow = [&](int kk) { return kk < C1 ? W1 + kk * CP1 : skip + (kk - C1) * CP1; };
-                x.template phase2<PwAcc>(
+                x.template phase2<PwAcc>(PH_PWCAT,
                     [&](int tid, PwAcc& a) {
                         PosGeo<L> g(tid, P1, 4);
 #pragma unroll
@@ -690,7 +696,7 @@ template <class P> struct Frame {
             }
             if (i < E) {
                 EpiGeo1 epi{W1, aux + A.dec2_b(i), nullptr, true};
-                x.phase([&](int tid) {
+                x.phase(PH_DEC, [&](int tid) {
                     pos_gemm<typename P::Conv3>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4, epi);
                 });
                 ci += P::Conv3::NCHUNK;
@@ -699,7 +705,7 @@ template <class P> struct Frame {
         }
         // transposed conv as a 3-tap conv to 8 virtual channels (o*4 + q) -> MASK (in W1)
         float* MASK = W1;
-        x.phase([&](int tid) {
+        x.phase(PH_CONVT, [&](int tid) {
             pos_gemm<typename P::ConvT>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4,
                                         [&](int vo, int s, int f, const float* v) {
                                             const float b = ldg(aux + A.convt_b + vo);
@@ -711,7 +717,7 @@ template <class P> struct Frame {
         if (dbg) dump_spec(MASK, TAP_MASK);
 
         // ================= mask * spectrum, decompression =================
-        x.phase([&](int tid) {
+        x.phase(PH_MASK, [&](int tid) {
             for (int idx = tid; idx < S * M; idx += NT) {
                 const int s = idx / M, k = idx % M, q = k & 3, m = k >> 2, gs = x.s0 + s;
                 const int o = q * CP1 + s * P1 + 4 + m;
@@ -734,7 +740,7 @@ template <class P> struct Frame {
         if (mode == MODE_SPEC) return;
 
         // ================= irFFT (packed), window, overlap-add =================
-        x.phase([&](int tid) {
+        x.phase(PH_PRETW, [&](int tid) {
             for (int idx = tid; idx < S * M; idx += NT) {
                 const int s = idx / M, k = idx % M;
                 f2 yk = ld2(W0 + s * N + 2 * k), ym;
@@ -749,7 +755,7 @@ template <class P> struct Frame {
         });
         const float* Y = fft(x, W1, W0, true);
         const int base = (hop * H) & NMASK;
-        x.phase([&](int tid) {
+        x.phase(PH_OLA, [&](int tid) {
             const float invM = 1.0f / (float)M;
             for (int idx = tid; idx < S * N; idx += NT) {
                 const int s = idx / N, i = idx % N, gs = x.s0 + s;

@@ -260,6 +260,7 @@ struct KParams {
     float* spec_out;          // mode 2 (optional): compressed masked spectrum [B][FIN][T][2]
     float* scratch;           // global scratch [grid][GS_TOTAL]
     float* dbg;               // optional tap dump of stream 0 (oracle tap layout), frame `dbg_hop`
+    long long* prof;          // optional [PH_COUNT] cycle counters of CTA 0 (accumulated over the launch)
     long long ld_in, ld_out;
     int n_streams, n_hops;    // n_hops = T frames in modes 1, 2
     int mode, L, dbg_hop;

@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "fe_last_error", "fe_weight_count", "fe_state_floats", "fe_create", "fe_destroy", "fe_state_create",
     "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
     "fe_spec", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
-    "fe_stream_taps",
+    "fe_stream_taps", "fe_profile_slots", "fe_set_profile",
 )
 
 
@@ -77,6 +77,8 @@ def load_library(build_if_missing: bool = True):
     lib.fe_kernel_launches.restype = ll
     lib.fe_tap_floats.argtypes = [vp]
     lib.fe_stream_taps.argtypes = [vp, vp, fp, fp, ip, ll, ll, fp, ip, vp]
+    lib.fe_profile_slots.argtypes = []
+    lib.fe_set_profile.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -174,6 +176,23 @@ class Engine:
 
     def set_streams_per_cta(self, s: int) -> None:
         _check(self._lib.fe_set_streams_per_cta(self._h, int(s)), "fe_set_streams_per_cta")
+
+    PHASES = ("init", "load", "window", "fft", "compress", "enc_pre", "enc", "lin_pre", "rf_pre", "hload", "gru", "rnn_fc", "qkv",
+              "attn", "attn_fc", "lin_post", "rf_post", "skip_load", "pwcat", "dec", "convt", "mask", "pretw", "ifft", "ola",
+              "dbg", "state")
+
+    def enable_profile(self, on: bool = True):
+        """Per-phase SM-cycle counters of CTA 0 (int64 cuda tensor, accumulated over launches) or None."""
+        import torch
+        if on:
+            n = int(self._lib.fe_profile_slots())
+            assert n == len(self.PHASES)
+            self._prof = torch.zeros(n, dtype=torch.int64, device=self.device)
+            _check(self._lib.fe_set_profile(self._h, self._prof.data_ptr()), "fe_set_profile")
+            return self._prof
+        _check(self._lib.fe_set_profile(self._h, None), "fe_set_profile")
+        self._prof = None
+        return None
 
     # ---- the hot path ----
     def stream(self, state: State, wav_in, out=None):

@@ -96,6 +96,12 @@ int fe_tap_floats(fe_engine* e);
 int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops,
                    long long ld_in, long long ld_out, float* taps_device, int tap_hop, void* cuda_stream);
 
+/* Profiling hook: when set, CTA 0 of every fused-kernel launch accumulates the SM cycles it spends in each
+ * phase of the frame (ids: enum PhaseId in fastenhancer_b200/csrc/fe_kernel.cuh) into counters_device
+ * [fe_profile_slots()] (int64).  NULL switches it off. */
+int fe_profile_slots(void);
+int fe_set_profile(fe_engine* e, long long* counters_device);
+
 #ifdef __cplusplus
 }
 #endif

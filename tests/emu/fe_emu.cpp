@@ -25,8 +25,8 @@ template <class P> struct EmuCtx {
         return blob + table[2 * ci];
     }
     void release(int) const {}
-    template <class F> void phase(F&& f) { for (int t = 0; t < P::NT; ++t) f(t); }
-    template <class A, class F1, class F2> void phase2(F1&& f1, F2&& f2) {
+    template <class F> void phase(int, F&& f) { for (int t = 0; t < P::NT; ++t) f(t); }
+    template <class A, class F1, class F2> void phase2(int, F1&& f1, F2&& f2) {
         std::vector<A> acc(P::NT);
         for (int t = 0; t < P::NT; ++t) f1(t, acc[t]);
         for (int t = 0; t < P::NT; ++t) f2(t, acc[t]);

@@ -1,0 +1,69 @@
+"""CPU emulation of the fused kernel body (tests/emu) against the oracle.
+
+The emulation compiles fastenhancer_b200/csrc/fe_kernel.cuh for the host and runs every
+barrier-separated phase as a loop over thread ids, reading weights from the very blob the GPU
+kernel consumes.  It pins the packer, the tile / layout index math, the buffer aliasing plan and the
+chunk schedule without a GPU; the GPU tests (test_gpu_parity.py) pin the real kernel.
+Tolerance: 2e-6 absolute on waveforms of RMS ~0.1 (fp32, different summation order)."""
+import numpy as np
+import pytest
+
+from fastenhancer_b200.config import PRESETS
+from fastenhancer_b200.synth import synthetic_noisy
+from oracle.oracle import Oracle, tap_schema
+from emu import emu
+
+VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 1), ("16k_m", 1), ("48k_t", 2), ("48k_s", 1)]
+
+
+@pytest.mark.parametrize("name,S", VARIANTS)
+def test_streaming_and_state_round_trip(name, S, canonical):
+    cfg = PRESETS[name]
+    canon = canonical(name)
+    o = Oracle(cfg, canon)
+    B, nh, H = 3, 4, cfg.hop_size                        # B not a multiple of S: ragged last CTA
+    x = synthetic_noisy(B, nh * H, cfg.sample_rate)
+    st = o.new_state(B)
+    want, taps_ref = o.stream(st, x, taps=True)
+    stn = emu.to_native(cfg, o.new_state(B))
+    got = np.zeros_like(x)
+    dbg = np.zeros(emu.tap_total(cfg), np.float32)
+    assert dbg.size == o.tap_floats
+    # two launches (2 + 2 hops): the overlap / GRU state must survive the round trip through global memory
+    x1, x2 = np.ascontiguousarray(x[:, :2 * H]), np.ascontiguousarray(x[:, 2 * H:])
+    y1, y2 = np.zeros_like(x1), np.zeros_like(x2)
+    emu.run(cfg, S, canon, emu.MODE_STREAM, stn, x1, y1, n_streams=B, n_hops=2, ld_in=2 * H, ld_out=2 * H)
+    emu.run(cfg, S, canon, emu.MODE_STREAM, stn, x2, y2, n_streams=B, n_hops=2, ld_in=2 * H, ld_out=2 * H, dbg=dbg, dbg_hop=1)
+    got = np.concatenate([y1, y2], axis=1)
+    assert np.abs(got - want).max() < 2e-6
+    assert np.abs(emu.to_canonical(cfg, stn) - st).max() < 5e-6
+    off = 0
+    for nm, shp in tap_schema(cfg):
+        n = int(np.prod(shp))
+        ref = taps_ref[nm][3]
+        assert np.abs(dbg[off:off + n].reshape(shp) - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), nm
+        off += n
+
+
+@pytest.mark.parametrize("name,S", [("16k_t", 2), ("16k_m", 1)])
+def test_spec_and_offline_modes(name, S, canonical):
+    cfg = PRESETS[name]
+    canon = canonical(name)
+    o = Oracle(cfg, canon)
+    B, T, N, H = 3, 3, cfg.n_fft, cfg.hop_size
+    spec = (np.random.RandomState(1).standard_normal((B, N // 2 + 1, T, 2)) * 0.5).astype(np.float32)
+    h = np.zeros((B, cfg.rf_blocks, cfg.rf_freq, cfg.rf_channels), np.float32)
+    want = o.spec(h, spec)
+    stn = emu.to_native(cfg, o.new_state(B))
+    got = np.full_like(spec, np.nan)
+    emu.run(cfg, S, canon, emu.MODE_SPEC, stn, spec, got, n_streams=B, n_hops=T)
+    assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+    assert np.all(got[:, -1] == 0)
+    L = 5 * H + 37                                       # ragged length: the reference floors to L // hop frames
+    w = synthetic_noisy(B, L, cfg.sample_rate)
+    w_ref, sp_ref = o.offline(w)
+    stn = emu.to_native(cfg, o.new_state(B))
+    w_out, sp_out = np.full_like(w_ref, np.nan), np.full_like(sp_ref, np.nan)
+    emu.run(cfg, S, canon, emu.MODE_OFFLINE, stn, w, w_out, spec_out=sp_out, n_streams=B, n_hops=1 + L // H, L=L)
+    assert np.abs(w_out - w_ref).max() < 2e-6
+    assert np.abs(sp_out - sp_ref).max() < 1e-4 * max(1.0, np.abs(sp_ref).max())

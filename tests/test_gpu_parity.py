@@ -1,0 +1,207 @@
+"""Parity of the fused CUDA kernel (through the C ABI, fastenhancer_b200.engine) against the CPU oracle and
+against the committed golden vectors produced by the reference itself (tools/gen_golden.py).
+
+Tolerance (north-star): <= 1e-4 RMS on the enhanced waveform in fp32; the engine is held to 1e-5 RMS
+(it is fp32 FMA arithmetic in a different summation order, with ex2-based SiLU).  Frame indexing
+(hop alignment, n_fft - hop delay, output lengths, zero Nyquist bin) is checked exactly."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rms
+from fastenhancer_b200.config import PRESETS
+from fastenhancer_b200.synth import synthetic_noisy
+
+pytestmark = pytest.mark.gpu
+ALL = sorted(PRESETS)
+N_HOPS = 24
+
+
+@pytest.fixture(scope="module")
+def engines(canonical):
+    from fastenhancer_b200.engine import Engine
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Engine(PRESETS[name], canonical(name), "cuda:0")
+        return cache[name]
+    return get
+
+
+def _oracle(name, canonical):
+    from oracle.oracle import Oracle
+    return Oracle(PRESETS[name], canonical(name))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_streaming_matches_reference_golden(name, golden, engines):
+    """stream_out / stream_state of the golden files come from the reference's own streaming graph."""
+    cfg, g, eng = PRESETS[name], golden(name), engines(name)
+    x = synthetic_noisy(2, N_HOPS * cfg.hop_size, cfg.sample_rate)
+    st = eng.new_state(2)
+    y = eng.stream(st, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape == g["stream_out"].shape
+    assert rms(y - g["stream_out"]) < 1e-5
+    assert np.abs(st.export().cpu().numpy() - g["stream_state"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_every_variant_matches_oracle(name, canonical, engines):
+    """every streams-per-CTA variant, ragged stream counts, state carried across launches."""
+    cfg, eng, o = PRESETS[name], engines(name), _oracle(name, canonical)
+    H = cfg.hop_size
+    try:
+        for S in (1, 2, 4):
+            try:
+                eng.set_streams_per_cta(S)
+            except RuntimeError:
+                continue
+            B = 2 * S + 1
+            x = synthetic_noisy(B, 6 * H, cfg.sample_rate, first_stream=7)
+            ost = o.new_state(B)
+            want = o.stream(ost, x)
+            st = eng.new_state(B)
+            xd = torch.from_numpy(x).cuda()
+            got = torch.cat([eng.stream(st, xd[:, :2 * H]), eng.stream(st, xd[:, 2 * H:])], dim=1).cpu().numpy()
+            assert rms(got - want) < 1e-5, (name, S)
+            assert np.abs(st.export().cpu().numpy() - ost).max() < 2e-5, (name, S)
+    finally:
+        eng.set_streams_per_cta(0)
+
+
+@pytest.mark.parametrize("name", ["16k_t", "16k_b", "16k_m", "48k_l"])
+def test_hop_by_hop_equals_one_launch_bit_exact(name, engines):
+    """1 launch of n hops == n launches of 1 hop: the state round trip through HBM loses nothing."""
+    cfg, eng = PRESETS[name], engines(name)
+    H = cfg.hop_size
+    x = torch.from_numpy(synthetic_noisy(3, 5 * H, cfg.sample_rate)).cuda()
+    s1, s2 = eng.new_state(3), eng.new_state(3)
+    y1 = eng.stream(s1, x)
+    y2 = torch.cat([eng.stream(s2, x[:, i * H:(i + 1) * H]) for i in range(5)], dim=1)
+    assert torch.equal(y1, y2) and torch.equal(s1.export(), s2.export())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_stage_taps(name, canonical, engines):
+    from oracle.oracle import tap_schema
+    cfg, eng, o = PRESETS[name], engines(name), _oracle(name, canonical)
+    x = synthetic_noisy(2, 5 * cfg.hop_size, cfg.sample_rate)
+    _, ref = o.stream(o.new_state(2), x, taps=True)
+    _, taps = eng.stream_taps(eng.new_state(2), torch.from_numpy(x).cuda(), 4)
+    taps = taps.cpu().numpy()
+    off = 0
+    for nm, shp in tap_schema(cfg):
+        n = int(np.prod(shp))
+        r = ref[nm][4]
+        assert np.abs(taps[off:off + n].reshape(shp) - r).max() < 2e-5 * max(1.0, np.abs(r).max()), nm
+        off += n
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_offline_matches_reference_golden(name, golden, engines):
+    cfg, g, eng = PRESETS[name], golden(name), engines(name)
+    L = int(g["offline_len"])
+    wav, spec = eng.offline(torch.from_numpy(synthetic_noisy(2, L, cfg.sample_rate)).cuda())
+    wav, spec = wav.cpu().numpy(), spec.cpu().numpy()
+    assert wav.shape == g["offline_wav"].shape == (2, cfg.hop_size * (L // cfg.hop_size))      # exact frame arithmetic
+    assert spec.shape == (2, cfg.f_in, 1 + L // cfg.hop_size, 2)
+    assert rms(wav - g["offline_wav"]) < 1e-5
+    if "offline_spec_frames" in g.files:
+        spec = spec[:, :, g["offline_spec_frames"]]
+    assert np.abs(spec - g["offline_spec"]).max() < 1e-4 * max(1.0, np.abs(g["offline_spec"]).max())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_spec2spec_matches_reference_golden(name, golden, engines):
+    cfg, g, eng = PRESETS[name], golden(name), engines(name)
+    st = eng.new_state(2)
+    sp = torch.from_numpy(g["spec_in"]).cuda()
+    out = torch.cat([eng.spec(st, sp[:, :, :3].contiguous()), eng.spec(st, sp[:, :, 3:6].contiguous())], dim=2).cpu().numpy()
+    assert np.abs(out - g["spec_out"]).max() < 1e-5 * np.abs(g["spec_out"]).max()
+    assert np.all(out[:, -1] == 0)                                   # Nyquist bin padded with zeros
+    h = st.export().cpu().numpy()[:, 2 * cfg.cache_len:].reshape(g["spec_h"].shape)
+    assert np.abs(h - g["spec_h"]).max() < 2e-5
+
+
+def test_state_import_export_round_trip(engines):
+    eng = engines("16k_b")
+    st = eng.new_state(5)
+    ref = torch.randn(5, eng.state_floats, device="cuda")
+    st.load(ref)
+    assert torch.equal(st.export(), ref)
+    st.reset()
+    assert float(st.export().abs().max()) == 0.0
+
+
+def test_streaming_delay_is_nfft_minus_hop(canonical, engines):
+    """bit-exact frame indexing: with an identity-like mask the streaming output is the input delayed by n_fft - hop
+    (docs/docs/onnx.md:37-72); an impulse at sample p must peak at p + n_fft - hop."""
+    cfg, eng = PRESETS["16k_b"], engines("16k_b")
+    H, N = cfg.hop_size, cfg.n_fft
+    x = np.zeros((1, 8 * H), np.float32)
+    p = 3 * H + 17
+    x[0, p] = 1.0
+    y = eng.stream(eng.new_state(1), torch.from_numpy(x).cuda()).cpu().numpy()[0]
+    want = _oracle("16k_b", canonical).stream(np.zeros((1, cfg.state_floats), np.float32), x)[0]
+    assert int(np.argmax(np.abs(want))) == p + N - H
+    assert int(np.argmax(np.abs(y))) == p + N - H
+    assert np.all(y[:p] == 0.0)                                      # nothing before the impulse reaches the output
+
+
+def test_host_buffer_path_equals_device_path(engines):
+    """fe_stream_host (pipelined H2D / kernel / D2H in pieces) == fe_stream on resident buffers, bit for bit."""
+    cfg, eng = PRESETS["16k_b"], engines("16k_b")
+    H = cfg.hop_size
+    x = torch.from_numpy(synthetic_noisy(9, 37 * H, cfg.sample_rate)).pin_memory()
+    y_dev = eng.stream(eng.new_state(9), x.cuda()).cpu()
+    y_host = eng.stream_host(eng.new_state(9), x, hops_per_chunk=8)
+    assert torch.equal(y_dev, y_host)
+
+
+def test_full_size_properties(canonical, engines):
+    """BASELINE config 2 at full size (FastEnhancer_B, 256 streams, 10 s = 626 hops): sampled streams against
+    the oracle, stream independence, and launch-split invariance."""
+    cfg, eng, o = PRESETS["16k_b"], engines("16k_b"), _oracle("16k_b", canonical)
+    H, B, nh = cfg.hop_size, 256, 626
+    x = synthetic_noisy(B, nh * H, cfg.sample_rate)
+    x[200] = x[3]                                                     # two streams with identical input
+    xd = torch.from_numpy(x).cuda()
+    st = eng.new_state(B)
+    y = eng.stream(st, xd)
+    pick = [0, 3, 131, 255]
+    want = o.stream(o.new_state(len(pick)), x[pick])
+    assert rms(y[pick].cpu().numpy() - want) < 1e-5
+    assert torch.equal(y[200], y[3])                                  # streams never mix
+    st2 = eng.new_state(B)
+    y2 = torch.cat([eng.stream(st2, xd[:, :300 * H]), eng.stream(st2, xd[:, 300 * H:])], dim=1)
+    assert torch.equal(y, y2)
+    assert rms(y.cpu().numpy()) > 0.05                                # mask ~ identity: output carries the signal
+
+
+def test_model_classes_drop_in(golden):
+    """Model / ONNXModel / StreamingModel (the reference-facing host classes) on the engine."""
+    from fastenhancer_b200.model import Model, ONNXModel, StreamingModel
+    cfg, g = PRESETS["16k_t"], golden("16k_t")
+    m = Model(**cfg.to_model_kwargs()).eval().cuda()
+    L = int(g["offline_len"])
+    wav, spec = m(torch.from_numpy(synthetic_noisy(2, L, cfg.sample_rate)).cuda())
+    assert rms(wav.cpu().numpy() - g["offline_wav"]) < 1e-5 and spec.shape[1:] == (cfg.f_in, 1 + L // cfg.hop_size, 2)
+    om = ONNXModel(**cfg.to_model_kwargs()).eval().cuda()
+    sp = torch.from_numpy(g["spec_in"]).cuda()
+    o1, *h = om(sp[:, :, :3].contiguous())
+    o2, *h = om(sp[:, :, 3:6].contiguous(), *h)
+    out = torch.cat([o1, o2], dim=2).cpu().numpy()
+    assert np.abs(out - g["spec_out"]).max() < 1e-5 * np.abs(g["spec_out"]).max()
+    assert tuple(h[0].shape) == (1, 2 * cfg.rf_freq, cfg.rf_channels)
+    # streaming graph with explicit caches, hop by hop, like scripts/test_onnx.py:44-49
+    sm = StreamingModel(om)
+    H = cfg.hop_size
+    x = torch.from_numpy(synthetic_noisy(2, N_HOPS * H, cfg.sample_rate)).cuda()
+    caches = sm.initialize_cache(x[:, :H])
+    hops = []
+    for i in range(N_HOPS):
+        y, *caches = sm(x[:, i * H:(i + 1) * H], *caches)
+        hops.append(y)
+    assert rms(torch.cat(hops, dim=1).cpu().numpy() - g["stream_out"]) < 1e-5
+    assert rms(sm.run(x).cpu().numpy() - g["stream_out"]) < 1e-5

@@ -32,7 +32,7 @@ def diag(name, S, B=5, nh=6):
     eng = Engine(cfg, canon)
     eng.set_streams_per_cta(S)
     state = eng.new_state(B)
-    hop = 3
+    hop = min(3, nh - 1)
     y, taps = eng.stream_taps(state, torch.from_numpy(x).cuda(), hop)
     torch.cuda.synchronize()
     y = y.cpu().numpy(); taps = taps.cpu().numpy()
@@ -76,9 +76,32 @@ def timing(name, B, nh, S=0):
           f"{fps / 1e6:.3f} Mframes/s, {tf:.2f} TFLOP/s alg, RTF/stream={ms * 1e-3 / (nh * H / cfg.sample_rate):.5f}")
 
 
+def profile(name, B, nh, S=0):
+    """per-phase SM cycles of CTA 0 (clock64 stamps after each barrier-separated phase)."""
+    cfg = PRESETS[name]
+    canon = fold_to_canonical(cfg, synthetic_state_dict(cfg, 0))
+    eng = Engine(cfg, canon)
+    if S:
+        eng.set_streams_per_cta(S)
+    x = torch.randn(B, nh * cfg.hop_size, device="cuda") * 0.1
+    state = eng.new_state(B)
+    eng.stream(state, x)
+    prof = eng.enable_profile(True)
+    eng.stream(state, x)
+    torch.cuda.synchronize()
+    p = prof.cpu().numpy().astype(np.float64) / nh
+    tot = p.sum()
+    print(f"PROF {name} B={B} S={eng.streams_per_cta(B)}: {tot:.0f} cycles/hop (CTA 0)")
+    for nm, v in sorted(zip(eng.PHASES, p), key=lambda t: -t[1]):
+        if v > 0:
+            print(f"  {nm:10s} {v:9.0f} cyc  {100 * v / tot:5.1f}%")
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    if sys.argv[1] == "--time":
+    if sys.argv[1] == "--prof":
+        profile(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 0)
+    elif sys.argv[1] == "--time":
         timing(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     else:
         diag(sys.argv[1], int(sys.argv[2]), *(int(a) for a in sys.argv[3:]))
