@@ -136,7 +136,8 @@ def test_state_import_export_round_trip(engines):
 
 def test_streaming_delay_is_nfft_minus_hop(canonical, engines):
     """bit-exact frame indexing: with an identity-like mask the streaming output is the input delayed by n_fft - hop
-    (docs/docs/onnx.md:37-72); an impulse at sample p must peak at p + n_fft - hop."""
+    (docs/docs/onnx.md:37-72); an impulse at sample p must peak at p + n_fft - hop, and nothing may come out before
+    the hop that first sees it (the frame containing the impulse legitimately spreads inside its own n_fft window)."""
     cfg, eng = PRESETS["16k_b"], engines("16k_b")
     H, N = cfg.hop_size, cfg.n_fft
     x = np.zeros((1, 8 * H), np.float32)
@@ -146,7 +147,7 @@ def test_streaming_delay_is_nfft_minus_hop(canonical, engines):
     want = _oracle("16k_b", canonical).stream(np.zeros((1, cfg.state_floats), np.float32), x)[0]
     assert int(np.argmax(np.abs(want))) == p + N - H
     assert int(np.argmax(np.abs(y))) == p + N - H
-    assert np.all(y[:p] == 0.0)                                      # nothing before the impulse reaches the output
+    assert np.all(y[:(p // H) * H] == 0.0) and np.all(want[:(p // H) * H] == 0.0)
 
 
 def test_host_buffer_path_equals_device_path(engines):
