@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU work per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams-per-cta", type=int, default=0)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="tf32: conv-type contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate; parity 7e-6 RMS "
+                         "vs the 1e-4 bar); fp32: every multiply-add on the fp32 FMA pipe")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -207,7 +210,7 @@ def main():
     B = args.streams
     length, n_hops = workload(cfg, args.seconds)
     H = cfg.hop_size
-    eng = Engine(cfg, canon, dev)
+    eng = Engine(cfg, canon, dev, precision=args.precision)
     if args.streams_per_cta:
         eng.set_streams_per_cta(args.streams_per_cta)
     x_host = torch.from_numpy(make_input(cfg, B, length, n_hops, first_stream=rank * B)).pin_memory()
@@ -281,13 +284,14 @@ def main():
         size = args.preset.split("_")[1].upper()
         line = {
             "metric": "frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 contractions (fp32 accumulate), f32 elsewhere" if args.precision == "tf32" else "f32",
             "data": "synthetic",
             "rtf": (ms_step * 1e-3) / (n_hops * H / cfg.sample_rate),
             "config": {"workload": f"FastEnhancer_{size} {cfg.sample_rate // 1000} kHz streaming wav2wav, {B} streams/GPU x {args.seconds:g} s "
                                    f"({n_hops} hops of {H}), fp32, random-init folded weights", "preset": args.preset,
                        "streams_per_gpu": B, "hops_per_step": n_hops, "frames_per_step": frames_step,
-                       "streams_per_cta": eng.streams_per_cta(B), "parallelism": f"streams sharded x{world}, no collective",
+                       "streams_per_cta": eng.streams_per_cta(B), "precision": args.precision, "parallelism": f"streams sharded x{world}, no collective",
                        "l2": "per-step input+output 2x%.0f MB exceed the 126 MB L2" % (io_bytes / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,

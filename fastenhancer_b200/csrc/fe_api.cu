@@ -81,6 +81,7 @@ struct fe_engine {
     std::vector<float> canonical;
     std::vector<Variant> variants;       // same shape, ascending S
     int forced_s = 0;
+    int tc = 1;                          // 1: conv-type contractions on tcgen05 (TF32 operands, fp32 accumulate); 0: all fp32 FMA
     long long* prof = nullptr;           // optional per-phase cycle counters (device)
     long long launches = 0;
     std::mutex mu;
@@ -104,15 +105,20 @@ struct fe_state {
 namespace {
 
 int pick_variant(fe_engine* e, int n_streams) {
+    // variants are sorted by (tc, S); only those of the engine's precision mode are eligible
+    int first = -1;
     if (e->forced_s > 0) {
-        for (size_t i = 0; i < e->variants.size(); ++i) if (e->variants[i].ops.S == e->forced_s) return (int)i;
+        for (size_t i = 0; i < e->variants.size(); ++i)
+            if (e->variants[i].ops.tc == e->tc && e->variants[i].ops.S == e->forced_s) return (int)i;
     }
     // largest S that still gives most SMs a CTA; otherwise the smallest S
     for (int i = (int)e->variants.size() - 1; i >= 0; --i) {
+        if (e->variants[i].ops.tc != e->tc) continue;
+        first = i;
         const int S = e->variants[i].ops.S;
         if ((n_streams + S - 1) / S >= (e->num_sms * 4) / 5) return i;
     }
-    return 0;
+    return first;
 }
 
 int ensure_variant(fe_engine* e, int vi) {
@@ -182,7 +188,8 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
         return fail(FE_ERR_UNSUPPORTED, "fe_create: model shape is not one of the shipped FastEnhancer configurations (T/B/S/M/L at 16 or 48 kHz)");
     if (n_floats != weight_count(*cfg)) return fail(FE_ERR_ARG, "fe_create: canonical weight array has the wrong length");
     if (!(cfg->compression > 0.f)) return fail(FE_ERR_ARG, "fe_create: compression must be positive");
-    std::sort(vs.begin(), vs.end(), [](const Variant& a, const Variant& b) { return a.ops.S < b.ops.S; });
+    std::sort(vs.begin(), vs.end(), [](const Variant& a, const Variant& b) {
+        return a.ops.tc != b.ops.tc ? a.ops.tc < b.ops.tc : a.ops.S < b.ops.S; });
     FE_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     FE_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -192,6 +199,7 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     e->canonical.assign(canonical, canonical + n_floats);
     e->variants = std::move(vs);
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
+    if (const char* env = std::getenv("FE_PRECISION")) e->tc = std::strcmp(env, "fp32") == 0 ? 0 : 1;
     *out = e;
     return FE_OK;
 }
@@ -385,12 +393,18 @@ FE_API int fe_set_streams_per_cta(fe_engine* e, int s) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_streams_per_cta: null engine");
     if (s != 0) {
         bool ok = false;
-        for (const Variant& v : e->variants) ok = ok || v.ops.S == s;
+        for (const Variant& v : e->variants) ok = ok || (v.ops.S == s && v.ops.tc == e->tc);
         if (!ok) return fail(FE_ERR_UNSUPPORTED, "fe_set_streams_per_cta: no such variant for this model");
     }
     e->forced_s = s;
     return FE_OK;
 }
+FE_API int fe_set_precision(fe_engine* e, int fp32_exact) {
+    if (!e) return fail(FE_ERR_ARG, "fe_set_precision: null engine");
+    e->tc = fp32_exact ? 0 : 1;
+    return FE_OK;
+}
+FE_API int fe_get_precision(fe_engine* e) { return e ? (e->tc ? 0 : 1) : fail(FE_ERR_ARG, "fe_get_precision: null engine"); }
 FE_API int fe_profile_slots(void) { return (int)fe::PH_COUNT; }
 FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_profile: null engine");

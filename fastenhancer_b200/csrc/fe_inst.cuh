@@ -41,6 +41,30 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// ---- tcgen05 (UMMA) primitives; encodings validated on hardware by tools/tc_probe.cu ----
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: element (row r, k) at
+//   start + (r % 8) * 16 + (r / 8) * SBO + (k / 4) * LBO + (k % 4) * 4   bytes (tf32: 4 elements per 16 B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D f32, A/B tf32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` once every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int NT> __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 template <class P> struct GpuCtx {
@@ -56,6 +80,46 @@ template <class P> struct GpuCtx {
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
     }
+    // ---- tensor-core state (TC variants) ----
+    uint32_t tmem;          // TMEM base address (lane 0, first allocated column)
+    uint32_t acc_bar;       // mbarrier: accumulators of the current layer are complete
+    unsigned acc_uses;
+    __device__ __forceinline__ void mma_fence() const { tc_fence_after(); }
+    __device__ __forceinline__ void mma(const float* a, int a_lbo_floats, const float* b, int b_lbo_floats, int np, int col,
+                                        bool acc, int /*rows*/) const {
+        umma_tf32(tmem + (uint32_t)col, umma_desc(smem_u32(a), (uint32_t)a_lbo_floats * 4u, 128u),
+                  umma_desc(smem_u32(b), (uint32_t)b_lbo_floats * 4u, 128u), umma_idesc_tf32_m128(np), acc ? 1u : 0u);
+    }
+    // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
+    // the stage, are done); the other warps never touch the stage and arrive at once
+    __device__ __forceinline__ void release_mma(int ci) const {
+        const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES;
+        __syncwarp();
+        if (tid == 0) umma_commit(bars + 8u * (P::STAGES + stage));
+        else if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
+    }
+    __device__ __forceinline__ void acc_commit_wait() {
+        if (tid == 0) umma_commit(acc_bar);
+        mbar_wait(acc_bar, acc_uses & 1u);
+        ++acc_uses;
+        tc_fence_after();
+    }
+    __device__ __forceinline__ void tmem_ld4(int /*tid*/, int col, float* v) const {
+        const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) << 5) << 16) + (uint32_t)col;   // this warp's lane quadrant
+        uint32_t r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+        v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    }
+    __device__ __forceinline__ void tmem_ld_wait() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+    // end of a phase: make generic-proxy shared-memory writes visible to the async proxy (MMA operand reads) and order
+    // TMEM accesses across the barrier
+    __device__ __forceinline__ void phase_sync() const {
+        if constexpr (P::TC) { fence_async_smem(); tc_fence_before(); }
+        bar_consumers<P::NT>();
+        if constexpr (P::TC) tc_fence_after();
+    }
+
     long long t_last;
     __device__ __forceinline__ void stamp(int id) {
         if (prm.prof != nullptr && cta == 0 && tid == 0) {
@@ -64,13 +128,13 @@ template <class P> struct GpuCtx {
             t_last = t;
         }
     }
-    template <class F> __device__ __forceinline__ void phase(int id, F&& f) { f(tid); bar_consumers<P::NT>(); stamp(id); }
+    template <class F> __device__ __forceinline__ void phase(int id, F&& f) { f(tid); phase_sync(); stamp(id); }
     template <class A, class F1, class F2> __device__ __forceinline__ void phase2(int id, F1&& f1, F2&& f2) {
         A a;
         f1(tid, a);
-        bar_consumers<P::NT>();
+        phase_sync();
         f2(tid, a);
-        bar_consumers<P::NT>();
+        phase_sync();
         stamp(id);
     }
     __device__ __forceinline__ void next_frame() { seq_base += P::NCHUNK_FRAME; }
@@ -87,9 +151,19 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
             mbar_init(bars + 8u * i, 1);                        // full: producer's expect_tx arrival
             mbar_init(bars + 8u * (P::STAGES + i), P::NW);      // empty: one arrival per consumer warp
         }
+        if constexpr (P::TC) mbar_init(bars + 8u * (2 * P::STAGES), 1);   // accumulator-ready barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P::SM_BAR + 4 * P::STAGES + 2);
+    if constexpr (P::TC) {
+        if (threadIdx.x < 32) {          // warp 0 owns the TMEM allocation (256 columns x 128 lanes of fp32 accumulators)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+    }
     __syncthreads();
+    if constexpr (P::TC) tc_fence_after();
     if (threadIdx.x >= P::NT) {
         // ---------------- producer warp: stream the weights of every frame through the ring ----------------
         if (threadIdx.x == P::NT) {
@@ -113,7 +187,14 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     x.sm = sm; x.blob = prm.blob; x.prm = prm; x.cta = blockIdx.x; x.s0 = blockIdx.x * P::S;
     x.gs = prm.scratch + (size_t)blockIdx.x * P::GS_TOTAL;
     x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64();
+    x.tmem = 0; x.acc_bar = bars + 8u * (2 * P::STAGES); x.acc_uses = 0;
+    if constexpr (P::TC) x.tmem = *tmem_slot;
     Frame<P>::run(x);
+    if constexpr (P::TC) {
+        tc_fence_before();
+        bar_consumers<P::NT>();
+        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(x.tmem) : "memory");
+    }
 }
 
 template <class P> struct VariantImpl {
@@ -128,7 +209,7 @@ template <class P> struct VariantImpl {
     static VariantOps ops(int cfg_id) {
         using C = typename P::Cf;
         VariantOps v{};
-        v.cfg_id = cfg_id; v.S = P::S;
+        v.cfg_id = cfg_id; v.S = P::S; v.tc = P::TC ? 1 : 0;
         v.shape = ShapeKey{C::N_FFT, C::HOP, C::C1, C::E, C::C2, C::F2, C::K, C::NH};
         v.smem_bytes = P::SMEM_BYTES; v.nthreads = P::NTHREADS; v.gs_floats = P::GS_TOTAL; v.state_floats = C::STATE;
         v.tap_floats = Frame<P>::TAP_TOTAL; v.nchunk_frame = P::NCHUNK_FRAME; v.blob_floats = P::make_aux().total;
@@ -139,7 +220,7 @@ template <class P> struct VariantImpl {
 
 }  // namespace fe
 
-#define FE_VARIANT_ENTRY(id, CFG, SV) fe::VariantImpl<fe::Plan<fe::CFG, SV>>::ops(id),
+#define FE_VARIANT_ENTRY(id, CFG, SV, TCV) fe::VariantImpl<fe::Plan<fe::CFG, SV, TCV>>::ops(id),
 #define FE_DEFINE_VARIANTS(fn, LIST)                                    \
     namespace fe {                                                      \
     const VariantOps* fn(int* n) {                                      \

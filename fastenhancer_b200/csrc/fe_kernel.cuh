@@ -25,6 +25,7 @@
 #include "fe_plan.h"
 
 #ifdef FE_EMU
+#include <cstdint>
 #include <cassert>
 #include <cmath>
 #include <cstring>
@@ -41,6 +42,7 @@ inline float ldg(const float* p) { return *p; }
 inline f2 ldg2(const float* p) { return ld2(p); }
 inline float fe_exp(float x) { return expf(x); }
 inline float fe_div(float a, float b) { return a / b; }
+inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 }  // namespace fe
 #else
 #define FE_DEV __device__ __forceinline__
@@ -55,6 +57,8 @@ FE_DEV float ldg(const float* p) { return __ldg(p); }
 FE_DEV f2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 FE_DEV float fe_exp(float x) { return __expf(x); }
 FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
+// round to nearest TF32 so that the tensor core (which reads the top 19 bits) sees the value exactly
+FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
 }  // namespace fe
 #endif
 
@@ -206,6 +210,110 @@ FE_DEV void row_gemm(X& x, int tid, int ci0, const float* xbase, int row_pitch, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row GEMM, one k per step (frequency-axis linear over a tensor-core-layout activation).
+// xrow(r) -> address of element k = 0 of row r; consecutive k are kstride floats apart.  epi(row, o0, values[NO]).
+// ---------------------------------------------------------------------------------------------
+template <class L, class X, class XRow, class Epi>
+FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
+    constexpr int RT = L::RT, NO = L::NO;
+    const int og = tid >> 5, lane = tid & 31;
+    const bool active = og < L::NOG;
+    float acc[RT][NO];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < NO; ++j) acc[i][j] = 0.f;
+    const float* xr[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) { int r = lane + 32 * i; xr[i] = xrow(r < L::NROWS ? r : 0); }
+    for (int c = 0; c < L::NCHUNK; ++c) {
+        const int rows = (c == L::NCHUNK - 1) ? L::K - c * L::KC : L::KC;
+        const float* w = x.acquire(ci0 + c, rows * L::ROW);
+        if (active) {
+            const float* wl = w + og * NO;
+#pragma unroll 4
+            for (int kk = 0; kk < rows; ++kk) {
+                const int k = c * L::KC + kk;
+                float xv[RT];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) xv[i] = xr[i][k * kstride];
+#pragma unroll
+                for (int j = 0; j < NO; j += 4) {
+                    f4 wv = ld4(wl + kk * L::ROW + j);
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) {
+                        acc[i][j] = fmaf(wv.x, xv[i], acc[i][j]);
+                        acc[i][j + 1] = fmaf(wv.y, xv[i], acc[i][j + 1]);
+                        acc[i][j + 2] = fmaf(wv.z, xv[i], acc[i][j + 2]);
+                        acc[i][j + 3] = fmaf(wv.w, xv[i], acc[i][j + 3]);
+                    }
+                }
+            }
+        }
+        x.release(ci0 + c);
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = lane + 32 * i;
+            if (r < L::NROWS) epi(r, og * NO, acc[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core layer (TcGemm): thread 0 issues one tcgen05.mma (M = 128, N = NP, K = 8, kind::tf32) per
+// (tap, k-step, M tile) as the weight tiles arrive in the ring, releasing each ring stage with a
+// tcgen05.commit onto its empty barrier; accumulators sit in TMEM.  After the last MMA every consumer
+// thread owns one accumulator row (TMEM lane = position) and half of the channel groups:
+// epi(global position, channel group, values[4]).
+// a_kstep(j) -> first of the two 4-channel slabs of k-step j (second slab SLABF floats further).
+// ---------------------------------------------------------------------------------------------
+template <class L, class P, class X, class AKstep, class Epi>
+FE_DEV void tc_layer(X& x, int tid, int ci0, AKstep a_kstep, Epi epi) {
+    constexpr int S = P::S;
+    for (int c = 0; c < L::NCHUNK; ++c) {
+        const int tiles = (c == L::NCHUNK - 1) ? L::NTILE - c * L::TPC : L::TPC;
+        const float* w = x.acquire(ci0 + c, tiles * L::TILE);
+        if (tid == 0) {
+            x.mma_fence();
+            for (int i = 0; i < tiles; ++i) {
+                const int tile = c * L::TPC + i, t = tile / L::NKS, j = tile % L::NKS;
+                const int shift = (L::TAPS == 3 ? t : 1) * S;          // first data slot is S; tap t reads position f + t - 1
+#pragma unroll
+                for (int mt = 0; mt < L::NMT; ++mt) {
+                    const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
+                    x.mma(a_kstep(j) + (shift + mt * 128) * 4, P::SLABF, w + i * L::TILE, L::NP * 4, L::NP, mt * L::NP, tile > 0, rows);
+                }
+            }
+        }
+        x.release_mma(ci0 + c);
+    }
+    x.acc_commit_wait();
+    constexpr int GH = (L::NG + 1) / 2;
+    const int half = tid >> 7, m = (((tid >> 5) & 3) << 5) + (tid & 31);
+#pragma unroll
+    for (int mt = 0; mt < L::NMT; ++mt) {
+        float v[GH][4];
+#pragma unroll
+        for (int i = 0; i < GH; ++i) {
+            const int g = half * GH + i;
+            if (g < L::NG) x.tmem_ld4(tid, mt * L::NP + 4 * g, v[i]);
+        }
+        x.tmem_ld_wait();
+        const int gp = mt * 128 + m;
+        if (gp < L::NPOS) {
+#pragma unroll
+            for (int i = 0; i < GH; ++i) {
+                const int g = half * GH + i;
+                if (g < L::NG) epi(gp, g, v[i]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The frame.
 // ---------------------------------------------------------------------------------------------
@@ -230,6 +338,38 @@ template <class P> struct Frame {
     static constexpr int TAP_TOTAL = TAP_SPECHAT + 2 * FIN;
 
     struct PwAcc { float v[P::PwCat::CT][P::PwCat::PT]; };
+    static constexpr int SLABF = P::SLABF;
+
+    // float offset of compressed-spectrum / mask element (c = re|im, stream s, bin k) and of activation element
+    // (channel c, stream s, position f) in the conv-section buffers of this variant (Geo1 or tensor-core layout)
+    FE_DEV static int spec_off(int c, int s, int k) {
+        if constexpr (P::TC) return c * SLABF + (((k >> 2) + 1) * S + s) * 4 + (k & 3);
+        else return (c * 4 + (k & 3)) * CP1 + s * P1 + 4 + (k >> 2);
+    }
+    FE_DEV static int act_off(int c, int s, int f) {
+        if constexpr (P::TC) return (c >> 2) * SLABF + ((f + 1) * S + s) * 4 + (c & 3);
+        else return c * CP1 + s * P1 + 4 + f;
+    }
+
+    // Tensor-core layer epilogue: bias (+SiLU), TF32 rounding for the next MMA, one float4 per 4-channel group;
+    // also re-zeroes the S halo slots at both ends of the slab (the buffers are aliased between layers).
+    struct TcEpiAct {
+        float* dst; const float* bias; float* gdst; bool act; bool round;
+        FE_DEV void operator()(int gp, int g, const float* v) const {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = v[e] + ldg(bias + 4 * g + e);
+                t = act ? silu(t) : t;
+                o[e] = round ? tf32_rna(t) : t;
+            }
+            const int off = g * SLABF + (S + gp) * 4;
+            st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
+            if (gp < S) st4(dst + g * SLABF + gp * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            if (gp >= S * F1 - S) st4(dst + g * SLABF + (gp + 2 * S) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
+        }
+    };
 
     // Geo1 output row: bias (+SiLU), data columns, the 4 zero pad columns and the buffer tail.
     struct EpiGeo1 {
@@ -320,7 +460,7 @@ template <class P> struct Frame {
 
     template <class X> FE_DEV static float* skip_dst(X& x, int i) {
         if (i < P::SKIP_SMEM) return x.sm + P::SM_SK + i * ACT;
-        return x.sm + P::SM_W + (((E - i + 1) & 1) ? ACT : 0);
+        return x.sm + P::SM_W + (((E - i + 1) & 1) ? (P::NWORK - 1) * ACT : 0);   // spilled: W0 / last work buffer
     }
     template <class X> FE_DEV static float* skip_gdst(X& x, int i) {
         return (i < P::SKIP_SMEM) ? nullptr : x.gs + (size_t)(i - P::SKIP_SMEM) * ACT;
@@ -392,9 +532,8 @@ template <class P> struct Frame {
                     float mag = sqrtf(re * re + im * im);
                     mag = mag < 1.0e-5f ? 1.0e-5f : mag;
                     float g = powf(mag, comp_e);
-                    int q = k & 3, m = k >> 2;
-                    SPEC[q * CP1 + s * P1 + 4 + m] = re * g;
-                    SPEC[(4 + q) * CP1 + s * P1 + 4 + m] = im * g;
+                    SPEC[spec_off(0, s, k)] = re * g;
+                    SPEC[spec_off(1, s, k)] = im * g;
                 }
             });
         } else {
@@ -409,9 +548,8 @@ template <class P> struct Frame {
                     float mag = sqrtf(re * re + im * im);
                     mag = mag < 1.0e-5f ? 1.0e-5f : mag;
                     float g = powf(mag, comp_e);
-                    int q = k & 3, m = k >> 2;
-                    SPEC[q * CP1 + s * P1 + 4 + m] = re * g;
-                    SPEC[(4 + q) * CP1 + s * P1 + 4 + m] = im * g;
+                    SPEC[spec_off(0, s, k)] = re * g;
+                    SPEC[spec_off(1, s, k)] = im * g;
                 }
             });
         }
@@ -419,13 +557,13 @@ template <class P> struct Frame {
             x.phase(PH_DBG, [&](int tid) {
                 for (int idx = tid; idx < 2 * FIN; idx += NT) {
                     int c = idx / FIN, k = idx % FIN;
-                    prm.dbg[off + idx] = buf[(c * 4 + (k & 3)) * CP1 + 4 + (k >> 2)];
+                    prm.dbg[off + idx] = buf[spec_off(c, 0, k)];
                 }
             });
         };
         auto dump_geo1 = [&](const float* buf, int off) {
             x.phase(PH_DBG, [&](int tid) {
-                for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = buf[(idx / F1) * CP1 + 4 + idx % F1];
+                for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = buf[act_off(idx / F1, 0, idx % F1)];
             });
         };
         auto dump_rf = [&](const float* buf, int off) {
@@ -439,17 +577,33 @@ template <class P> struct Frame {
         const float* src = SPEC;
         for (int i = 0; i <= E; ++i) {
             float* dst = skip_dst(x, i);
-            EpiGeo1 epi{dst, aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1)), skip_gdst(x, i), true};
-            if (i == 0) {
-                x.phase(PH_ENC_PRE, [&](int tid) {
-                    pos_gemm<typename P::EncPre>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
-                });
-                ci += P::EncPre::NCHUNK;
+            const float* bias = aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1));
+            if constexpr (P::TC) {
+                TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true};
+                if (i == 0) {
+                    x.phase(PH_ENC_PRE, [&](int tid) {
+                        tc_layer<typename P::TEncPre, P>(x, tid, ci, [&](int) { return src; }, epi);
+                    });
+                    ci += P::TEncPre::NCHUNK;
+                } else {
+                    x.phase(PH_ENC, [&](int tid) {
+                        tc_layer<typename P::TConv3, P>(x, tid, ci, [&](int j) { return src + 2 * j * SLABF; }, epi);
+                    });
+                    ci += P::TConv3::NCHUNK;
+                }
             } else {
-                x.phase(PH_ENC, [&](int tid) {
-                    pos_gemm<typename P::Conv3>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
-                });
-                ci += P::Conv3::NCHUNK;
+                EpiGeo1 epi{dst, bias, skip_gdst(x, i), true};
+                if (i == 0) {
+                    x.phase(PH_ENC_PRE, [&](int tid) {
+                        pos_gemm<typename P::EncPre>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
+                    });
+                    ci += P::EncPre::NCHUNK;
+                } else {
+                    x.phase(PH_ENC, [&](int tid) {
+                        pos_gemm<typename P::Conv3>(x, tid, ci, [&](int k) { return src + k * CP1; }, P1, 4, epi);
+                    });
+                    ci += P::Conv3::NCHUNK;
+                }
             }
             if (dbg) dump_geo1(dst, TAP_ENC + i * C1 * F1);
             src = dst;
@@ -458,14 +612,26 @@ template <class P> struct Frame {
         // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
         float* Y1 = AB + P::O_Y1;
         float* XR = AB + P::O_XR;
-        x.phase(PH_LIN_PRE, [&](int tid) {
-            row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
+        if constexpr (P::TC) {
+            x.phase(PH_LIN_PRE, [&](int tid) {
+                row_gemm_k1<typename P::LinPreT>(x, tid, ci, [&](int r) { return src + act_off(r / S, r % S, 0); }, S * 4,
+                                                 [&](int r, int o0, const float* v) {
 #pragma unroll
-                for (int j = 0; j < P::LinPre::NO; j += 4)
-                    if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    for (int j = 0; j < P::LinPreT::NO; j += 4)
+                        if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                });
             });
-        });
-        ci += P::LinPre::NCHUNK;
+            ci += P::LinPreT::NCHUNK;
+        } else {
+            x.phase(PH_LIN_PRE, [&](int tid) {
+                row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
+#pragma unroll
+                    for (int j = 0; j < P::LinPre::NO; j += 4)
+                        if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                });
+            });
+            ci += P::LinPre::NCHUNK;
+        }
         x.phase(PH_RF_PRE, [&](int tid) {
             pos_gemm<typename P::RfPre>(x, tid, ci, [&](int k) { return Y1 + k * PR; }, F2P, 0,
                                         [&](int co, int s, int f, const float* v) {
@@ -639,15 +805,35 @@ template <class P> struct Frame {
 
         // ================= rf_post: Linear(F2->F1), 1x1 conv =================
         float* Zb = AB + P::O_Z;
-        x.phase(PH_LIN_POST, [&](int tid) {
-            row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
+        if constexpr (P::TC) {
+            x.phase(PH_LIN_POST, [&](int tid) {
+                row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
+                    float* zr = Zb + act_off(r / S, r % S, 0);
 #pragma unroll
-                for (int j = 0; j < P::LinPost::NO; j += 4)
-                    if (o0 + j < F1) st4(Zb + r * P1 + 4 + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    for (int j = 0; j < P::LinPost::NO; ++j)
+                        if (o0 + j < F1) zr[(o0 + j) * S * 4] = tf32_rna(v[j]);
+                });
+                // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
+                for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {
+                    const int c = C2 + idx / (S * F1), r = idx % (S * F1);
+                    Zb[act_off(c, r % S, r / S)] = 0.f;
+                }
             });
-        });
-        ci += P::LinPost::NCHUNK;
-        {
+            ci += P::LinPost::NCHUNK;
+            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
+            x.phase(PH_RF_POST, [&](int tid) {
+                tc_layer<typename P::TRfPost, P>(x, tid, ci, [&](int j) { return Zb + 2 * j * SLABF; }, epi);
+            });
+            ci += P::TRfPost::NCHUNK;
+        } else {
+            x.phase(PH_LIN_POST, [&](int tid) {
+                row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
+#pragma unroll
+                    for (int j = 0; j < P::LinPost::NO; j += 4)
+                        if (o0 + j < F1) st4(Zb + r * P1 + 4 + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                });
+            });
+            ci += P::LinPost::NCHUNK;
             EpiGeo1 epi{W1, aux + A.rf_post_b, nullptr, false};
             x.phase(PH_RF_POST, [&](int tid) {
                 pos_gemm<typename P::RfPost>(x, tid, ci, [&](int kk) { return Zb + kk * CP1; }, P1, 4, epi);
@@ -669,10 +855,28 @@ template <class P> struct Frame {
                 });
                 skip = W0;
             }
-            // 1x1 conv over cat([x, skip]) + SiLU; stored to W0 after a barrier (W0 may hold the skip)
-            {
+            const float* b1 = aux + (i < E ? A.dec1_b(i) : A.dp_b);
+            if constexpr (P::TC) {
+                // 1x1 conv over cat([x, skip]) + SiLU: k-steps 0..C1/8-1 read x (W1), the rest read the skip tensor.
+                // All MMAs complete before any epilogue thread stores, so writing W0 (which may hold the skip) is safe.
+                TcEpiAct epi{W0, b1, nullptr, true, true};
+                x.phase(PH_PWCAT, [&](int tid) {
+                    tc_layer<typename P::TPwCat, P>(x, tid, ci, [&](int j) {
+                        return j < C1 / 8 ? (const float*)W1 + 2 * j * SLABF : skip + 2 * (j - C1 / 8) * SLABF; }, epi);
+                });
+                ci += P::TPwCat::NCHUNK;
+                if (i < E) {
+                    TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};
+                    x.phase(PH_DEC, [&](int tid) {
+                        tc_layer<typename P::TConv3, P>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, epi2);
+                    });
+                    ci += P::TConv3::NCHUNK;
+                    if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
+                }
+            } else {
+                // 1x1 conv over cat([x, skip]) + SiLU; stored to W0 after a barrier (W0 may hold the skip)
                 using L = typename P::PwCat;
-                EpiGeo1 epi{W0, aux + (i < E ? A.dec1_b(i) : A.dp_b), nullptr, true};
+                EpiGeo1 epi{W0, b1, nullptr, true};
                 auto xrow = [&](int kk) { return kk < C1 ? W1 + kk * CP1 : skip + (kk - C1) * CP1; };
                 x.template phase2<PwAcc>(PH_PWCAT,
                     [&](int tid, PwAcc& a) {
@@ -693,35 +897,43 @@ template <class P> struct Frame {
                         }
                     });
                 ci += L::NCHUNK;
-            }
-            if (i < E) {
-                EpiGeo1 epi{W1, aux + A.dec2_b(i), nullptr, true};
-                x.phase(PH_DEC, [&](int tid) {
-                    pos_gemm<typename P::Conv3>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4, epi);
-                });
-                ci += P::Conv3::NCHUNK;
-                if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
+                if (i < E) {
+                    EpiGeo1 epi2{W1, aux + A.dec2_b(i), nullptr, true};
+                    x.phase(PH_DEC, [&](int tid) {
+                        pos_gemm<typename P::Conv3>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4, epi2);
+                    });
+                    ci += P::Conv3::NCHUNK;
+                    if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
+                }
             }
         }
         // transposed conv as a 3-tap conv to 8 virtual channels (o*4 + q) -> MASK (in W1)
         float* MASK = W1;
-        x.phase(PH_CONVT, [&](int tid) {
-            pos_gemm<typename P::ConvT>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4,
-                                        [&](int vo, int s, int f, const float* v) {
-                                            const float b = ldg(aux + A.convt_b + vo);
-                                            st4(MASK + vo * CP1 + s * P1 + 4 + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
-                                        });
-        });
-        ci += P::ConvT::NCHUNK;
+        if constexpr (P::TC) {
+            TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};
+            x.phase(PH_CONVT, [&](int tid) {
+                tc_layer<typename P::TConvT, P>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, epi);
+            });
+            ci += P::TConvT::NCHUNK;
+        } else {
+            x.phase(PH_CONVT, [&](int tid) {
+                pos_gemm<typename P::ConvT>(x, tid, ci, [&](int kk) { return W0 + kk * CP1; }, P1, 4,
+                                            [&](int vo, int s, int f, const float* v) {
+                                                const float b = ldg(aux + A.convt_b + vo);
+                                                st4(MASK + vo * CP1 + s * P1 + 4 + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                            });
+            });
+            ci += P::ConvT::NCHUNK;
+        }
         x.check_frame(ci);
         if (dbg) dump_spec(MASK, TAP_MASK);
 
         // ================= mask * spectrum, decompression =================
         x.phase(PH_MASK, [&](int tid) {
             for (int idx = tid; idx < S * M; idx += NT) {
-                const int s = idx / M, k = idx % M, q = k & 3, m = k >> 2, gs = x.s0 + s;
-                const int o = q * CP1 + s * P1 + 4 + m;
-                const float xr = SPEC[o], xi = SPEC[o + 4 * CP1], mr = MASK[o], mi = MASK[o + 4 * CP1];
+                const int s = idx / M, k = idx % M, gs = x.s0 + s;
+                const int o0 = spec_off(0, s, k), o1 = spec_off(1, s, k);
+                const float xr = SPEC[o0], xi = SPEC[o1], mr = MASK[o0], mi = MASK[o1];
                 const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
                 if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + k] = yr; prm.dbg[TAP_SPECHAT + FIN + k] = yi; }
                 const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);

@@ -8,6 +8,7 @@
 // PosGemm / RowGemm tiles of fe_plan.h read (one contiguous slice per ring chunk).
 #pragma once
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -89,6 +90,44 @@ template <class P> class Packer {
         off_ += L::FLOATS;
     }
 
+    // round-to-nearest (ties away) to TF32: what cvt.rna.tf32.f32 does; the tensor core then reads the value exactly
+    static float tf32_rna(float x) {
+        uint32_t u;
+        std::memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;
+        std::memcpy(&x, &u, 4);
+        return x;
+    }
+    // tensor-core tiles, w(n, k, tap): tile (tap, k-step j) = [2][NP][4] holding W[n][8j + 4*kc2 + e][tap]
+    template <class L, class W> void tc(W w) {
+        for (int c = 0; c < L::NCHUNK; ++c) {
+            int tiles = cmin(L::TPC, L::NTILE - c * L::TPC);
+            table_.push_back((int)(off_ + (long)c * L::TPC * L::TILE));
+            table_.push_back(tiles * L::TILE);
+        }
+        for (int tile = 0; tile < L::NTILE; ++tile) {
+            const int t = tile / L::NKS, j = tile % L::NKS;
+            for (int kc2 = 0; kc2 < 2; ++kc2)
+                for (int n = 0; n < L::NP; ++n)
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 8 * j + 4 * kc2 + e;
+                        blob_[off_ + (long)tile * L::TILE + (kc2 * L::NP + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(n, k, t)) : 0.f;
+                    }
+        }
+        off_ += L::FLOATS;
+    }
+    // w(o, k), one ring row per k: [og][NO]
+    template <class L, class W> void rowk1(W w) {
+        for (int c = 0; c < L::NCHUNK; ++c) {
+            int rows = cmin(L::KC, L::K - c * L::KC);
+            table_.push_back((int)(off_ + (long)c * L::KC * L::ROW));
+            table_.push_back(rows * L::ROW);
+        }
+        for (int k = 0; k < L::K; ++k)
+            for (int o = 0; o < L::NOG * L::NO; ++o) blob_[off_ + (long)k * L::ROW + o] = o < L::NOUT ? w(o, k) : 0.f;
+        off_ += L::FLOATS;
+    }
+
 public:
     explicit Packer(std::vector<float>& blob) : blob_(blob), off_(0) {}
 
@@ -138,44 +177,66 @@ public:
         cp(A.rf_post_b, cw.rf_post_b, C1);
         for (int i = 0; i < C::E; ++i) { cp(A.dec1_b(i), cw.dec_b1[i], C1); cp(A.dec2_b(i), cw.dec_b2[i], C1); }
         cp(A.dp_b, cw.dp_b, C1);
-        for (int vo = 0; vo < 8; ++vo) blob_[A.convt_b + vo] = cw.dp_bt[vo / 4];
+        for (int vo = 0; vo < 8; ++vo) blob_[A.convt_b + vo] = cw.dp_bt[vo / 4];   // entries 8..15 stay zero (tensor-core N padding)
 
         // ---- ring section, execution order (must match fe_kernel.cuh::frame) ----
         off_ = A.ring;
         table_.clear();
-        // enc_pre as a 3-tap conv over 8 virtual channels v = c*4 + q holding x[c][4m + q]:
-        // original tap k = 4*dj + q + 2 (model.py:15-59, weight index [co][(k%4)*2 + c][k/4])
-        pos<typename P::EncPre>([&](int, int co, int v, int t) {
+        auto w_enc_pre = [&](int co, int v, int t) {
+            // enc_pre as a 3-tap conv over 8 virtual channels v = c*4 + q holding x[c][4m + q]:
+            // original tap k = 4*dj + q + 2 (model.py:15-59, weight index [co][(k%4)*2 + c][k/4])
             int c = v / 4, q = v % 4, k = 4 * (t - 1) + q + 2;
             return (k >= 0 && k < 8) ? cw.enc_pre_w[(co * 8 + (k % 4) * 2 + c) * 2 + k / 4] : 0.f;
-        });
-        for (int i = 0; i < C::E; ++i)
-            pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
-        row<typename P::LinPre>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
-        pos<typename P::RfPre>([&](int, int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
-        for (int k = 0; k < C::K; ++k) {
-            const auto& b = cw.blk[k];
-            pos<typename P::Gru>([&](int set, int c, int ci, int) {
-                return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
-            });
-            pos<typename P::Fc>([&](int, int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
-            for (int g = 0; g < P::NQG; ++g)
-                pos<typename P::Qkv>([&](int, int co, int ci, int) { return b.qkv_w[(g * 3 * C::HD * P::HG + co) * C2 + ci]; });
-            pos<typename P::Fc>([&](int, int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
-        }
-        row<typename P::LinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
-        pos<typename P::RfPost>([&](int, int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
-        for (int i = 0; i < C::E; ++i) {
-            pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });
-            pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; });
-        }
-        pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; });
-        // transposed conv as a 3-tap conv to 8 virtual output channels vo = o*4 + q (bin 4m + q):
-        // original tap k = -4*dj + q + 2 (model.py:62-95)
-        pos<typename P::ConvT>([&](int, int vo, int ci, int t) {
+        };
+        auto w_convt = [&](int vo, int ci, int t) {
+            // transposed conv as a 3-tap conv to 8 virtual output channels vo = o*4 + q (bin 4m + q):
+            // original tap k = -4*dj + q + 2 (model.py:62-95)
             int o = vo / 4, q = vo % 4, k = -4 * (t - 1) + q + 2;
             return (k >= 0 && k < 8) ? cw.dp_wt[(ci * 2 + o) * 8 + k] : 0.f;
-        });
+        };
+        auto blocks = [&]() {
+            for (int k = 0; k < C::K; ++k) {
+                const auto& b = cw.blk[k];
+                pos<typename P::Gru>([&](int set, int c, int ci, int) {
+                    return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
+                });
+                pos<typename P::Fc>([&](int, int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
+                for (int g = 0; g < P::NQG; ++g)
+                    pos<typename P::Qkv>([&](int, int co, int ci, int) { return b.qkv_w[(g * 3 * C::HD * P::HG + co) * C2 + ci]; });
+                pos<typename P::Fc>([&](int, int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
+            }
+        };
+        if constexpr (P::TC) {
+            tc<typename P::TEncPre>(w_enc_pre);
+            for (int i = 0; i < C::E; ++i)
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
+            rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
+            pos<typename P::RfPre>([&](int, int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
+            blocks();
+            row<typename P::LinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+            tc<typename P::TRfPost>([&](int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
+            for (int i = 0; i < C::E; ++i) {
+                tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; });
+            }
+            tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; });
+            tc<typename P::TConvT>(w_convt);
+        } else {
+            pos<typename P::EncPre>([&](int, int co, int v, int t) { return w_enc_pre(co, v, t); });
+            for (int i = 0; i < C::E; ++i)
+                pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
+            row<typename P::LinPre>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
+            pos<typename P::RfPre>([&](int, int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
+            blocks();
+            row<typename P::LinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+            pos<typename P::RfPost>([&](int, int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
+            for (int i = 0; i < C::E; ++i) {
+                pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });
+                pos<typename P::Conv3>([&](int, int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; });
+            }
+            pos<typename P::PwCat>([&](int, int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; });
+            pos<typename P::ConvT>([&](int, int vo, int ci, int t) { return w_convt(vo, ci, t); });
+        }
         if (off_ != A.total || (int)table_.size() != 2 * P::NCHUNK_FRAME) throw std::runtime_error("fe_pack: schedule mismatch");
         std::memcpy(&blob_[A.table], table_.data(), table_.size() * sizeof(int));
     }

@@ -111,6 +111,46 @@ struct RowGemm {
 };
 
 // ----------------------------------------------------------------------------------------------
+// "Tensor-core GEMM" (tcgen05.mma kind::tf32, accumulators in TMEM): D[pos][n] = sum_{k,tap} X[k][pos+tap-1] W[n][k][tap].
+// Activations live in shared memory as K-major, un-swizzled UMMA operands:  X[k/4][slot][k%4]  with
+// slot = (f + 1) * S + s  (streams interleaved, S zero slots before and after the data), so rows are 16 B
+// apart and a shift by one frequency position is a start-address offset of S*16 bytes: the three taps
+// of a k=3 conv are three MMAs on the same buffer.  M = 128 rows per MMA (NMT tiles of 128 positions).
+// Weights stream through the ring as tiles of one (tap, 8-wide k-step):  [2][NP][4]  (K-major B operand),
+// NP = N rounded up to 16, zero rows / zero k beyond the real sizes, values pre-rounded to TF32.
+// ----------------------------------------------------------------------------------------------
+template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_>
+struct TcGemm {
+    static constexpr int NPOS = NPOS_, N = N_, K = K_, TAPS = TAPS_;
+    static constexpr int NP = round_up(N, 16), KP = round_up(K, 8);
+    static constexpr int NKS = KP / 8;                 // k-steps per tap
+    static constexpr int NTILE = TAPS * NKS;
+    static constexpr int TILE = NP * 8;                // floats per tile
+    static_assert(TILE <= CHUNK_, "one weight tile must fit a ring chunk");
+    static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
+    static constexpr int NCHUNK = cdiv(NTILE, TPC);
+    static constexpr int FLOATS = NTILE * TILE;
+    static constexpr int NMT = cdiv(NPOS, 128);        // 128-row M tiles
+    static constexpr int NG = cdiv(N, 4);              // output channel groups of 4
+    static_assert(NMT * NP <= 256, "accumulators exceed the TMEM allocation");
+};
+
+// Row GEMM reading one k per step (frequency-axis linear on a tensor-core-layout activation, where
+// consecutive frequencies are not contiguous).  Ring rows: one per k: [og][NO].
+template <int NROWS_, int K_, int NOUT_, int NW_, int CHUNK_>
+struct RowGemmK1 {
+    static constexpr int NROWS = NROWS_, K = K_, NOUT = NOUT_, NW = NW_;
+    static constexpr int RT = cdiv(NROWS, 32);
+    static constexpr int NO = round_up(cdiv(NOUT, NW), 4);
+    static constexpr int NOG = cdiv(NOUT, NO);
+    static_assert(NOG <= NW && RT * NO <= 64, "row gemm tile too large: lower S");
+    static constexpr int ROW = NOG * NO;
+    static constexpr int KC = cmax(1, cmin(K, CHUNK_ / ROW));
+    static constexpr int NCHUNK = cdiv(K, KC);
+    static constexpr int FLOATS = K * ROW;
+};
+
+// ----------------------------------------------------------------------------------------------
 // Per-(config, S) tuning.  Primary template = generic heuristics; specialise to override.
 // ----------------------------------------------------------------------------------------------
 template <class C, int S> struct Tune {
@@ -127,10 +167,11 @@ template <class C, int S> struct Tune {
     static constexpr int SKIP_SMEM_MAX = C::E + 1;
 };
 
-template <class C, int S_>
+template <class C, int S_, bool TC_ = false>
 struct Plan {
     using Cf = C;
     static constexpr int S = S_;
+    static constexpr bool TC = TC_;                    // conv-type contractions on tcgen05 (TF32) instead of the FMA pipe
     using T = Tune<C, S_>;
     static constexpr int NW = T::NW, NT = NW * 32, NTHREADS = NT + 32;
     static constexpr int CHUNK = T::CHUNK, STAGES = T::STAGES;
@@ -138,8 +179,14 @@ struct Plan {
     //      columns of the next row are the right halo, +4 floats after the very last row ----
     static constexpr int P1 = C::F1 + 4;
     static constexpr int CP1 = S * P1;                 // channel pitch
-    static constexpr int ACT = C::C1 * CP1 + 4;
-    static constexpr int SPECF = 8 * CP1 + 4;          // compressed spectrum as 8 virtual channels (c*4+q)
+    // ---- tensor-core geometry ("GeoT"): [C/4][SLOTS][4], slot = (f+1)*S + s ----
+    static constexpr int SLOTS = (C::F1 + 2) * S;
+    static constexpr int SLABF = SLOTS * 4;            // floats per 4-channel slab
+    static constexpr int C2P = round_up(C::C2, 8);     // rf_post conv input channels padded to a k-step
+    static constexpr int ACT = TC ? (C::C1 / 4) * SLABF : C::C1 * CP1 + 4;
+    static constexpr int SPECF = TC ? 2 * SLABF : 8 * CP1 + 4;   // compressed spectrum: 8 virtual channels (c*4+q)
+    static constexpr int ZBF = TC ? (C2P / 4) * SLABF : C::C2 * CP1;   // rf_post linear output
+    static_assert(C::C1 % 8 == 0, "C1 must be a multiple of 8");
     // ---- RNNFormer geometry: [C2][S][F2P] channel-major, F2P = 4*odd ----
     static constexpr int F2P = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
     static constexpr int PR = S * F2P;
@@ -156,12 +203,12 @@ struct Plan {
     static constexpr int O_Y1 = 0;                     // rf_pre linear output [C1][PR]
     static constexpr int O_Z = 0;                      // rf_post linear output [C2][S][P1]
     static_assert(XRS + cmax(XRS, QKVS) <= O_XR, "RNNFormer scratch does not fit: lower Tune::HG");
-    static_assert(C::C1 * PR <= O_XR && C::C1 * PR <= ACT, "rf_pre scratch does not fit");
-    static_assert(C::C2 * CP1 <= O_XR, "rf_post scratch does not fit");
+    static_assert(C::C1 * PR <= O_XR && C::C1 * PR <= (NWORK - 1) * ACT, "rf_pre scratch does not fit");
+    static_assert(ZBF <= O_XR, "rf_post scratch does not fit");
     static_assert(S * C::N_FFT <= ACT, "FFT buffers do not fit");
     // ---- shared memory map (float offsets) ----
     static constexpr int NSK = C::E + 1;
-    static constexpr int SM_FIXED = AB + SPECF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES;
+    static constexpr int SM_FIXED = AB + SPECF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES + 4;
     static_assert(SM_FIXED <= 227 * 256, "shared memory plan exceeds 227 KB even with every skip tensor spilled");
     static constexpr int SKIP_SMEM = cmax(0, cmin(cmin(NSK, T::SKIP_SMEM_MAX), (227 * 256 - SM_FIXED) / ACT));
     static constexpr int SM_SK = 0;
@@ -171,7 +218,7 @@ struct Plan {
     static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
     static constexpr int SM_RING = SM_OLA + S * C::N_FFT;
     static constexpr int SM_BAR = SM_RING + STAGES * CHUNK;    // 2*STAGES mbarriers (8 bytes each)
-    static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES;
+    static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES + 4;   // + accumulator-ready mbarrier, TMEM base slot
     static_assert(SM_RING % 4 == 0 && SM_BAR % 2 == 0, "alignment");
     static constexpr int SMEM_BYTES = SM_TOTAL * 4;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
@@ -192,13 +239,26 @@ struct Plan {
     using RfPost = PosGemm<S * C::F1, C::F1, C::C1, C::C2, 1, 4, T::CT_CONV, NW, CHUNK>;
     static_assert(PwCat::NPASS == 1, "the concatenating 1x1 conv stores in place after a barrier: one pass only");
 
+    // tensor-core versions of the conv-type layers (TC variants only)
+    using TEncPre = TcGemm<S * C::F1, C::C1, 8, 3, CHUNK>;
+    using TConv3 = TcGemm<S * C::F1, C::C1, C::C1, 3, CHUNK>;
+    using TPwCat = TcGemm<S * C::F1, C::C1, 2 * C::C1, 1, CHUNK>;
+    using TConvT = TcGemm<S * C::F1, 8, C::C1, 3, CHUNK>;
+    using TRfPost = TcGemm<S * C::F1, C::C1, C::C2, 1, CHUNK>;
+    using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
+
     static constexpr int BLK_CHUNKS = Gru::NCHUNK + 2 * Fc::NCHUNK + NQG * Qkv::NCHUNK;
-    static constexpr int NCHUNK_FRAME = EncPre::NCHUNK + C::E * Conv3::NCHUNK + LinPre::NCHUNK + RfPre::NCHUNK +
-                                        C::K * BLK_CHUNKS + LinPost::NCHUNK + RfPost::NCHUNK +
-                                        C::E * (PwCat::NCHUNK + Conv3::NCHUNK) + PwCat::NCHUNK + ConvT::NCHUNK;
-    static constexpr long RING_FLOATS = (long)EncPre::FLOATS + (long)C::E * Conv3::FLOATS + LinPre::FLOATS + RfPre::FLOATS +
-                                        (long)C::K * (Gru::FLOATS + 2 * Fc::FLOATS + NQG * Qkv::FLOATS) + LinPost::FLOATS +
-                                        RfPost::FLOATS + (long)C::E * (PwCat::FLOATS + Conv3::FLOATS) + PwCat::FLOATS + ConvT::FLOATS;
+    static constexpr long BLK_FLOATS = (long)Gru::FLOATS + 2 * Fc::FLOATS + NQG * Qkv::FLOATS;
+    static constexpr int NCHUNK_FRAME = TC
+        ? TEncPre::NCHUNK + C::E * TConv3::NCHUNK + LinPreT::NCHUNK + RfPre::NCHUNK + C::K * BLK_CHUNKS + LinPost::NCHUNK +
+              TRfPost::NCHUNK + C::E * (TPwCat::NCHUNK + TConv3::NCHUNK) + TPwCat::NCHUNK + TConvT::NCHUNK
+        : EncPre::NCHUNK + C::E * Conv3::NCHUNK + LinPre::NCHUNK + RfPre::NCHUNK + C::K * BLK_CHUNKS + LinPost::NCHUNK +
+              RfPost::NCHUNK + C::E * (PwCat::NCHUNK + Conv3::NCHUNK) + PwCat::NCHUNK + ConvT::NCHUNK;
+    static constexpr long RING_FLOATS = TC
+        ? (long)TEncPre::FLOATS + (long)C::E * TConv3::FLOATS + LinPreT::FLOATS + RfPre::FLOATS + (long)C::K * BLK_FLOATS +
+              LinPost::FLOATS + TRfPost::FLOATS + (long)C::E * (TPwCat::FLOATS + TConv3::FLOATS) + TPwCat::FLOATS + TConvT::FLOATS
+        : (long)EncPre::FLOATS + (long)C::E * Conv3::FLOATS + LinPre::FLOATS + RfPre::FLOATS + (long)C::K * BLK_FLOATS +
+              LinPost::FLOATS + RfPost::FLOATS + (long)C::E * (PwCat::FLOATS + Conv3::FLOATS) + PwCat::FLOATS + ConvT::FLOATS;
 
     // ---- blob layout (float offsets): [aux tables + biases | chunk table | ring section] ----
     // Per-layer arrays are affine (base + index * stride) so that device code never indexes a
@@ -243,7 +303,7 @@ struct Plan {
         }
         a.rf_post_b = take(C::C1);
         a.dec2_rel = round_up(C::C1, 4); a.dec_bs = 2 * a.dec2_rel; a.dec_b0 = take(C::E * a.dec_bs);
-        a.dp_b = take(C::C1); a.convt_b = take(8);
+        a.dp_b = take(C::C1); a.convt_b = take(16);
         a.table = take(2 * NCHUNK_FRAME);
         a.ring = o;
         a.total = o + (int)RING_FLOATS;

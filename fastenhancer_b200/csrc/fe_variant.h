@@ -9,7 +9,7 @@
 namespace fe {
 
 struct VariantOps {
-    int cfg_id, S;
+    int cfg_id, S, tc;
     ShapeKey shape;
     int smem_bytes, nthreads, gs_floats, state_floats, tap_floats, nchunk_frame;
     long blob_floats;

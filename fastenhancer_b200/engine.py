@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "fe_last_error", "fe_weight_count", "fe_state_floats", "fe_create", "fe_destroy", "fe_state_create",
     "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
     "fe_spec", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
-    "fe_stream_taps", "fe_profile_slots", "fe_set_profile",
+    "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision",
 )
 
 
@@ -79,6 +79,8 @@ def load_library(build_if_missing: bool = True):
     lib.fe_stream_taps.argtypes = [vp, vp, fp, fp, ip, ll, ll, fp, ip, vp]
     lib.fe_profile_slots.argtypes = []
     lib.fe_set_profile.argtypes = [vp, vp]
+    lib.fe_set_precision.argtypes = [vp, ip]
+    lib.fe_get_precision.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -127,7 +129,10 @@ class State:
 class Engine:
     """One folded FastEnhancer model resident on one B200."""
 
-    def __init__(self, cfg: FEConfig, canonical: np.ndarray, device: tp.Union[int, str, None] = None):
+    def __init__(self, cfg: FEConfig, canonical: np.ndarray, device: tp.Union[int, str, None] = None,
+                 precision: tp.Optional[str] = None):
+        """``precision``: "tf32" (default; conv-type contractions on tcgen05 tensor cores with TF32 operands, fp32
+        accumulate) or "fp32" (everything on the fp32 FMA pipe).  ``FE_PRECISION`` in the environment sets the default."""
         import torch
         cfg.validate()
         if not torch.cuda.is_available():
@@ -148,6 +153,8 @@ class Engine:
                                    ctypes.byref(h)), "fe_create")
         self._h = h
         self.state_floats = int(self._lib.fe_state_floats(ctypes.byref(self._c)))
+        if precision is not None:
+            self.set_precision(precision)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -163,6 +170,15 @@ class Engine:
         if shape is not None and tuple(t.shape) != tuple(shape):
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' or 'fp32'")
+        _check(self._lib.fe_set_precision(self._h, 1 if precision == "fp32" else 0), "fe_set_precision")
+
+    @property
+    def precision(self) -> str:
+        return "fp32" if self._lib.fe_get_precision(self._h) == 1 else "tf32"
 
     def new_state(self, n_streams: int) -> State:
         return State(self, n_streams)

@@ -86,6 +86,15 @@ int fe_spec(fe_engine* e, fe_state* s, const float* spec_in, float* spec_out, in
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
 
+/* Arithmetic of the channel contractions of the conv-type layers (encoder, decoder, 1x1 convs, mask head):
+ *   fp32_exact = 0 (default): tcgen05 tensor cores, TF32 operands (round-to-nearest), fp32 accumulation in TMEM --
+ *                what PyTorch itself does for cuDNN convolutions by default (allow_tf32); waveform error vs the
+ *                fp32 reference ~7e-6 RMS, against the 1e-4 RMS bar;
+ *   fp32_exact = 1: every multiply-add on the fp32 FMA pipe (~6e-8 RMS).
+ * GRU, attention, FFTs, (de)compression and all state are fp32 in both modes. */
+int fe_set_precision(fe_engine* e, int fp32_exact);
+int fe_get_precision(fe_engine* e);               /* 1 = fp32 exact, 0 = TF32 tensor-core contractions */
+
 /* Introspection used by the host wrapper, tests and bench. */
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
 int fe_set_streams_per_cta(fe_engine* e, int s);                /* force a variant (0 = automatic) */

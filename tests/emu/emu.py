@@ -28,7 +28,7 @@ def _load():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         fp = ctypes.POINTER(ctypes.c_float)
-        _lib.fee_run.argtypes = [ctypes.c_int] * 9 + [fp, ctypes.c_int, fp, fp, fp, fp] + [ctypes.c_int] * 3 + \
+        _lib.fee_run.argtypes = [ctypes.c_int] * 10 + [fp, ctypes.c_int, fp, fp, fp, fp] + [ctypes.c_int] * 3 + \
             [ctypes.c_longlong] * 2 + [fp, ctypes.c_int, ctypes.c_float]
         _lib.fee_tap_total.argtypes = [ctypes.c_int] * 8
     return _lib
@@ -61,9 +61,9 @@ def to_canonical(cfg, state):
 
 
 def run(cfg, S, canonical, mode, state_native, inp, out, spec_out=None, n_streams=1, n_hops=1, L=0, ld_in=0, ld_out=0,
-        dbg=None, dbg_hop=-1):
+        dbg=None, dbg_hop=-1, tc=False):
     lib = _load()
-    rc = lib.fee_run(*_shape(cfg), S, _p(np.ascontiguousarray(canonical, np.float32)), mode, _p(state_native), _p(inp), _p(out),
+    rc = lib.fee_run(*_shape(cfg), S, int(tc), _p(np.ascontiguousarray(canonical, np.float32)), mode, _p(state_native), _p(inp), _p(out),
                      _p(spec_out), n_streams, n_hops, L, ld_in, ld_out, _p(dbg), dbg_hop, cfg.input_compression)
     if rc != 0:
         raise RuntimeError(f"fee_run failed rc={rc}")

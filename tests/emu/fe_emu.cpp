@@ -5,6 +5,7 @@
 // index math and the buffer aliasing plan against the oracle on the build container (no GPU).
 // It is never linked into the product library.
 #define FE_EMU 1
+#include <cstdint>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -31,6 +32,27 @@ template <class P> struct EmuCtx {
         for (int t = 0; t < P::NT; ++t) f1(t, acc[t]);
         for (int t = 0; t < P::NT; ++t) f2(t, acc[t]);
     }
+    // ---- tensor-core emulation: TMEM as a [128 lanes][512 columns] array; operands are read through the
+    //      canonical K-major / no-swizzle formula the descriptors encode (row r at r*16 B, k-chunk at LBO) ----
+    std::vector<float> tmem = std::vector<float>(128 * 512, std::nanf(""));
+    static float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
+    void mma_fence() const {}
+    void mma(const float* a, int a_lbo, const float* b, int b_lbo, int NP, int col, bool acc, int rows) {
+        for (int m = 0; m < rows; ++m)
+            for (int n = 0; n < NP; ++n) {
+                float sum = acc ? tmem[m * 512 + col + n] : 0.f;
+                for (int k = 0; k < 8; ++k)
+                    sum += tf32_trunc(a[(k / 4) * a_lbo + m * 4 + (k % 4)]) * tf32_trunc(b[(k / 4) * b_lbo + n * 4 + (k % 4)]);
+                tmem[m * 512 + col + n] = sum;
+            }
+    }
+    void release_mma(int) const {}
+    void acc_commit_wait() const {}
+    void tmem_ld4(int tid, int col, float* v) const {
+        const int row = (((tid >> 5) & 3) << 5) + (tid & 31);
+        for (int e = 0; e < 4; ++e) v[e] = tmem[row * 512 + col + e];
+    }
+    void tmem_ld_wait() const {}
     void next_frame() { ++frames_done; }
     void check_frame(int ci) const { if (ci != P::NCHUNK_FRAME) throw std::runtime_error("emu: frame consumed wrong number of chunks"); }
 };
@@ -54,7 +76,7 @@ template <class P> int run_variant(const float* canonical, KParams prm) {
 
 }  // namespace fe
 
-extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S,
+extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S, int tc,
                        const float* canonical, int mode, float* state, const float* in, float* out, float* spec_out,
                        int n_streams, int n_hops, int L, long long ld_in, long long ld_out, float* dbg, int dbg_hop,
                        float compression)
@@ -65,7 +87,7 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
     prm.ld_in = ld_in; prm.ld_out = ld_out; prm.n_streams = n_streams; prm.n_hops = n_hops; prm.mode = mode; prm.L = L;
     prm.dbg_hop = dbg_hop; prm.compression = compression;
     try {
-#define X(id, CFG, SV) if (fe::shape_matches<fe::CFG>(key) && S == SV) return fe::run_variant<fe::Plan<fe::CFG, SV>>(canonical, prm);
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key) && S == SV && (tc != 0) == TCV) return fe::run_variant<fe::Plan<fe::CFG, SV, TCV>>(canonical, prm);
         FE_ALL_VARIANTS(X)
 #undef X
     } catch (const std::exception& e) {
@@ -78,7 +100,7 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
 extern "C" int fee_tap_total(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads)
 {
     fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
-#define X(id, CFG, SV) if (fe::shape_matches<fe::CFG>(key)) return fe::Frame<fe::Plan<fe::CFG, SV>>::TAP_TOTAL;
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key)) return fe::Frame<fe::Plan<fe::CFG, SV, TCV>>::TAP_TOTAL;
     FE_ALL_VARIANTS(X)
 #undef X
     return -1;

@@ -1,9 +1,10 @@
 """Parity of the fused CUDA kernel (through the C ABI, fastenhancer_b200.engine) against the CPU oracle and
 against the committed golden vectors produced by the reference itself (tools/gen_golden.py).
 
-Tolerance (north-star): <= 1e-4 RMS on the enhanced waveform in fp32; the engine is held to 1e-5 RMS
-(it is fp32 FMA arithmetic in a different summation order, with ex2-based SiLU).  Frame indexing
-(hop alignment, n_fft - hop delay, output lengths, zero Nyquist bin) is checked exactly."""
+Tolerance (north-star): <= 1e-4 RMS on the enhanced waveform against the fp32 reference.  Both arithmetic modes of
+the engine are tested: "fp32" (every multiply-add on the FMA pipe) is held to 1e-5 RMS, "tf32" (the default: conv-type
+contractions on tcgen05 tensor cores with TF32 operands and fp32 accumulation) to 5e-5 RMS.  Frame indexing
+(hop alignment, n_fft - hop delay, output lengths, zero Nyquist bin) is checked exactly in both."""
 import numpy as np
 import pytest
 import torch
@@ -17,14 +18,25 @@ ALL = sorted(PRESETS)
 N_HOPS = 24
 
 
+#                 waveform RMS, state max, tap relative, spectrum relative
+TOL = {"fp32": dict(wav=1e-5, state=2e-5, tap=2e-5, spec=1e-5, spec_abs=1e-4),
+       "tf32": dict(wav=5e-5, state=3e-4, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
+
+
+@pytest.fixture(scope="module", params=["tf32", "fp32"])
+def precision(request):
+    return request.param
+
+
 @pytest.fixture(scope="module")
-def engines(canonical):
+def engines(canonical, precision):
     from fastenhancer_b200.engine import Engine
     cache = {}
 
     def get(name):
         if name not in cache:
-            cache[name] = Engine(PRESETS[name], canonical(name), "cuda:0")
+            cache[name] = Engine(PRESETS[name], canonical(name), "cuda:0", precision=precision)
+            assert cache[name].precision == precision
         return cache[name]
     return get
 
@@ -35,19 +47,19 @@ def _oracle(name, canonical):
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_streaming_matches_reference_golden(name, golden, engines):
+def test_streaming_matches_reference_golden(name, golden, engines, precision):
     """stream_out / stream_state of the golden files come from the reference's own streaming graph."""
     cfg, g, eng = PRESETS[name], golden(name), engines(name)
     x = synthetic_noisy(2, N_HOPS * cfg.hop_size, cfg.sample_rate)
     st = eng.new_state(2)
     y = eng.stream(st, torch.from_numpy(x).cuda()).cpu().numpy()
     assert y.shape == g["stream_out"].shape
-    assert rms(y - g["stream_out"]) < 1e-5
-    assert np.abs(st.export().cpu().numpy() - g["stream_state"]).max() < 2e-5
+    assert rms(y - g["stream_out"]) < TOL[precision]["wav"]
+    assert np.abs(st.export().cpu().numpy() - g["stream_state"]).max() < TOL[precision]["state"]
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_every_variant_matches_oracle(name, canonical, engines):
+def test_every_variant_matches_oracle(name, canonical, engines, precision):
     """every streams-per-CTA variant, ragged stream counts, state carried across launches."""
     cfg, eng, o = PRESETS[name], engines(name), _oracle(name, canonical)
     H = cfg.hop_size
@@ -64,8 +76,8 @@ def test_every_variant_matches_oracle(name, canonical, engines):
             st = eng.new_state(B)
             xd = torch.from_numpy(x).cuda()
             got = torch.cat([eng.stream(st, xd[:, :2 * H]), eng.stream(st, xd[:, 2 * H:])], dim=1).cpu().numpy()
-            assert rms(got - want) < 1e-5, (name, S)
-            assert np.abs(st.export().cpu().numpy() - ost).max() < 2e-5, (name, S)
+            assert rms(got - want) < TOL[precision]["wav"], (name, S)
+            assert np.abs(st.export().cpu().numpy() - ost).max() < TOL[precision]["state"], (name, S)
     finally:
         eng.set_streams_per_cta(0)
 
@@ -83,7 +95,7 @@ def test_hop_by_hop_equals_one_launch_bit_exact(name, engines):
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_stage_taps(name, canonical, engines):
+def test_stage_taps(name, canonical, engines, precision):
     from oracle.oracle import tap_schema
     cfg, eng, o = PRESETS[name], engines(name), _oracle(name, canonical)
     x = synthetic_noisy(2, 5 * cfg.hop_size, cfg.sample_rate)
@@ -94,34 +106,34 @@ def test_stage_taps(name, canonical, engines):
     for nm, shp in tap_schema(cfg):
         n = int(np.prod(shp))
         r = ref[nm][4]
-        assert np.abs(taps[off:off + n].reshape(shp) - r).max() < 2e-5 * max(1.0, np.abs(r).max()), nm
+        assert np.abs(taps[off:off + n].reshape(shp) - r).max() < TOL[precision]["tap"] * max(1.0, np.abs(r).max()), nm
         off += n
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_offline_matches_reference_golden(name, golden, engines):
+def test_offline_matches_reference_golden(name, golden, engines, precision):
     cfg, g, eng = PRESETS[name], golden(name), engines(name)
     L = int(g["offline_len"])
     wav, spec = eng.offline(torch.from_numpy(synthetic_noisy(2, L, cfg.sample_rate)).cuda())
     wav, spec = wav.cpu().numpy(), spec.cpu().numpy()
     assert wav.shape == g["offline_wav"].shape == (2, cfg.hop_size * (L // cfg.hop_size))      # exact frame arithmetic
     assert spec.shape == (2, cfg.f_in, 1 + L // cfg.hop_size, 2)
-    assert rms(wav - g["offline_wav"]) < 1e-5
+    assert rms(wav - g["offline_wav"]) < TOL[precision]["wav"]
     if "offline_spec_frames" in g.files:
         spec = spec[:, :, g["offline_spec_frames"]]
-    assert np.abs(spec - g["offline_spec"]).max() < 1e-4 * max(1.0, np.abs(g["offline_spec"]).max())
+    assert np.abs(spec - g["offline_spec"]).max() < TOL[precision]["spec_abs"] * max(1.0, np.abs(g["offline_spec"]).max())
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_spec2spec_matches_reference_golden(name, golden, engines):
+def test_spec2spec_matches_reference_golden(name, golden, engines, precision):
     cfg, g, eng = PRESETS[name], golden(name), engines(name)
     st = eng.new_state(2)
     sp = torch.from_numpy(g["spec_in"]).cuda()
     out = torch.cat([eng.spec(st, sp[:, :, :3].contiguous()), eng.spec(st, sp[:, :, 3:6].contiguous())], dim=2).cpu().numpy()
-    assert np.abs(out - g["spec_out"]).max() < 1e-5 * np.abs(g["spec_out"]).max()
+    assert np.abs(out - g["spec_out"]).max() < TOL[precision]["spec"] * np.abs(g["spec_out"]).max()
     assert np.all(out[:, -1] == 0)                                   # Nyquist bin padded with zeros
     h = st.export().cpu().numpy()[:, 2 * cfg.cache_len:].reshape(g["spec_h"].shape)
-    assert np.abs(h - g["spec_h"]).max() < 2e-5
+    assert np.abs(h - g["spec_h"]).max() < TOL[precision]["state"]
 
 
 def test_state_import_export_round_trip(engines):
@@ -160,7 +172,7 @@ def test_host_buffer_path_equals_device_path(engines):
     assert torch.equal(y_dev, y_host)
 
 
-def test_full_size_properties(canonical, engines):
+def test_full_size_properties(canonical, engines, precision):
     """BASELINE config 2 at full size (FastEnhancer_B, 256 streams, 10 s = 626 hops): sampled streams against
     the oracle, stream independence, and launch-split invariance."""
     cfg, eng, o = PRESETS["16k_b"], engines("16k_b"), _oracle("16k_b", canonical)
@@ -172,7 +184,7 @@ def test_full_size_properties(canonical, engines):
     y = eng.stream(st, xd)
     pick = [0, 3, 131, 255]
     want = o.stream(o.new_state(len(pick)), x[pick])
-    assert rms(y[pick].cpu().numpy() - want) < 1e-5
+    assert rms(y[pick].cpu().numpy() - want) < TOL[precision]["wav"]
     assert torch.equal(y[200], y[3])                                  # streams never mix
     st2 = eng.new_state(B)
     y2 = torch.cat([eng.stream(st2, xd[:, :300 * H]), eng.stream(st2, xd[:, 300 * H:])], dim=1)
@@ -187,13 +199,13 @@ def test_model_classes_drop_in(golden):
     m = Model(**cfg.to_model_kwargs()).eval().cuda()
     L = int(g["offline_len"])
     wav, spec = m(torch.from_numpy(synthetic_noisy(2, L, cfg.sample_rate)).cuda())
-    assert rms(wav.cpu().numpy() - g["offline_wav"]) < 1e-5 and spec.shape[1:] == (cfg.f_in, 1 + L // cfg.hop_size, 2)
+    assert rms(wav.cpu().numpy() - g["offline_wav"]) < 5e-5 and spec.shape[1:] == (cfg.f_in, 1 + L // cfg.hop_size, 2)
     om = ONNXModel(**cfg.to_model_kwargs()).eval().cuda()
     sp = torch.from_numpy(g["spec_in"]).cuda()
     o1, *h = om(sp[:, :, :3].contiguous())
     o2, *h = om(sp[:, :, 3:6].contiguous(), *h)
     out = torch.cat([o1, o2], dim=2).cpu().numpy()
-    assert np.abs(out - g["spec_out"]).max() < 1e-5 * np.abs(g["spec_out"]).max()
+    assert np.abs(out - g["spec_out"]).max() < 1e-3 * np.abs(g["spec_out"]).max()
     assert tuple(h[0].shape) == (1, 2 * cfg.rf_freq, cfg.rf_channels)
     # streaming graph with explicit caches, hop by hop, like scripts/test_onnx.py:44-49
     sm = StreamingModel(om)
@@ -204,5 +216,5 @@ def test_model_classes_drop_in(golden):
     for i in range(N_HOPS):
         y, *caches = sm(x[:, i * H:(i + 1) * H], *caches)
         hops.append(y)
-    assert rms(torch.cat(hops, dim=1).cpu().numpy() - g["stream_out"]) < 1e-5
-    assert rms(sm.run(x).cpu().numpy() - g["stream_out"]) < 1e-5
+    assert rms(torch.cat(hops, dim=1).cpu().numpy() - g["stream_out"]) < 5e-5
+    assert rms(sm.run(x).cpu().numpy() - g["stream_out"]) < 5e-5

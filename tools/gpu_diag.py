@@ -46,8 +46,8 @@ def diag(name, S, B=5, nh=6):
     e_w = float(np.abs(y - y_ref).max())
     e_s = float(np.abs(state.export().cpu().numpy() - st).max())
     rms = float(np.sqrt(np.mean((y - y_ref) ** 2)))
-    print(f"DIAG {name} S={S}: wav max|d|={e_w:.3e} rms={rms:.3e} state max|d|={e_s:.3e} worst tap rel={worst:.2e} "
-          f"{'OK' if rms < 1e-5 and e_s < 1e-4 else 'FAIL'}")
+    print(f"DIAG {name} S={S} {eng.precision}: wav max|d|={e_w:.3e} rms={rms:.3e} state max|d|={e_s:.3e} worst tap rel={worst:.2e} "
+          f"{'OK' if rms < (1e-5 if eng.precision == 'fp32' else 5e-5) and e_s < 5e-4 else 'FAIL'}")
 
 
 def timing(name, B, nh, S=0):
@@ -72,7 +72,7 @@ def timing(name, B, nh, S=0):
     ms = ev0.elapsed_time(ev1) / reps
     fps = B * nh / (ms * 1e-3)
     tf = fps * cfg.flops_per_frame() / 1e12
-    print(f"TIME {name} B={B} hops={nh} S={eng.streams_per_cta(B)}: {ms:.3f} ms/launch, {ms * 1e3 / nh:.2f} us/hop, "
+    print(f"TIME {name} {eng.precision} B={B} hops={nh} S={eng.streams_per_cta(B)}: {ms:.3f} ms/launch, {ms * 1e3 / nh:.2f} us/hop, "
           f"{fps / 1e6:.3f} Mframes/s, {tf:.2f} TFLOP/s alg, RTF/stream={ms * 1e-3 / (nh * H / cfg.sample_rate):.5f}")
 
 
@@ -91,7 +91,7 @@ def profile(name, B, nh, S=0):
     torch.cuda.synchronize()
     p = prof.cpu().numpy().astype(np.float64) / nh
     tot = p.sum()
-    print(f"PROF {name} B={B} S={eng.streams_per_cta(B)}: {tot:.0f} cycles/hop (CTA 0)")
+    print(f"PROF {name} {eng.precision} B={B} S={eng.streams_per_cta(B)}: {tot:.0f} cycles/hop (CTA 0)")
     for nm, v in sorted(zip(eng.PHASES, p), key=lambda t: -t[1]):
         if v > 0:
             print(f"  {nm:10s} {v:9.0f} cyc  {100 * v / tot:5.1f}%")
