@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     }
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P::SM_BAR + 4 * P::STAGES + 2);
     if constexpr (P::TC) {
-        if (threadIdx.x < 32) {          // warp 0 owns the TMEM allocation (256 columns x 128 lanes of fp32 accumulators)
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        if (threadIdx.x < 32) {          // warp 0 owns the TMEM allocation (TMEMC columns x 128 lanes of fp32 accumulators)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(P::TMEMC) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         tc_fence_before();
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     if constexpr (P::TC) {
         tc_fence_before();
         bar_consumers<P::NT>();
-        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(x.tmem) : "memory");
+        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(x.tmem), "n"(P::TMEMC) : "memory");
     }
 }
 

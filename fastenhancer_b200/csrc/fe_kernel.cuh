@@ -40,6 +40,7 @@ inline void st4(float* p, f4 v) { std::memcpy(p, &v, 16); }
 inline void st2(float* p, f2 v) { std::memcpy(p, &v, 8); }
 inline float ldg(const float* p) { return *p; }
 inline f2 ldg2(const float* p) { return ld2(p); }
+inline f4 ldg4(const float* p) { return ld4(p); }
 inline float fe_exp(float x) { return expf(x); }
 inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
@@ -55,6 +56,7 @@ FE_DEV void st4(float* p, f4 v) { *reinterpret_cast<float4*>(p) = v; }
 FE_DEV void st2(float* p, f2 v) { *reinterpret_cast<float2*>(p) = v; }
 FE_DEV float ldg(const float* p) { return __ldg(p); }
 FE_DEV f2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+FE_DEV f4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 FE_DEV float fe_exp(float x) { return __expf(x); }
 FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
 // round to nearest TF32 so that the tensor core (which reads the top 19 bits) sees the value exactly
@@ -72,7 +74,12 @@ enum PhaseId { PH_INIT = 0, PH_LOAD, PH_WINDOW, PH_FFT, PH_COMPRESS, PH_ENC_PRE,
 FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
 FE_DEV float silu(float x) { return fe_div(x, 1.0f + fe_exp(-x)); }
-FE_DEV float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GRU gates: ex2.approx / rcp.approx based (absolute error ~1e-7, far inside the fp32 noise of the recurrence)
+FE_DEV float sigmoid_acc(float x) { return fe_div(1.0f, 1.0f + fe_exp(-x)); }
+FE_DEV float tanh_acc(float x) {
+    const float xc = fminf(fmaxf(x, -15.f), 15.f);
+    return 1.0f - fe_div(2.0f, 1.0f + fe_exp(2.0f * xc));
+}
 
 template <int PT> FE_DEV void load_pt(const float* p, float* v) {
     if constexpr (PT == 4) { f4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
@@ -271,27 +278,24 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
 // epi(global position, channel group, values[4]).
 // a_kstep(j) -> first of the two 4-channel slabs of k-step j (second slab SLABF floats further).
 // ---------------------------------------------------------------------------------------------
-template <class L, class P, class X, class AKstep, class Epi>
-FE_DEV void tc_layer(X& x, int tid, int ci0, AKstep a_kstep, Epi epi) {
-    constexpr int S = P::S;
+// weight tiles of layer L stream through the ring; thread 0 calls issue(tile index, tile pointer) for each
+template <class L, class X, class Issue>
+FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
     for (int c = 0; c < L::NCHUNK; ++c) {
         const int tiles = (c == L::NCHUNK - 1) ? L::NTILE - c * L::TPC : L::TPC;
         const float* w = x.acquire(ci0 + c, tiles * L::TILE);
         if (tid == 0) {
             x.mma_fence();
-            for (int i = 0; i < tiles; ++i) {
-                const int tile = c * L::TPC + i, t = tile / L::NKS, j = tile % L::NKS;
-                const int shift = (L::TAPS == 3 ? t : 1) * S;          // first data slot is S; tap t reads position f + t - 1
-#pragma unroll
-                for (int mt = 0; mt < L::NMT; ++mt) {
-                    const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
-                    x.mma(a_kstep(j) + (shift + mt * 128) * 4, P::SLABF, w + i * L::TILE, L::NP * 4, L::NP, mt * L::NP, tile > 0, rows);
-                }
-            }
+            for (int i = 0; i < tiles; ++i) issue(c * L::TPC + i, w + i * L::TILE);
         }
         x.release_mma(ci0 + c);
     }
     x.acc_commit_wait();
+}
+
+// every consumer thread owns accumulator row m (TMEM lane) and half of the NG channel groups
+template <class L, class X, class Epi>
+FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
     constexpr int GH = (L::NG + 1) / 2;
     const int half = tid >> 7, m = (((tid >> 5) & 3) << 5) + (tid & 31);
 #pragma unroll
@@ -312,6 +316,22 @@ FE_DEV void tc_layer(X& x, int tid, int ci0, AKstep a_kstep, Epi epi) {
             }
         }
     }
+}
+
+// a_kstep(j) -> first of the two 4-channel slabs of k-step j (the second is a_lbo floats further);
+// slot0 = first data slot of a slab, tap t of a 3-tap layer reads slots shifted by (t - 1) * tapstride.
+template <class L, class X, class AKstep, class Epi>
+FE_DEV void tc_layer(X& x, int tid, int ci0, AKstep a_kstep, int a_lbo, int slot0, int tapstride, Epi epi) {
+    tc_stream<L>(x, tid, ci0, [&](int tile, const float* w) {
+        const int t = tile / L::NKS, j = tile % L::NKS;
+        const int shift = slot0 + (L::TAPS == 3 ? (t - 1) * tapstride : 0);
+#pragma unroll
+        for (int mt = 0; mt < L::NMT; ++mt) {
+            const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
+            x.mma(a_kstep(j) + (shift + mt * 128) * 4, a_lbo, w, L::NP * 4, L::NP, mt * L::NP, tile > 0, rows);
+        }
+    });
+    tc_epilogue<L>(x, tid, epi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,9 +377,11 @@ template <class P> struct Frame {
         float* dst; const float* bias; float* gdst; bool act; bool round;
         FE_DEV void operator()(int gp, int g, const float* v) const {
             float o[4];
+            const f4 b4 = ldg4(bias + 4 * g);
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float t = v[e] + ldg(bias + 4 * g + e);
+                float t = v[e] + bv[e];
                 t = act ? silu(t) : t;
                 o[e] = round ? tf32_rna(t) : t;
             }
@@ -411,9 +433,30 @@ template <class P> struct Frame {
                 }
             });
         }
+        if constexpr (P::H_RES) {       // GRU state of every block stays in shared memory for the whole launch
+            x.phase(PH_STATE, [&](int tid) {
+                for (int idx = tid; idx < S * C::K * P::C2P * F2; idx += NT) {
+                    const int s = idx / (C::K * P::C2P * F2), r = idx % (C::K * P::C2P * F2);
+                    const int k = r / (P::C2P * F2), c = (r / F2) % P::C2P, f = r % F2, gs = x.s0 + s;
+                    float v = 0.f;
+                    if (c < C2 && gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f];
+                    sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)] = v;
+                }
+            });
+        }
         for (int hop = 0; hop < prm.n_hops; ++hop) {
             frame(x, hop);
             x.next_frame();
+        }
+        if constexpr (P::H_RES) {
+            x.phase(PH_STATE, [&](int tid) {
+                for (int idx = tid; idx < S * C::K * C2 * F2; idx += NT) {
+                    const int s = idx / (C::K * C2 * F2), r = idx % (C::K * C2 * F2);
+                    const int k = r / (C2 * F2), c = (r / F2) % C2, f = r % F2, gs = x.s0 + s;
+                    if (gs < prm.n_streams)
+                        prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f] = sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)];
+                }
+            });
         }
         if (prm.mode == MODE_STREAM) {
             const int n = prm.n_hops;
@@ -464,6 +507,212 @@ template <class P> struct Frame {
     }
     template <class X> FE_DEV static float* skip_gdst(X& x, int i) {
         return (i < P::SKIP_SMEM) ? nullptr : x.gs + (size_t)(i - P::SKIP_SMEM) * ACT;
+    }
+
+
+    static constexpr int RSLABF = P::RSLABF, XTS = P::XTS, C2P = P::C2P;
+    // float offset of RNNFormer element (channel c, stream s, frequency f) in a GeoR buffer (TC variants)
+    FE_DEV static int rf_off(int c, int s, int f) { return (c >> 2) * RSLABF + (f * S + s) * 4 + (c & 3); }
+
+    // ---- rf_pre and the RNNFormer blocks with every GEMM on the tensor cores (TC variants) ----
+    // x lives twice: XR = fp32 master (residual stream), XT = TF32-rounded copy the MMAs read.  The GRU state of block
+    // k is GeoR too: resident in shared memory across hops (P::H_RES) or staged through HB from global memory each hop.
+    template <class X> FE_DEV static int rnnformer_tc(X& x, int hop, int ci, const float* enc_last, bool dbg) {
+        const KParams& prm = x.prm;
+        constexpr auto A = P::make_aux();
+        const float* aux = x.blob;
+        float* AB = x.sm + P::SM_W;
+        float* XR = AB + P::O_XR;
+        float* XT = AB + P::O_XT;
+        float* ATT = AB + P::O_ATT_T;
+        float* Y1 = AB + P::O_Y1;
+        float* QKV = AB + P::O_QKV;
+        constexpr int NGX = C2 / 4, NGP = C2P / 4;          // real / padded channel groups
+        auto dump_rf = [&](const float* buf, int off) {
+            x.phase(PH_DBG, [&](int tid) {
+                for (int idx = tid; idx < F2 * C2; idx += NT) prm.dbg[off + idx] = buf[rf_off(idx % C2, 0, idx / C2)];
+            });
+        };
+        // x_new -> master + rounded copy; the thread that owns the last real group also zeroes the K-padding group
+        auto store_x = [&](int p, int g, const float* o) {
+            st4(XR + g * RSLABF + p * 4, mk4(o[0], o[1], o[2], o[3]));
+            if constexpr (P::XT_COPY) st4(XT + g * RSLABF + p * 4, mk4(tf32_rna(o[0]), tf32_rna(o[1]), tf32_rna(o[2]), tf32_rna(o[3])));
+            if (NGP > NGX && g == NGX - 1) {
+                st4(XR + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));
+                if constexpr (P::XT_COPY) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            }
+        };
+
+        // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
+        x.phase(PH_LIN_PRE, [&](int tid) {
+            row_gemm_k1<typename P::LinPreT>(x, tid, ci, [&](int r) { return enc_last + act_off(r / S, r % S, 0); }, S * 4,
+                                             [&](int r, int o0, const float* v) {
+                float* yr = Y1 + rf_off(r / S, r % S, 0);
+#pragma unroll
+                for (int j = 0; j < P::LinPreT::NO; ++j)
+                    if (o0 + j < F2) yr[(o0 + j) * S * 4] = tf32_rna(v[j]);
+            });
+        });
+        ci += P::LinPreT::NCHUNK;
+        // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
+        x.phase(PH_RF_PRE, [&](int tid) {
+            tc_layer<typename P::TRfPre>(x, tid, ci, [&](int j) { return (const float*)Y1 + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                                         [&](int p, int g, const float* v) {
+                const f4 b4 = ldg4(aux + A.rf_pre_b + 4 * g);
+                const float o[4] = {v[0] + b4.x, v[1] + b4.y, v[2] + b4.z, v[3] + b4.w};
+                store_x(p, g, o);
+            });
+        });
+        ci += P::TRfPre::NCHUNK;
+        if (dbg) dump_rf(XR, TAP_RFPRE);
+
+        for (int k = 0; k < C::K; ++k) {
+            const auto ab = A.blk(k);
+            float* H = P::H_RES ? x.sm + P::SM_HST + k * XTS : AB + P::O_HB_T;
+            const size_t hoff = 2 * C::CL + (size_t)k * C2 * F2;
+            if constexpr (!P::H_RES) {
+                x.phase(PH_HLOAD, [&](int tid) {
+                    for (int idx = tid; idx < S * C2P * F2; idx += NT) {
+                        const int s = idx / (C2P * F2), r = idx % (C2P * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
+                        float v = 0.f;
+                        if (c < C2 && gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + hoff + c * F2 + f];
+                        H[rf_off(c, s, f)] = v;
+                    }
+                });
+            }
+            // ---- fused GRU step: 6 weight sets -> accumulators R | Z | NX | NH (NPG columns each) ----
+            x.phase(PH_GRU, [&](int tid) {
+                using L = typename P::TGru;
+                constexpr int NPG = P::NPG;
+                static_assert(L::NP == NPG, "GRU tile width");
+                tc_stream<L>(x, tid, ci, [&](int tile, const float* w) {
+                    const int set = tile / L::NKS, j = tile % L::NKS;
+                    const float* a = (set < 3 ? (const float*)XT : (const float*)H) + 2 * j * RSLABF;
+                    const int col = (set < 3 ? set : (set == 5 ? 3 : set - 3)) * NPG;
+                    const bool acc = set < 3 ? j > 0 : (set == 5 ? j > 0 : true);
+                    x.mma(a, RSLABF, w, NPG * 4, NPG, col, acc, P::RSLOTS);
+                });
+                constexpr int GH = (NGX + 1) / 2;
+                const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
+                const int f = p / S, s = p % S, gs = x.s0 + s;
+                for (int i = 0; i < GH; ++i) {
+                    const int g = half * GH + i;
+                    float vr[4], vz[4], vx[4], vh[4];
+                    if (g < NGX) {
+                        x.tmem_ld4(tid, 0 * NPG + 4 * g, vr); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz);
+                        x.tmem_ld4(tid, 2 * NPG + 4 * g, vx); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh);
+                    }
+                    x.tmem_ld_wait();
+                    if (g < NGX && p < P::RSLOTS) {
+                        float* hp = H + g * RSLABF + p * 4;
+                        const f4 ho = ld4(hp);
+                        const float hov[4] = {ho.x, ho.y, ho.z, ho.w};
+                        float hn[4];
+                        const f4 b4r = ldg4(aux + ab.b_r + 4 * g), b4z = ldg4(aux + ab.b_z + 4 * g);
+                        const f4 b4i = ldg4(aux + ab.b_in + 4 * g), b4h = ldg4(aux + ab.b_hn + 4 * g);
+                        const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w};
+                        const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float r = sigmoid_acc(vr[e] + br[e]);
+                            const float z = sigmoid_acc(vz[e] + bz[e]);
+                            const float nn = tanh_acc(vx[e] + bi[e] + r * (vh[e] + bh[e]));
+                            hn[e] = (1.0f - z) * nn + z * hov[e];
+                        }
+                        st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed
+                        if constexpr (!P::H_RES) {
+                            if (gs < prm.n_streams) {
+                                float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)(4 * g) * F2 + f;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) gp[e * F2] = hn[e];
+                            }
+                        }
+                    }
+                }
+            });
+            ci += P::TGru::NCHUNK;
+            // ---- rnn_fc (+ folded BN) + residual (+ positional embedding in block 0) ----
+            x.phase(PH_RNN_FC, [&](int tid) {
+                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return (const float*)H + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                                          [&](int p, int g, const float* v) {
+                    const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.fc_b + 4 * g);
+                    float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
+                    if (k == 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] += ldg(aux + ab.pe + (4 * g + e) * F2 + p / S);
+                    }
+                    store_x(p, g, o);
+                });
+            });
+            ci += P::TFc::NCHUNK;
+            if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
+            // ---- attention over the F2 tokens of the frame, HG heads per round ----
+            for (int hg = 0; hg < P::NQG; ++hg) {
+                x.phase(PH_QKV, [&](int tid) {
+                    tc_layer<typename P::TQkv>(x, tid, ci, [&](int j) { return (const float*)XT + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                                               [&](int p, int g, const float* v) {
+                        float* q = QKV + (4 * g) * PR + (p % S) * F2P + p / S;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * g + e < 3 * HD * P::HG) q[e * PR] = v[e] + ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + 4 * g + e);
+                    });
+                });
+                ci += P::TQkv::NCHUNK;
+                x.phase(PH_ATTN, [&](int tid) {
+                    const float scale = 1.0f / sqrtf((float)HD);
+                    if (hg == 0)
+                        for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)       // K-padding channels of the attn_fc operand
+                            ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
+                    for (int it = tid; it < S * P::HG * F2; it += NT) {
+                        const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
+                        const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
+                        float q[HD], o[HD];
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
+                        float mx = -INFINITY;
+                        for (int j = 0; j < F2; ++j) {
+                            float sc = 0.f;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                            mx = fmaxf(mx, sc);
+                        }
+                        float den = 0.f;
+                        for (int j = 0; j < F2; ++j) {
+                            float sc = 0.f;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                            const float pj = fe_exp(sc - mx);
+                            den += pj;
+#pragma unroll
+                            for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
+                        }
+                        const float inv = 1.0f / den;
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_rna(o[d] * inv);
+                    }
+                });
+            }
+            x.phase(PH_ATTN_FC, [&](int tid) {
+                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return (const float*)ATT + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                                          [&](int p, int g, const float* v) {
+                    const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.afc_b + 4 * g);
+                    const float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
+                    store_x(p, g, o);
+                });
+            });
+            ci += P::TFc::NCHUNK;
+            if (dbg) {
+                dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
+                x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
+                    for (int idx = tid; idx < F2 * C2; idx += NT) {
+                        const int c = idx % C2, f = idx / C2;
+                        prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
+                            P::H_RES ? H[rf_off(c, 0, f)] : prm.state[(size_t)x.s0 * C::STATE + hoff + c * F2 + f];
+                    }
+                });
+            }
+        }
+        return ci;
     }
 
     template <class X> FE_DEV static void frame(X& x, int hop) {
@@ -582,12 +831,12 @@ template <class P> struct Frame {
                 TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true};
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
-                        tc_layer<typename P::TEncPre, P>(x, tid, ci, [&](int) { return src; }, epi);
+                        tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return src; }, SLABF, S, S, epi);
                     });
                     ci += P::TEncPre::NCHUNK;
                 } else {
                     x.phase(PH_ENC, [&](int tid) {
-                        tc_layer<typename P::TConv3, P>(x, tid, ci, [&](int j) { return src + 2 * j * SLABF; }, epi);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return src + 2 * j * SLABF; }, SLABF, S, S, epi);
                     });
                     ci += P::TConv3::NCHUNK;
                 }
@@ -609,197 +858,190 @@ template <class P> struct Frame {
             src = dst;
         }
 
-        // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
+        // ================= rf_pre, RNNFormer blocks =================
         float* Y1 = AB + P::O_Y1;
         float* XR = AB + P::O_XR;
         if constexpr (P::TC) {
-            x.phase(PH_LIN_PRE, [&](int tid) {
-                row_gemm_k1<typename P::LinPreT>(x, tid, ci, [&](int r) { return src + act_off(r / S, r % S, 0); }, S * 4,
-                                                 [&](int r, int o0, const float* v) {
-#pragma unroll
-                    for (int j = 0; j < P::LinPreT::NO; j += 4)
-                        if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                });
-            });
-            ci += P::LinPreT::NCHUNK;
+            ci = rnnformer_tc(x, hop, ci, src, dbg);
         } else {
+            // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
             x.phase(PH_LIN_PRE, [&](int tid) {
                 row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
-#pragma unroll
+    #pragma unroll
                     for (int j = 0; j < P::LinPre::NO; j += 4)
                         if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 });
             });
             ci += P::LinPre::NCHUNK;
-        }
-        x.phase(PH_RF_PRE, [&](int tid) {
-            pos_gemm<typename P::RfPre>(x, tid, ci, [&](int k) { return Y1 + k * PR; }, F2P, 0,
-                                        [&](int co, int s, int f, const float* v) {
-                                            const float b = ldg(aux + A.rf_pre_b + co);
-                                            st4(XR + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
-                                        });
-        });
-        ci += P::RfPre::NCHUNK;
-        if (dbg) dump_rf(XR, TAP_RFPRE);
+            x.phase(PH_RF_PRE, [&](int tid) {
+                pos_gemm<typename P::RfPre>(x, tid, ci, [&](int k) { return Y1 + k * PR; }, F2P, 0,
+                                            [&](int co, int s, int f, const float* v) {
+                                                const float b = ldg(aux + A.rf_pre_b + co);
+                                                st4(XR + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                            });
+            });
+            ci += P::RfPre::NCHUNK;
+            if (dbg) dump_rf(XR, TAP_RFPRE);
 
-        // ================= RNNFormer blocks =================
-        float* HB = AB + P::O_HB;
-        float* G = AB + P::O_G;
-        float* QKV = AB + P::O_QKV;
-        float* ATT = AB + P::O_ATT;
-        for (int k = 0; k < C::K; ++k) {
-            const auto ab = A.blk(k);
-            // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
-            x.phase(PH_HLOAD, [&](int tid) {
-                for (int idx = tid; idx < S * C2 * F2; idx += NT) {
-                    int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
-                    float v = 0.f;
-                    if (gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + r];
-                    HB[c * PR + s * F2P + f] = v;
-                }
-            });
-            // fused GRU step (PyTorch gate order r, z, n; b_hn inside the r * (.) term)
-            x.phase(PH_GRU, [&](int tid) {
-                using L = typename P::Gru;
-                constexpr int CT = L::CT, PT = L::PT, RW = L::RW;
-                PosGeo<L> g(tid, F2P, 0);
-                for (int pass = 0; pass < L::NPASS; ++pass) {
-                    float ar[CT][PT], az[CT][PT], anx[CT][PT], anh[CT][PT];
-#pragma unroll
-                    for (int i = 0; i < CT; ++i)
-#pragma unroll
-                        for (int j = 0; j < PT; ++j) ar[i][j] = az[i][j] = anx[i][j] = anh[i][j] = 0.f;
-                    const int co0 = g.co0(pass);
-                    const bool active = g.pvalid && co0 < C2;
-                    for (int c = 0; c < L::NCHUNK_PASS; ++c) {
-                        const int rows = (c == L::NCHUNK_PASS - 1) ? L::K - c * L::KC : L::KC;
-                        const float* w = x.acquire(ci + pass * L::NCHUNK_PASS + c, rows * L::ROW);
-                        if (active) {
-                            const float* wl = w + (g.cgp * L::CL + g.cl) * RW;
-#pragma unroll 2
-                            for (int kk = 0; kk < rows; ++kk) {
-                                const int kx = c * L::KC + kk;
-                                float xv[PT], hv[PT], wv[RW];
-                                load_pt<PT>(XR + kx * PR + g.xoff, xv);
-                                load_pt<PT>(HB + kx * PR + g.xoff, hv);
-#pragma unroll
-                                for (int e = 0; e < RW; e += 4) { f4 t = ld4(wl + kk * L::ROW + e); wv[e] = t.x; wv[e + 1] = t.y; wv[e + 2] = t.z; wv[e + 3] = t.w; }
-#pragma unroll
-                                for (int i = 0; i < CT; ++i)
-#pragma unroll
-                                    for (int j = 0; j < PT; ++j) {
-                                        ar[i][j] = fmaf(wv[3 * CT + i], hv[j], fmaf(wv[0 * CT + i], xv[j], ar[i][j]));
-                                        az[i][j] = fmaf(wv[4 * CT + i], hv[j], fmaf(wv[1 * CT + i], xv[j], az[i][j]));
-                                        anx[i][j] = fmaf(wv[2 * CT + i], xv[j], anx[i][j]);
-                                        anh[i][j] = fmaf(wv[5 * CT + i], hv[j], anh[i][j]);
-                                    }
-                            }
-                        }
-                        x.release(ci + pass * L::NCHUNK_PASS + c);
+            // ================= RNNFormer blocks =================
+            float* HB = AB + P::O_HB;
+            float* G = AB + P::O_G;
+            float* QKV = AB + P::O_QKV;
+            float* ATT = AB + P::O_ATT;
+            for (int k = 0; k < C::K; ++k) {
+                const auto ab = A.blk(k);
+                // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
+                x.phase(PH_HLOAD, [&](int tid) {
+                    for (int idx = tid; idx < S * C2 * F2; idx += NT) {
+                        int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
+                        float v = 0.f;
+                        if (gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + r];
+                        HB[c * PR + s * F2P + f] = v;
                     }
-                    if (active) {
-                        const int gs = x.s0 + g.s;
-#pragma unroll
-                        for (int i = 0; i < CT; ++i) {
-                            const int c = co0 + i;
-                            if (c < C2) {
-                                const float br = ldg(aux + ab.b_r + c), bz = ldg(aux + ab.b_z + c);
-                                const float bin = ldg(aux + ab.b_in + c), bhn = ldg(aux + ab.b_hn + c);
-                                float hn[PT], ho[PT];
-                                load_pt<PT>(HB + c * PR + g.xoff, ho);
-#pragma unroll
-                                for (int j = 0; j < PT; ++j) {
-                                    float r = sigmoid_acc(ar[i][j] + br);
-                                    float z = sigmoid_acc(az[i][j] + bz);
-                                    float nn = tanhf(anx[i][j] + bin + r * (anh[i][j] + bhn));
-                                    hn[j] = (1.0f - z) * nn + z * ho[j];
+                });
+                // fused GRU step (PyTorch gate order r, z, n; b_hn inside the r * (.) term)
+                x.phase(PH_GRU, [&](int tid) {
+                    using L = typename P::Gru;
+                    constexpr int CT = L::CT, PT = L::PT, RW = L::RW;
+                    PosGeo<L> g(tid, F2P, 0);
+                    for (int pass = 0; pass < L::NPASS; ++pass) {
+                        float ar[CT][PT], az[CT][PT], anx[CT][PT], anh[CT][PT];
+    #pragma unroll
+                        for (int i = 0; i < CT; ++i)
+    #pragma unroll
+                            for (int j = 0; j < PT; ++j) ar[i][j] = az[i][j] = anx[i][j] = anh[i][j] = 0.f;
+                        const int co0 = g.co0(pass);
+                        const bool active = g.pvalid && co0 < C2;
+                        for (int c = 0; c < L::NCHUNK_PASS; ++c) {
+                            const int rows = (c == L::NCHUNK_PASS - 1) ? L::K - c * L::KC : L::KC;
+                            const float* w = x.acquire(ci + pass * L::NCHUNK_PASS + c, rows * L::ROW);
+                            if (active) {
+                                const float* wl = w + (g.cgp * L::CL + g.cl) * RW;
+    #pragma unroll 2
+                                for (int kk = 0; kk < rows; ++kk) {
+                                    const int kx = c * L::KC + kk;
+                                    float xv[PT], hv[PT], wv[RW];
+                                    load_pt<PT>(XR + kx * PR + g.xoff, xv);
+                                    load_pt<PT>(HB + kx * PR + g.xoff, hv);
+    #pragma unroll
+                                    for (int e = 0; e < RW; e += 4) { f4 t = ld4(wl + kk * L::ROW + e); wv[e] = t.x; wv[e + 1] = t.y; wv[e + 2] = t.z; wv[e + 3] = t.w; }
+    #pragma unroll
+                                    for (int i = 0; i < CT; ++i)
+    #pragma unroll
+                                        for (int j = 0; j < PT; ++j) {
+                                            ar[i][j] = fmaf(wv[3 * CT + i], hv[j], fmaf(wv[0 * CT + i], xv[j], ar[i][j]));
+                                            az[i][j] = fmaf(wv[4 * CT + i], hv[j], fmaf(wv[1 * CT + i], xv[j], az[i][j]));
+                                            anx[i][j] = fmaf(wv[2 * CT + i], xv[j], anx[i][j]);
+                                            anh[i][j] = fmaf(wv[5 * CT + i], hv[j], anh[i][j]);
+                                        }
                                 }
-                                store_pt<PT>(G + c * PR + g.xoff, hn);
-                                if (gs < prm.n_streams)
-                                    store_pt<PT>(prm.state + (size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + c * F2 + g.f, hn);
+                            }
+                            x.release(ci + pass * L::NCHUNK_PASS + c);
+                        }
+                        if (active) {
+                            const int gs = x.s0 + g.s;
+    #pragma unroll
+                            for (int i = 0; i < CT; ++i) {
+                                const int c = co0 + i;
+                                if (c < C2) {
+                                    const float br = ldg(aux + ab.b_r + c), bz = ldg(aux + ab.b_z + c);
+                                    const float bin = ldg(aux + ab.b_in + c), bhn = ldg(aux + ab.b_hn + c);
+                                    float hn[PT], ho[PT];
+                                    load_pt<PT>(HB + c * PR + g.xoff, ho);
+    #pragma unroll
+                                    for (int j = 0; j < PT; ++j) {
+                                        float r = sigmoid_acc(ar[i][j] + br);
+                                        float z = sigmoid_acc(az[i][j] + bz);
+                                        float nn = tanh_acc(anx[i][j] + bin + r * (anh[i][j] + bhn));
+                                        hn[j] = (1.0f - z) * nn + z * ho[j];
+                                    }
+                                    store_pt<PT>(G + c * PR + g.xoff, hn);
+                                    if (gs < prm.n_streams)
+                                        store_pt<PT>(prm.state + (size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + c * F2 + g.f, hn);
+                                }
                             }
                         }
                     }
+                });
+                ci += P::Gru::NCHUNK;
+                // rnn_fc (+ folded BN) + residual (+ positional embedding in block 0)
+                x.phase(PH_RNN_FC, [&](int tid) {
+                    pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return G + kk * PR; }, F2P, 0,
+                                             [&](int co, int s, int f, const float* v) {
+                                                 const float b = ldg(aux + ab.fc_b + co);
+                                                 float* p = XR + co * PR + s * F2P + f;
+                                                 f4 o = ld4(p);
+                                                 o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
+                                                 if (k == 0) {
+                                                     const float* pe = aux + ab.pe + co * F2 + f;
+                                                     o.x += ldg(pe); o.y += ldg(pe + 1); o.z += ldg(pe + 2); o.w += ldg(pe + 3);
+                                                 }
+                                                 st4(p, o);
+                                             });
+                });
+                ci += P::Fc::NCHUNK;
+                if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
+                // attention over the F2 tokens of the frame, HG heads per round
+                for (int hg = 0; hg < P::NQG; ++hg) {
+                    x.phase(PH_QKV, [&](int tid) {
+                        pos_gemm<typename P::Qkv>(x, tid, ci, [&](int kk) { return XR + kk * PR; }, F2P, 0,
+                                                  [&](int co, int s, int f, const float* v) {
+                                                      const float b = ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + co);
+                                                      st4(QKV + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
+                                                  });
+                    });
+                    ci += P::Qkv::NCHUNK;
+                    x.phase(PH_ATTN, [&](int tid) {
+                        const float scale = 1.0f / sqrtf((float)HD);
+                        for (int it = tid; it < S * P::HG * F2; it += NT) {
+                            const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
+                            const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
+                            float q[HD], o[HD];
+    #pragma unroll
+                            for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
+                            float mx = -INFINITY;
+                            for (int j = 0; j < F2; ++j) {
+                                float sc = 0.f;
+    #pragma unroll
+                                for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                                mx = fmaxf(mx, sc);
+                            }
+                            float den = 0.f;
+                            for (int j = 0; j < F2; ++j) {
+                                float sc = 0.f;
+    #pragma unroll
+                                for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
+                                const float p = fe_exp(sc - mx);
+                                den += p;
+    #pragma unroll
+                                for (int d = 0; d < HD; ++d) o[d] = fmaf(p, qb[(2 * HD + d) * PR + j], o[d]);
+                            }
+                            const float inv = 1.0f / den;
+                            float* ob = ATT + ((hg * P::HG + hh) * HD) * PR + s * F2P + i;
+    #pragma unroll
+                            for (int d = 0; d < HD; ++d) ob[d * PR] = o[d] * inv;
+                        }
+                    });
                 }
-            });
-            ci += P::Gru::NCHUNK;
-            // rnn_fc (+ folded BN) + residual (+ positional embedding in block 0)
-            x.phase(PH_RNN_FC, [&](int tid) {
-                pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return G + kk * PR; }, F2P, 0,
-                                         [&](int co, int s, int f, const float* v) {
-                                             const float b = ldg(aux + ab.fc_b + co);
-                                             float* p = XR + co * PR + s * F2P + f;
-                                             f4 o = ld4(p);
-                                             o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
-                                             if (k == 0) {
-                                                 const float* pe = aux + ab.pe + co * F2 + f;
-                                                 o.x += ldg(pe); o.y += ldg(pe + 1); o.z += ldg(pe + 2); o.w += ldg(pe + 3);
-                                             }
-                                             st4(p, o);
-                                         });
-            });
-            ci += P::Fc::NCHUNK;
-            if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
-            // attention over the F2 tokens of the frame, HG heads per round
-            for (int hg = 0; hg < P::NQG; ++hg) {
-                x.phase(PH_QKV, [&](int tid) {
-                    pos_gemm<typename P::Qkv>(x, tid, ci, [&](int kk) { return XR + kk * PR; }, F2P, 0,
-                                              [&](int co, int s, int f, const float* v) {
-                                                  const float b = ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + co);
-                                                  st4(QKV + co * PR + s * F2P + f, mk4(v[0] + b, v[1] + b, v[2] + b, v[3] + b));
-                                              });
+                x.phase(PH_ATTN_FC, [&](int tid) {
+                    pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return ATT + kk * PR; }, F2P, 0,
+                                             [&](int co, int s, int f, const float* v) {
+                                                 const float b = ldg(aux + ab.afc_b + co);
+                                                 float* p = XR + co * PR + s * F2P + f;
+                                                 f4 o = ld4(p);
+                                                 o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
+                                                 st4(p, o);
+                                             });
                 });
-                ci += P::Qkv::NCHUNK;
-                x.phase(PH_ATTN, [&](int tid) {
-                    const float scale = 1.0f / sqrtf((float)HD);
-                    for (int it = tid; it < S * P::HG * F2; it += NT) {
-                        const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
-                        const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
-                        float q[HD], o[HD];
-#pragma unroll
-                        for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
-                        float mx = -INFINITY;
-                        for (int j = 0; j < F2; ++j) {
-                            float sc = 0.f;
-#pragma unroll
-                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                            mx = fmaxf(mx, sc);
-                        }
-                        float den = 0.f;
-                        for (int j = 0; j < F2; ++j) {
-                            float sc = 0.f;
-#pragma unroll
-                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                            const float p = expf(sc - mx);
-                            den += p;
-#pragma unroll
-                            for (int d = 0; d < HD; ++d) o[d] = fmaf(p, qb[(2 * HD + d) * PR + j], o[d]);
-                        }
-                        const float inv = 1.0f / den;
-                        float* ob = ATT + ((hg * P::HG + hh) * HD) * PR + s * F2P + i;
-#pragma unroll
-                        for (int d = 0; d < HD; ++d) ob[d * PR] = o[d] * inv;
-                    }
-                });
-            }
-            x.phase(PH_ATTN_FC, [&](int tid) {
-                pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return ATT + kk * PR; }, F2P, 0,
-                                         [&](int co, int s, int f, const float* v) {
-                                             const float b = ldg(aux + ab.afc_b + co);
-                                             float* p = XR + co * PR + s * F2P + f;
-                                             f4 o = ld4(p);
-                                             o.x += v[0] + b; o.y += v[1] + b; o.z += v[2] + b; o.w += v[3] + b;
-                                             st4(p, o);
-                                         });
-            });
-            ci += P::Fc::NCHUNK;
-            if (dbg) {
-                dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
-                x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
-                    for (int idx = tid; idx < F2 * C2; idx += NT)
-                        prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
-                            prm.state[(size_t)x.s0 * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + (idx % C2) * F2 + idx / C2];
-                });
+                ci += P::Fc::NCHUNK;
+                if (dbg) {
+                    dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
+                    x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
+                        for (int idx = tid; idx < F2 * C2; idx += NT)
+                            prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
+                                prm.state[(size_t)x.s0 * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + (idx % C2) * F2 + idx / C2];
+                    });
+                }
             }
         }
 
@@ -807,10 +1049,11 @@ template <class P> struct Frame {
         float* Zb = AB + P::O_Z;
         if constexpr (P::TC) {
             x.phase(PH_LIN_POST, [&](int tid) {
-                row_gemm<typename P::LinPost>(x, tid, ci, XR, F2P, [&](int r, int o0, const float* v) {
+                row_gemm_k1<typename P::LinPostT>(x, tid, ci, [&](int r) { return XR + rf_off(r / S, r % S, 0); }, S * 4,
+                                                  [&](int r, int o0, const float* v) {
                     float* zr = Zb + act_off(r / S, r % S, 0);
 #pragma unroll
-                    for (int j = 0; j < P::LinPost::NO; ++j)
+                    for (int j = 0; j < P::LinPostT::NO; ++j)
                         if (o0 + j < F1) zr[(o0 + j) * S * 4] = tf32_rna(v[j]);
                 });
                 // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
@@ -819,10 +1062,10 @@ template <class P> struct Frame {
                     Zb[act_off(c, r % S, r / S)] = 0.f;
                 }
             });
-            ci += P::LinPost::NCHUNK;
+            ci += P::LinPostT::NCHUNK;
             TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
             x.phase(PH_RF_POST, [&](int tid) {
-                tc_layer<typename P::TRfPost, P>(x, tid, ci, [&](int j) { return Zb + 2 * j * SLABF; }, epi);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return Zb + 2 * j * SLABF; }, SLABF, S, S, epi);
             });
             ci += P::TRfPost::NCHUNK;
         } else {
@@ -861,14 +1104,14 @@ template <class P> struct Frame {
                 // All MMAs complete before any epilogue thread stores, so writing W0 (which may hold the skip) is safe.
                 TcEpiAct epi{W0, b1, nullptr, true, true};
                 x.phase(PH_PWCAT, [&](int tid) {
-                    tc_layer<typename P::TPwCat, P>(x, tid, ci, [&](int j) {
-                        return j < C1 / 8 ? (const float*)W1 + 2 * j * SLABF : skip + 2 * (j - C1 / 8) * SLABF; }, epi);
+                    tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
+                        return j < C1 / 8 ? (const float*)W1 + 2 * j * SLABF : skip + 2 * (j - C1 / 8) * SLABF; }, SLABF, S, S, epi);
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {
                     TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};
                     x.phase(PH_DEC, [&](int tid) {
-                        tc_layer<typename P::TConv3, P>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, epi2);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, SLABF, S, S, epi2);
                     });
                     ci += P::TConv3::NCHUNK;
                     if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
@@ -912,7 +1155,7 @@ template <class P> struct Frame {
         if constexpr (P::TC) {
             TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};
             x.phase(PH_CONVT, [&](int tid) {
-                tc_layer<typename P::TConvT, P>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, epi);
+                tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, SLABF, S, S, epi);
             });
             ci += P::TConvT::NCHUNK;
         } else {

@@ -211,9 +211,18 @@ public:
             for (int i = 0; i < C::E; ++i)
                 tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
             rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
-            pos<typename P::RfPre>([&](int, int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
-            blocks();
-            row<typename P::LinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+            tc<typename P::TRfPre>([&](int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
+            for (int k = 0; k < C::K; ++k) {
+                const auto& b = cw.blk[k];
+                tc<typename P::TGru>([&](int c, int ci, int set) {
+                    return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
+                });
+                tc<typename P::TFc>([&](int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
+                for (int g = 0; g < P::NQG; ++g)
+                    tc<typename P::TQkv>([&](int co, int ci, int) { return b.qkv_w[(g * 3 * C::HD * P::HG + co) * C2 + ci]; });
+                tc<typename P::TFc>([&](int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
+            }
+            rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
             tc<typename P::TRfPost>([&](int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
             for (int i = 0; i < C::E; ++i) {
                 tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });

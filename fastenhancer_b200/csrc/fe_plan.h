@@ -119,9 +119,9 @@ struct RowGemm {
 // Weights stream through the ring as tiles of one (tap, 8-wide k-step):  [2][NP][4]  (K-major B operand),
 // NP = N rounded up to 16, zero rows / zero k beyond the real sizes, values pre-rounded to TF32.
 // ----------------------------------------------------------------------------------------------
-template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_>
+template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_, int TMEMC_ = 256>
 struct TcGemm {
-    static constexpr int NPOS = NPOS_, N = N_, K = K_, TAPS = TAPS_;
+    static constexpr int NPOS = NPOS_, N = N_, K = K_, TAPS = TAPS_;   // TAPS doubles as "weight sets" for the GRU (6)
     static constexpr int NP = round_up(N, 16), KP = round_up(K, 8);
     static constexpr int NKS = KP / 8;                 // k-steps per tap
     static constexpr int NTILE = TAPS * NKS;
@@ -132,7 +132,7 @@ struct TcGemm {
     static constexpr int FLOATS = NTILE * TILE;
     static constexpr int NMT = cdiv(NPOS, 128);        // 128-row M tiles
     static constexpr int NG = cdiv(N, 4);              // output channel groups of 4
-    static_assert(NMT * NP <= 256, "accumulators exceed the TMEM allocation");
+    static_assert(NMT * NP <= TMEMC_, "accumulators exceed the TMEM allocation");
 };
 
 // Row GEMM reading one k per step (frequency-axis linear on a tensor-core-layout activation, where
@@ -194,25 +194,46 @@ struct Plan {
     static constexpr int HG = T::HG, NQG = C::NH / HG;
     static_assert(C::NH % HG == 0, "HG must divide NH");
     static constexpr int QKVS = 3 * C::HD * HG * PR;
+    // ---- RNNFormer tensor-core geometry ("GeoR", TC variants): [C2P/4][RSLOTS][4], slot = f2*S + s ----
+    static constexpr int RSLOTS = S * C::F2;
+    static constexpr int RSLABF = RSLOTS * 4;
+    static constexpr int XTS = (C2P / 4) * RSLABF;     // one RNNFormer activation in GeoR (x, h, attention output)
+    static constexpr int Y1TS = (C::C1 / 4) * RSLABF;  // rf_pre linear output in GeoR
+    static constexpr int NPG = round_up(C::C2, 16);    // accumulator columns per GRU gate
+    static_assert(RSLOTS <= 128, "RNNFormer positions exceed one M tile: lower S");
     // work region AB = [W0 | W1 (| W2)]; RNNFormer: XR at the tail, ATT/HB at 0, G/QKV at XRS.
     // W2 exists only when the RNNFormer scratch needs the room (16 kHz L).
-    static constexpr int NWORK = (2 * XRS + cmax(XRS, QKVS) > 2 * ACT) ? 3 : 2;
+    // TC variants: [QKV | Y1T | Zb from 0 ... | ATT (= h scratch when h is not resident) | XT | XR at the tail].
+    // XT is a TF32-rounded copy of x for the MMAs; when it does not fit (48 kHz L) the MMAs read the fp32 master
+    // (the tensor core then truncates instead of rounding).
+    static constexpr int SM_REST = SPECF + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
+    static constexpr int RF_NEED1 = cmax(QKVS + XTS, Y1TS) + XTS;
+    static constexpr int RF_NEED2 = RF_NEED1 + XTS;
+    static constexpr int NWORK2 = cmax(2, cdiv(RF_NEED2, ACT));
+    static constexpr bool XT_COPY = TC && (NWORK2 * ACT + SM_REST <= 227 * 256);
+    static constexpr int NWORK = TC ? (XT_COPY ? NWORK2 : cmax(2, cdiv(RF_NEED1, ACT))) : ((2 * XRS + cmax(XRS, QKVS) > 2 * ACT) ? 3 : 2);
     static constexpr int AB = NWORK * ACT;
-    static constexpr int O_XR = AB - XRS;
-    static constexpr int O_HB = 0, O_ATT = 0, O_G = XRS, O_QKV = XRS;
-    static constexpr int O_Y1 = 0;                     // rf_pre linear output [C1][PR]
-    static constexpr int O_Z = 0;                      // rf_post linear output [C2][S][P1]
-    static_assert(XRS + cmax(XRS, QKVS) <= O_XR, "RNNFormer scratch does not fit: lower Tune::HG");
-    static_assert(C::C1 * PR <= O_XR && C::C1 * PR <= (NWORK - 1) * ACT, "rf_pre scratch does not fit");
+    static constexpr int O_XR = AB - (TC ? XTS : XRS);
+    static constexpr int O_XT = XT_COPY ? O_XR - XTS : O_XR;
+    static constexpr int O_ATT_T = O_XT - XTS, O_HB_T = O_ATT_T;           // TC variants
+    static constexpr int O_HB = 0, O_ATT = 0, O_G = XRS, O_QKV = TC ? 0 : XRS;
+    static constexpr int O_Y1 = 0;                     // rf_pre linear output
+    static constexpr int O_Z = 0;                      // rf_post linear output
+    static_assert(TC || XRS + cmax(XRS, QKVS) <= O_XR, "RNNFormer scratch does not fit: lower Tune::HG");
+    static_assert(!TC || (QKVS <= O_ATT_T && Y1TS <= O_XT && Y1TS <= (NWORK - 1) * ACT), "RNNFormer tensor-core scratch does not fit");
+    static_assert(TC || (C::C1 * PR <= O_XR && C::C1 * PR <= (NWORK - 1) * ACT), "rf_pre scratch does not fit");
     static_assert(ZBF <= O_XR, "rf_post scratch does not fit");
     static_assert(S * C::N_FFT <= ACT, "FFT buffers do not fit");
     // ---- shared memory map (float offsets) ----
     static constexpr int NSK = C::E + 1;
-    static constexpr int SM_FIXED = AB + SPECF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES + 4;
+    static constexpr int SM_FIXED = AB + SM_REST;
     static_assert(SM_FIXED <= 227 * 256, "shared memory plan exceeds 227 KB even with every skip tensor spilled");
     static constexpr int SKIP_SMEM = cmax(0, cmin(cmin(NSK, T::SKIP_SMEM_MAX), (227 * 256 - SM_FIXED) / ACT));
+    // TC variants keep the GRU state of all K blocks resident in shared memory across hops when it fits
+    static constexpr bool H_RES = TC && (SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
     static constexpr int SM_SK = 0;
-    static constexpr int SM_W = SM_SK + SKIP_SMEM * ACT;
+    static constexpr int SM_HST = SM_SK + SKIP_SMEM * ACT;          // [K][XTS] resident GRU state (GeoR)
+    static constexpr int SM_W = SM_HST + (H_RES ? C::K * XTS : 0);
     static constexpr int SM_SPEC = SM_W + AB;
     static constexpr int SM_TIN = SM_SPEC + SPECF;             // last N input samples per stream (circular)
     static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
@@ -246,17 +267,26 @@ struct Plan {
     using TConvT = TcGemm<S * C::F1, 8, C::C1, 3, CHUNK>;
     using TRfPost = TcGemm<S * C::F1, C::C1, C::C2, 1, CHUNK>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
+    static constexpr int TMEMC = pow2ceil(cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(3 * C::HD * HG, 16))));
+    static_assert(TMEMC <= 512, "TMEM columns");
+    using TRfPre = TcGemm<S * C::F2, C::C2, C::C1, 1, CHUNK, 512>;
+    using TGru = TcGemm<S * C::F2, C::C2, C::C2, 6, CHUNK, 512>;       // 6 sets: W_ir W_iz W_in W_hr W_hz W_hn
+    using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
+    using TQkv = TcGemm<S * C::F2, 3 * C::HD * HG, C::C2, 1, CHUNK, 512>;
+    using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
 
     static constexpr int BLK_CHUNKS = Gru::NCHUNK + 2 * Fc::NCHUNK + NQG * Qkv::NCHUNK;
     static constexpr long BLK_FLOATS = (long)Gru::FLOATS + 2 * Fc::FLOATS + NQG * Qkv::FLOATS;
+    static constexpr int TBLK_CHUNKS = TGru::NCHUNK + 2 * TFc::NCHUNK + NQG * TQkv::NCHUNK;
+    static constexpr long TBLK_FLOATS = (long)TGru::FLOATS + 2 * TFc::FLOATS + NQG * TQkv::FLOATS;
     static constexpr int NCHUNK_FRAME = TC
-        ? TEncPre::NCHUNK + C::E * TConv3::NCHUNK + LinPreT::NCHUNK + RfPre::NCHUNK + C::K * BLK_CHUNKS + LinPost::NCHUNK +
+        ? TEncPre::NCHUNK + C::E * TConv3::NCHUNK + LinPreT::NCHUNK + TRfPre::NCHUNK + C::K * TBLK_CHUNKS + LinPostT::NCHUNK +
               TRfPost::NCHUNK + C::E * (TPwCat::NCHUNK + TConv3::NCHUNK) + TPwCat::NCHUNK + TConvT::NCHUNK
         : EncPre::NCHUNK + C::E * Conv3::NCHUNK + LinPre::NCHUNK + RfPre::NCHUNK + C::K * BLK_CHUNKS + LinPost::NCHUNK +
               RfPost::NCHUNK + C::E * (PwCat::NCHUNK + Conv3::NCHUNK) + PwCat::NCHUNK + ConvT::NCHUNK;
     static constexpr long RING_FLOATS = TC
-        ? (long)TEncPre::FLOATS + (long)C::E * TConv3::FLOATS + LinPreT::FLOATS + RfPre::FLOATS + (long)C::K * BLK_FLOATS +
-              LinPost::FLOATS + TRfPost::FLOATS + (long)C::E * (TPwCat::FLOATS + TConv3::FLOATS) + TPwCat::FLOATS + TConvT::FLOATS
+        ? (long)TEncPre::FLOATS + (long)C::E * TConv3::FLOATS + LinPreT::FLOATS + TRfPre::FLOATS + (long)C::K * TBLK_FLOATS +
+              LinPostT::FLOATS + TRfPost::FLOATS + (long)C::E * (TPwCat::FLOATS + TConv3::FLOATS) + TPwCat::FLOATS + TConvT::FLOATS
         : (long)EncPre::FLOATS + (long)C::E * Conv3::FLOATS + LinPre::FLOATS + RfPre::FLOATS + (long)C::K * BLK_FLOATS +
               LinPost::FLOATS + RfPost::FLOATS + (long)C::E * (PwCat::FLOATS + Conv3::FLOATS) + PwCat::FLOATS + ConvT::FLOATS;
 

@@ -20,7 +20,7 @@ N_HOPS = 24
 
 #                 waveform RMS, state max, tap relative, spectrum relative
 TOL = {"fp32": dict(wav=1e-5, state=2e-5, tap=2e-5, spec=1e-5, spec_abs=1e-4),
-       "tf32": dict(wav=5e-5, state=3e-4, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
+       "tf32": dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
 
 
 @pytest.fixture(scope="module", params=["tf32", "fp32"])

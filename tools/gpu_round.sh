@@ -10,11 +10,13 @@ lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket" >> $OUT/gpu.txt
 echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
 echo "=== smoke"; timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke.txt
 echo "=== bench"; timeout 600 python bench.py 2>&1 | tail -2 | tee $OUT/bench.json
+echo "=== bench fp32-exact variant"; timeout 600 python bench.py --precision fp32 --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/bench_fp32.json
 echo "=== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_reference.json
 echo "=== phase profile"
 timeout 120 python tools/gpu_diag.py --prof 16k_b 256 50 2>&1 | tee $OUT/phase_profile_16k_b.txt
 timeout 120 python tools/gpu_diag.py --prof 16k_t 256 50 2>&1 | tee $OUT/phase_profile_16k_t.txt
 timeout 120 python tools/gpu_diag.py --prof 16k_l 148 20 2>&1 | tee $OUT/phase_profile_16k_l.txt
+FE_PRECISION=fp32 timeout 120 python tools/gpu_diag.py --prof 16k_b 256 50 2>&1 | tee $OUT/phase_profile_16k_b_fp32.txt
 echo "=== timings"
 for a in "16k_t 256 200" "16k_b 256 200" "16k_s 256 100" "16k_m 256 60" "16k_l 256 30" "16k_b 1 200" "16k_b 4096 40" "16k_m 512 40" "48k_l 256 20" "16k_t 4096 50"; do
   timeout 120 python tools/gpu_diag.py --time $a 2>&1 | grep TIME
@@ -29,5 +31,5 @@ ncu -i $OUT/prof_fused.ncu-rep --page raw --csv > $OUT/prof_fused_raw.csv 2>/dev
 echo "=== sanitizers"
 timeout 300 compute-sanitizer --tool memcheck --log-file $OUT/memcheck.log python tools/gpu_diag.py 16k_t 2 3 2 > $OUT/memcheck_run.log 2>&1; tail -3 $OUT/memcheck.log
 timeout 300 compute-sanitizer --tool memcheck --log-file $OUT/memcheck_l.log python tools/gpu_diag.py 16k_l 1 2 2 > $OUT/memcheck_l_run.log 2>&1; tail -3 $OUT/memcheck_l.log
-timeout 600 compute-sanitizer --tool racecheck --log-file $OUT/racecheck.log python tools/gpu_diag.py 16k_t 2 2 2 > $OUT/racecheck_run.log 2>&1; head -30 $OUT/racecheck.log; tail -3 $OUT/racecheck.log
+timeout 600 compute-sanitizer --tool racecheck --log-file $OUT/racecheck.log python tools/gpu_diag.py 16k_t 2 2 2 > $OUT/racecheck_run.log 2>&1; grep -E "Error:|SUMMARY" $OUT/racecheck.log | head
 ls -la $OUT
