@@ -61,6 +61,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` once every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {      // one lane of a converged warp (always the same one)
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -85,21 +90,35 @@ template <class P> struct GpuCtx {
     uint32_t acc_bar;       // mbarrier: accumulators of the current layer are complete
     unsigned acc_uses;
     __device__ __forceinline__ void mma_fence() const { tc_fence_after(); }
-    __device__ __forceinline__ void mma(const float* a, int a_lbo_floats, const float* b, int b_lbo_floats, int np, int col,
-                                        bool acc, int /*rows*/) const {
-        umma_tf32(tmem + (uint32_t)col, umma_desc(smem_u32(a), (uint32_t)a_lbo_floats * 4u, 128u),
-                  umma_desc(smem_u32(b), (uint32_t)b_lbo_floats * 4u, 128u), umma_idesc_tf32_m128(np), acc ? 1u : 0u);
+    // K-major / no-swizzle operand descriptor split in two words: lo = start address | LBO, hi = SBO (128 B) | version.
+    // Advancing the start address is one 32-bit add (addresses stay below 256 KB, so no carry into the LBO field).
+    struct Desc { uint32_t lo, hi; };
+    __device__ __forceinline__ Desc make_desc(const float* p, int lbo_floats) const {
+        Desc d;
+        d.lo = ((smem_u32(p) >> 4) & 0x3fffu) | ((((uint32_t)lbo_floats * 4u) >> 4) << 16);
+        d.hi = (128u >> 4) | (1u << 14);
+        return d;
+    }
+    __device__ __forceinline__ Desc desc_add(Desc d, int floats) const { d.lo += (uint32_t)(floats >> 2); return d; }
+    // called by every lane of warp 0 (converged); one elected lane issues
+    __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
+        const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32_m128(np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
     // the stage, are done); the other warps never touch the stage and arrive at once
     __device__ __forceinline__ void release_mma(int ci) const {
         const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES;
         __syncwarp();
-        if (tid == 0) umma_commit(bars + 8u * (P::STAGES + stage));
-        else if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
+        if (tid < 32) {
+            if (elect_one()) umma_commit(bars + 8u * (P::STAGES + stage));      // the lane that issued this warp's MMAs
+        } else if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
     }
     __device__ __forceinline__ void acc_commit_wait() {
-        if (tid == 0) umma_commit(acc_bar);
+        if (tid < 32) { __syncwarp(); if (elect_one()) umma_commit(acc_bar); }
         mbar_wait(acc_bar, acc_uses & 1u);
         ++acc_uses;
         tc_fence_after();
@@ -120,7 +139,11 @@ template <class P> struct GpuCtx {
         if constexpr (P::TC) tc_fence_after();
     }
 
-    long long t_last;
+    long long t_last, t_sub;
+    __device__ __forceinline__ void sub_begin(int) { if (prm.prof != nullptr && cta == 0 && tid == 0) t_sub = clock64(); }
+    __device__ __forceinline__ void sub_end(int, int id) {
+        if (prm.prof != nullptr && cta == 0 && tid == 0) { const long long t = clock64(); prm.prof[id] += t - t_sub; t_sub = t; }
+    }
     __device__ __forceinline__ void stamp(int id) {
         if (prm.prof != nullptr && cta == 0 && tid == 0) {
             const long long t = clock64();

@@ -69,7 +69,9 @@ namespace fe {
 // phase ids for the optional in-kernel profile (KParams::prof): cycles of CTA 0 accumulated per id
 enum PhaseId { PH_INIT = 0, PH_LOAD, PH_WINDOW, PH_FFT, PH_COMPRESS, PH_ENC_PRE, PH_ENC, PH_LIN_PRE, PH_RF_PRE, PH_HLOAD, PH_GRU,
                PH_RNN_FC, PH_QKV, PH_ATTN, PH_ATTN_FC, PH_LIN_POST, PH_RF_POST, PH_SKIP_LOAD, PH_PWCAT, PH_DEC, PH_CONVT, PH_MASK,
-               PH_PRETW, PH_IFFT, PH_OLA, PH_DBG, PH_STATE, PH_COUNT };
+               PH_PRETW, PH_IFFT, PH_OLA, PH_DBG, PH_STATE,
+               // sub-timers of the tensor-core layers (thread 0; overlapping the phase ids above, not additive)
+               PH_TC_WAITW, PH_TC_ISSUE, PH_TC_MMA, PH_TC_LD, PH_TC_EPI, PH_COUNT };
 
 FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
@@ -278,19 +280,26 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
 // epi(global position, channel group, values[4]).
 // a_kstep(j) -> first of the two 4-channel slabs of k-step j (second slab SLABF floats further).
 // ---------------------------------------------------------------------------------------------
-// weight tiles of layer L stream through the ring; thread 0 calls issue(tile index, tile pointer) for each
+// Weight tiles of layer L stream through the ring.  Warp 0 runs issue(tile index, descriptor of the tile) for each
+// tile, converged (the MMA itself is issued by one elected lane inside x.mma); the other warps only keep the ring
+// protocol going.  Operand descriptors are built once and advanced by one add per MMA.
 template <class L, class X, class Issue>
 FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
     for (int c = 0; c < L::NCHUNK; ++c) {
         const int tiles = (c == L::NCHUNK - 1) ? L::NTILE - c * L::TPC : L::TPC;
+        x.sub_begin(tid);
         const float* w = x.acquire(ci0 + c, tiles * L::TILE);
-        if (tid == 0) {
+        x.sub_end(tid, PH_TC_WAITW);
+        if ((tid >> 5) == 0) {
             x.mma_fence();
-            for (int i = 0; i < tiles; ++i) issue(c * L::TPC + i, w + i * L::TILE);
+            const typename X::Desc wd = x.make_desc(w, L::NP * 4);
+            for (int i = 0; i < tiles; ++i) issue(c * L::TPC + i, x.desc_add(wd, i * L::TILE));
         }
         x.release_mma(ci0 + c);
+        x.sub_end(tid, PH_TC_ISSUE);
     }
     x.acc_commit_wait();
+    x.sub_end(tid, PH_TC_MMA);
 }
 
 // every consumer thread owns accumulator row m (TMEM lane) and half of the NG channel groups
@@ -307,6 +316,7 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
             if (g < L::NG) x.tmem_ld4(tid, mt * L::NP + 4 * g, v[i]);
         }
         x.tmem_ld_wait();
+        x.sub_end(tid, PH_TC_LD);
         const int gp = mt * 128 + m;
         if (gp < L::NPOS) {
 #pragma unroll
@@ -315,20 +325,24 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
                 if (g < L::NG) epi(gp, g, v[i]);
             }
         }
+        x.sub_end(tid, PH_TC_EPI);
     }
 }
 
-// a_kstep(j) -> first of the two 4-channel slabs of k-step j (the second is a_lbo floats further);
-// slot0 = first data slot of a slab, tap t of a 3-tap layer reads slots shifted by (t - 1) * tapstride.
-template <class L, class X, class AKstep, class Epi>
-FE_DEV void tc_layer(X& x, int tid, int ci0, AKstep a_kstep, int a_lbo, int slot0, int tapstride, Epi epi) {
-    tc_stream<L>(x, tid, ci0, [&](int tile, const float* w) {
+// a_desc(j) -> descriptor of the A operand of k-step j (two 4-channel slabs, LBO apart), positioned at the first data
+// slot; tap t of a 3-tap layer reads slots shifted by (t - 1) * tapstride (one slot = 16 bytes = 4 floats).
+template <class L, class X, class ADesc, class Epi>
+FE_DEV void tc_layer(X& x, int tid, int ci0, ADesc a_desc, int tapstride, Epi epi) {
+    tc_stream<L>(x, tid, ci0, [&](int tile, typename X::Desc wd) {
         const int t = tile / L::NKS, j = tile % L::NKS;
-        const int shift = slot0 + (L::TAPS == 3 ? (t - 1) * tapstride : 0);
+        const int shift = (L::TAPS == 3 ? (t - 1) * tapstride : 0);
 #pragma unroll
         for (int mt = 0; mt < L::NMT; ++mt) {
             const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
-            x.mma(a_kstep(j) + (shift + mt * 128) * 4, a_lbo, w, L::NP * 4, L::NP, mt * L::NP, tile > 0, rows);
+#pragma unroll
+            for (int ns = 0; ns < L::NSPLIT; ++ns)
+                x.mma(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
+                      mt * L::NP + ns * L::NPS, tile > 0, rows);
         }
     });
     tc_epilogue<L>(x, tid, epi);
@@ -556,7 +570,8 @@ template <class P> struct Frame {
         ci += P::LinPreT::NCHUNK;
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
         x.phase(PH_RF_PRE, [&](int tid) {
-            tc_layer<typename P::TRfPre>(x, tid, ci, [&](int j) { return (const float*)Y1 + 2 * j * RSLABF; }, RSLABF, 0, 0,
+            const auto a0 = x.make_desc(Y1, RSLABF);
+            tc_layer<typename P::TRfPre>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
                                          [&](int p, int g, const float* v) {
                 const f4 b4 = ldg4(aux + A.rf_pre_b + 4 * g);
                 const float o[4] = {v[0] + b4.x, v[1] + b4.y, v[2] + b4.z, v[3] + b4.w};
@@ -585,12 +600,12 @@ template <class P> struct Frame {
                 using L = typename P::TGru;
                 constexpr int NPG = P::NPG;
                 static_assert(L::NP == NPG, "GRU tile width");
-                tc_stream<L>(x, tid, ci, [&](int tile, const float* w) {
+                const auto dx = x.make_desc(XT, RSLABF), dh = x.make_desc(H, RSLABF);
+                tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
                     const int set = tile / L::NKS, j = tile % L::NKS;
-                    const float* a = (set < 3 ? (const float*)XT : (const float*)H) + 2 * j * RSLABF;
                     const int col = (set < 3 ? set : (set == 5 ? 3 : set - 3)) * NPG;
                     const bool acc = set < 3 ? j > 0 : (set == 5 ? j > 0 : true);
-                    x.mma(a, RSLABF, w, NPG * 4, NPG, col, acc, P::RSLOTS);
+                    x.mma(tid, x.desc_add(set < 3 ? dx : dh, 2 * j * RSLABF), wd, NPG, col, acc, P::RSLOTS);
                 });
                 constexpr int GH = (NGX + 1) / 2;
                 const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
@@ -633,7 +648,8 @@ template <class P> struct Frame {
             ci += P::TGru::NCHUNK;
             // ---- rnn_fc (+ folded BN) + residual (+ positional embedding in block 0) ----
             x.phase(PH_RNN_FC, [&](int tid) {
-                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return (const float*)H + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                const auto a0 = x.make_desc(H, RSLABF);
+                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
                                           [&](int p, int g, const float* v) {
                     const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.fc_b + 4 * g);
                     float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
@@ -649,7 +665,8 @@ template <class P> struct Frame {
             // ---- attention over the F2 tokens of the frame, HG heads per round ----
             for (int hg = 0; hg < P::NQG; ++hg) {
                 x.phase(PH_QKV, [&](int tid) {
-                    tc_layer<typename P::TQkv>(x, tid, ci, [&](int j) { return (const float*)XT + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                    const auto a0 = x.make_desc(XT, RSLABF);
+                    tc_layer<typename P::TQkv>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
                                                [&](int p, int g, const float* v) {
                         float* q = QKV + (4 * g) * PR + (p % S) * F2P + p / S;
 #pragma unroll
@@ -693,7 +710,8 @@ template <class P> struct Frame {
                 });
             }
             x.phase(PH_ATTN_FC, [&](int tid) {
-                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return (const float*)ATT + 2 * j * RSLABF; }, RSLABF, 0, 0,
+                const auto a0 = x.make_desc(ATT, RSLABF);
+                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
                                           [&](int p, int g, const float* v) {
                     const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.afc_b + 4 * g);
                     const float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
@@ -831,12 +849,14 @@ template <class P> struct Frame {
                 TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true};
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
-                        tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return src; }, SLABF, S, S, epi);
+                        const auto a0 = x.make_desc(src + S * 4, SLABF);
+                        tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi);
                     });
                     ci += P::TEncPre::NCHUNK;
                 } else {
                     x.phase(PH_ENC, [&](int tid) {
-                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return src + 2 * j * SLABF; }, SLABF, S, S, epi);
+                        const auto a0 = x.make_desc(src + S * 4, SLABF);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
                     });
                     ci += P::TConv3::NCHUNK;
                 }
@@ -867,7 +887,7 @@ template <class P> struct Frame {
             // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
             x.phase(PH_LIN_PRE, [&](int tid) {
                 row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
-    #pragma unroll
+#pragma unroll
                     for (int j = 0; j < P::LinPre::NO; j += 4)
                         if (o0 + j < F2) st4(Y1 + r * F2P + o0 + j, mk4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 });
@@ -906,9 +926,9 @@ template <class P> struct Frame {
                     PosGeo<L> g(tid, F2P, 0);
                     for (int pass = 0; pass < L::NPASS; ++pass) {
                         float ar[CT][PT], az[CT][PT], anx[CT][PT], anh[CT][PT];
-    #pragma unroll
+#pragma unroll
                         for (int i = 0; i < CT; ++i)
-    #pragma unroll
+#pragma unroll
                             for (int j = 0; j < PT; ++j) ar[i][j] = az[i][j] = anx[i][j] = anh[i][j] = 0.f;
                         const int co0 = g.co0(pass);
                         const bool active = g.pvalid && co0 < C2;
@@ -917,17 +937,17 @@ template <class P> struct Frame {
                             const float* w = x.acquire(ci + pass * L::NCHUNK_PASS + c, rows * L::ROW);
                             if (active) {
                                 const float* wl = w + (g.cgp * L::CL + g.cl) * RW;
-    #pragma unroll 2
+#pragma unroll 2
                                 for (int kk = 0; kk < rows; ++kk) {
                                     const int kx = c * L::KC + kk;
                                     float xv[PT], hv[PT], wv[RW];
                                     load_pt<PT>(XR + kx * PR + g.xoff, xv);
                                     load_pt<PT>(HB + kx * PR + g.xoff, hv);
-    #pragma unroll
+#pragma unroll
                                     for (int e = 0; e < RW; e += 4) { f4 t = ld4(wl + kk * L::ROW + e); wv[e] = t.x; wv[e + 1] = t.y; wv[e + 2] = t.z; wv[e + 3] = t.w; }
-    #pragma unroll
+#pragma unroll
                                     for (int i = 0; i < CT; ++i)
-    #pragma unroll
+#pragma unroll
                                         for (int j = 0; j < PT; ++j) {
                                             ar[i][j] = fmaf(wv[3 * CT + i], hv[j], fmaf(wv[0 * CT + i], xv[j], ar[i][j]));
                                             az[i][j] = fmaf(wv[4 * CT + i], hv[j], fmaf(wv[1 * CT + i], xv[j], az[i][j]));
@@ -940,7 +960,7 @@ template <class P> struct Frame {
                         }
                         if (active) {
                             const int gs = x.s0 + g.s;
-    #pragma unroll
+#pragma unroll
                             for (int i = 0; i < CT; ++i) {
                                 const int c = co0 + i;
                                 if (c < C2) {
@@ -948,7 +968,7 @@ template <class P> struct Frame {
                                     const float bin = ldg(aux + ab.b_in + c), bhn = ldg(aux + ab.b_hn + c);
                                     float hn[PT], ho[PT];
                                     load_pt<PT>(HB + c * PR + g.xoff, ho);
-    #pragma unroll
+#pragma unroll
                                     for (int j = 0; j < PT; ++j) {
                                         float r = sigmoid_acc(ar[i][j] + br);
                                         float z = sigmoid_acc(az[i][j] + bz);
@@ -997,28 +1017,46 @@ template <class P> struct Frame {
                             const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
                             const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
                             float q[HD], o[HD];
-    #pragma unroll
+#pragma unroll
                             for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
-                            float mx = -INFINITY;
-                            for (int j = 0; j < F2; ++j) {
-                                float sc = 0.f;
-    #pragma unroll
-                                for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                                mx = fmaxf(mx, sc);
-                            }
-                            float den = 0.f;
-                            for (int j = 0; j < F2; ++j) {
-                                float sc = 0.f;
-    #pragma unroll
-                                for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                                const float p = fe_exp(sc - mx);
-                                den += p;
-    #pragma unroll
-                                for (int d = 0; d < HD; ++d) o[d] = fmaf(p, qb[(2 * HD + d) * PR + j], o[d]);
+                            float mx = -INFINITY, den = 0.f;
+                            if constexpr (F2 <= 48) {          // scores stay in registers between the two softmax passes
+                                float sc[F2];
+#pragma unroll
+                                for (int j = 0; j < F2; ++j) {
+                                    float a = 0.f;
+#pragma unroll
+                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
+                                    sc[j] = a;
+                                    mx = fmaxf(mx, a);
+                                }
+#pragma unroll
+                                for (int j = 0; j < F2; ++j) {
+                                    const float pj = fe_exp(sc[j] - mx);
+                                    den += pj;
+#pragma unroll
+                                    for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
+                                }
+                            } else {
+                                for (int j = 0; j < F2; ++j) {
+                                    float a = 0.f;
+#pragma unroll
+                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
+                                    mx = fmaxf(mx, a);
+                                }
+                                for (int j = 0; j < F2; ++j) {
+                                    float a = 0.f;
+#pragma unroll
+                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
+                                    const float pj = fe_exp(a - mx);
+                                    den += pj;
+#pragma unroll
+                                    for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
+                                }
                             }
                             const float inv = 1.0f / den;
                             float* ob = ATT + ((hg * P::HG + hh) * HD) * PR + s * F2P + i;
-    #pragma unroll
+#pragma unroll
                             for (int d = 0; d < HD; ++d) ob[d * PR] = o[d] * inv;
                         }
                     });
@@ -1065,7 +1103,8 @@ template <class P> struct Frame {
             ci += P::LinPostT::NCHUNK;
             TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
             x.phase(PH_RF_POST, [&](int tid) {
-                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return Zb + 2 * j * SLABF; }, SLABF, S, S, epi);
+                const auto a0 = x.make_desc(Zb + S * 4, SLABF);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
             });
             ci += P::TRfPost::NCHUNK;
         } else {
@@ -1104,14 +1143,16 @@ template <class P> struct Frame {
                 // All MMAs complete before any epilogue thread stores, so writing W0 (which may hold the skip) is safe.
                 TcEpiAct epi{W0, b1, nullptr, true, true};
                 x.phase(PH_PWCAT, [&](int tid) {
+                    const auto ax = x.make_desc(W1 + S * 4, SLABF), as = x.make_desc(skip + S * 4, SLABF);
                     tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
-                        return j < C1 / 8 ? (const float*)W1 + 2 * j * SLABF : skip + 2 * (j - C1 / 8) * SLABF; }, SLABF, S, S, epi);
+                        return j < C1 / 8 ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - C1 / 8) * SLABF); }, S, epi);
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {
                     TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};
                     x.phase(PH_DEC, [&](int tid) {
-                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, SLABF, S, S, epi2);
+                        const auto a0 = x.make_desc(W0 + S * 4, SLABF);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2);
                     });
                     ci += P::TConv3::NCHUNK;
                     if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
@@ -1155,7 +1196,8 @@ template <class P> struct Frame {
         if constexpr (P::TC) {
             TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};
             x.phase(PH_CONVT, [&](int tid) {
-                tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return (const float*)W0 + 2 * j * SLABF; }, SLABF, S, S, epi);
+                const auto a0 = x.make_desc(W0 + S * 4, SLABF);
+                tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
             });
             ci += P::TConvT::NCHUNK;
         } else {

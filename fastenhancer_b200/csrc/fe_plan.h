@@ -132,6 +132,9 @@ struct TcGemm {
     static constexpr int FLOATS = NTILE * TILE;
     static constexpr int NMT = cdiv(NPOS, 128);        // 128-row M tiles
     static constexpr int NG = cdiv(N, 4);              // output channel groups of 4
+    static constexpr int NSPLIT = cdiv(NP, 256);       // one tcgen05.mma covers at most 256 accumulator columns
+    static constexpr int NPS = NP / NSPLIT;
+    static_assert(NPS * NSPLIT == NP && NPS % 16 == 0 && NPS <= 256, "N split");
     static_assert(NMT * NP <= TMEMC_, "accumulators exceed the TMEM allocation");
 };
 
@@ -191,7 +194,20 @@ struct Plan {
     static constexpr int F2P = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
     static constexpr int PR = S * F2P;
     static constexpr int XRS = C::C2 * PR;
-    static constexpr int HG = T::HG, NQG = C::NH / HG;
+    // heads per attention round.  fp32 variants: Tune::HG.  Tensor-core variants: as many as the shared-memory budget
+    // allows (more parallel work for the thread-per-query attention), trading resident skip tensors for scratch.
+    static constexpr int hg_tc() {
+        for (int hg = C::NH; hg > 1; hg /= 2) {
+            if (C::NH % hg) continue;
+            const int act = (C::C1 / 4) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
+            const int f2p = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
+            const int need1 = cmax(3 * C::HD * hg * S * f2p + xts, (C::C1 / 4) * S * C::F2 * 4) + xts;
+            const int rest = 2 * (C::F1 + 2) * S * 4 + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
+            if (cmax(2, cdiv(need1, act)) * act + rest <= 227 * 256) return hg;
+        }
+        return 1;
+    }
+    static constexpr int HG = TC ? hg_tc() : T::HG, NQG = C::NH / HG;
     static_assert(C::NH % HG == 0, "HG must divide NH");
     static constexpr int QKVS = 3 * C::HD * HG * PR;
     // ---- RNNFormer tensor-core geometry ("GeoR", TC variants): [C2P/4][RSLOTS][4], slot = f2*S + s ----

@@ -195,7 +195,7 @@ class Engine:
 
     PHASES = ("init", "load", "window", "fft", "compress", "enc_pre", "enc", "lin_pre", "rf_pre", "hload", "gru", "rnn_fc", "qkv",
               "attn", "attn_fc", "lin_post", "rf_post", "skip_load", "pwcat", "dec", "convt", "mask", "pretw", "ifft", "ola",
-              "dbg", "state")
+              "dbg", "state", "tc:wait_weights", "tc:issue", "tc:mma_done", "tc:tmem_ld", "tc:epi_math")
 
     def enable_profile(self, on: bool = True):
         """Per-phase SM-cycle counters of CTA 0 (int64 cuda tensor, accumulated over launches) or None."""

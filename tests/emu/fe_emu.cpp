@@ -37,12 +37,18 @@ template <class P> struct EmuCtx {
     std::vector<float> tmem = std::vector<float>(128 * 512, std::nanf(""));
     static float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
     void mma_fence() const {}
-    void mma(const float* a, int a_lbo, const float* b, int b_lbo, int NP, int col, bool acc, int rows) {
+    void sub_begin(int) const {}
+    void sub_end(int, int) const {}
+    struct Desc { const float* p; int lbo; };
+    Desc make_desc(const float* p, int lbo_floats) const { return Desc{p, lbo_floats}; }
+    Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
+    void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
+        if (tid != 0) return;                       // one elected lane of warp 0 issues
         for (int m = 0; m < rows; ++m)
             for (int n = 0; n < NP; ++n) {
                 float sum = acc ? tmem[m * 512 + col + n] : 0.f;
                 for (int k = 0; k < 8; ++k)
-                    sum += tf32_trunc(a[(k / 4) * a_lbo + m * 4 + (k % 4)]) * tf32_trunc(b[(k / 4) * b_lbo + n * 4 + (k % 4)]);
+                    sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
                 tmem[m * 512 + col + n] = sum;
             }
     }
