@@ -297,6 +297,26 @@ FE_API int fe_spec(fe_engine* e, fe_state* s, const float* spec_in, float* spec_
     return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream);
 }
 
+FE_API int fe_stft(fe_engine* e, fe_state* s, const float* wav_in, float* spec_out, int n_hops, long long ld_in, void* cuda_stream) {
+    if (!e || !s || s->e != e || !wav_in || !spec_out) return fail(FE_ERR_ARG, "fe_stft: null / mismatched argument");
+    if (n_hops < 0 || ld_in < (long long)n_hops * e->cfg.hop) return fail(FE_ERR_ARG, "fe_stft: leading dimension smaller than n_hops*hop");
+    FE_CUDA(cudaSetDevice(e->device));
+    fe::KParams prm{};
+    prm.state = s->data; prm.in = wav_in; prm.out = spec_out; prm.ld_in = ld_in;
+    prm.n_streams = s->n_streams; prm.n_hops = n_hops; prm.mode = fe::MODE_STFT; prm.dbg_hop = -1;
+    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream);
+}
+
+FE_API int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, int n_hops, long long ld_out, void* cuda_stream) {
+    if (!e || !s || s->e != e || !spec_in || !wav_out) return fail(FE_ERR_ARG, "fe_istft: null / mismatched argument");
+    if (n_hops < 0 || ld_out < (long long)n_hops * e->cfg.hop) return fail(FE_ERR_ARG, "fe_istft: leading dimension smaller than n_hops*hop");
+    FE_CUDA(cudaSetDevice(e->device));
+    fe::KParams prm{};
+    prm.state = s->data; prm.in = spec_in; prm.out = wav_out; prm.ld_out = ld_out;
+    prm.n_streams = s->n_streams; prm.n_hops = n_hops; prm.mode = fe::MODE_ISTFT; prm.dbg_hop = -1;
+    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream);
+}
+
 FE_API int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream) {
     if (!e || !wav || !wav_out || B <= 0) return fail(FE_ERR_ARG, "fe_offline: bad argument");
     if (L <= e->cfg.n_fft / 2) return fail(FE_ERR_ARG, "fe_offline: input shorter than n_fft/2 + 1 samples (reflect padding needs more)");

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     if constexpr (P::TC) tc_fence_after();
     if (threadIdx.x >= P::NT) {
         // ---------------- producer warp: stream the weights of every frame through the ring ----------------
-        if (threadIdx.x == P::NT) {
+        if (threadIdx.x == P::NT && prm.mode <= MODE_OFFLINE) {      // the STFT-only modes consume no weights
             constexpr auto A = P::make_aux();
             const int* table = reinterpret_cast<const int*>(prm.blob + A.table);
             const uint32_t ring = smem_u32(sm + P::SM_RING);

@@ -432,7 +432,8 @@ template <class P> struct Frame {
         x.phase(PH_INIT, [&](int tid) {
             for (int i = tid * 4; i < P::SM_RING; i += NT * 4) st4(sm + i, mk4(0.f, 0.f, 0.f, 0.f));
         });
-        if (prm.mode == MODE_STREAM) {
+        const bool has_model = prm.mode <= MODE_OFFLINE;
+        if (prm.mode == MODE_STREAM || prm.mode >= MODE_STFT) {
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::CL; idx += NT) {
                     int s = idx / C::CL, i = idx % C::CL;
@@ -447,7 +448,7 @@ template <class P> struct Frame {
                 }
             });
         }
-        if constexpr (P::H_RES) {       // GRU state of every block stays in shared memory for the whole launch
+        if (P::H_RES && has_model) {    // GRU state of every block stays in shared memory for the whole launch
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::K * P::C2P * F2; idx += NT) {
                     const int s = idx / (C::K * P::C2P * F2), r = idx % (C::K * P::C2P * F2);
@@ -462,7 +463,7 @@ template <class P> struct Frame {
             frame(x, hop);
             x.next_frame();
         }
-        if constexpr (P::H_RES) {
+        if (P::H_RES && has_model) {
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::K * C2 * F2; idx += NT) {
                     const int s = idx / (C::K * C2 * F2), r = idx % (C::K * C2 * F2);
@@ -472,7 +473,7 @@ template <class P> struct Frame {
                 }
             });
         }
-        if (prm.mode == MODE_STREAM) {
+        if (prm.mode == MODE_STREAM || prm.mode >= MODE_STFT) {
             const int n = prm.n_hops;
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::CL; idx += NT) {
@@ -480,8 +481,8 @@ template <class P> struct Frame {
                     int gs = x.s0 + s;
                     if (gs < prm.n_streams) {
                         float* st = prm.state + (size_t)gs * C::STATE;
-                        st[i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
-                        st[C::CL + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
+                        if (prm.mode != MODE_ISTFT) st[i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
+                        if (prm.mode != MODE_STFT) st[C::CL + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
                     }
                 }
             });
@@ -733,6 +734,63 @@ template <class P> struct Frame {
         return ci;
     }
 
+    // ---- irFFT (packed real), synthesis window, overlap-add, emit one hop.  The decompressed spectrum (bins 0..M-1)
+    //      is in W0; the Nyquist bin is zero in the fused path and SPEC[s] (real part) for the standalone inverse ----
+    template <class X> FE_DEV static void back_end(X& x, int hop) {
+        const KParams& prm = x.prm;
+        constexpr auto A = P::make_aux();
+        const float* aux = x.blob;
+        float* sm = x.sm;
+        float* W0 = sm + P::SM_W;
+        float* W1 = W0 + ACT;
+        float* SPEC = sm + P::SM_SPEC;
+        float* OLA = sm + P::SM_OLA;
+        const int mode = prm.mode;
+        const int T = prm.n_hops;
+        x.phase(PH_PRETW, [&](int tid) {
+            for (int idx = tid; idx < S * M; idx += NT) {
+                const int s = idx / M, k = idx % M;
+                f2 yk = ld2(W0 + s * N + 2 * k), ym;
+                if (k == 0) { yk.y = 0.f; ym = mk2(mode == MODE_ISTFT ? SPEC[s] : 0.f, 0.f); }   // imag of DC / Nyquist ignored
+                else ym = ld2(W0 + s * N + 2 * (M - k));
+                const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
+                const float dr = 0.5f * (yk.x - ym.x), di = 0.5f * (yk.y + ym.y);
+                f2 w = ldg2(aux + A.twn + 2 * k);                        // O = D * conj(w)
+                const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+                st2(W1 + s * N + 2 * k, mk2(er - oi, ei + orr));         // Z = E + i O
+            }
+        });
+        const float* Y = fft(x, W1, W0, true);
+        const int base = (hop * H) & NMASK;
+        x.phase(PH_OLA, [&](int tid) {
+            const float invM = 1.0f / (float)M;
+            for (int idx = tid; idx < S * N; idx += NT) {
+                const int s = idx / N, i = idx % N, gs = x.s0 + s;
+                const int slot = s * N + ((base + i) & NMASK);
+                float y = Y[s * N + i] * invM;
+                if (mode != MODE_OFFLINE) {
+                    float v = y * ldg(aux + A.window_istft + i) + (i < C::CL ? OLA[slot] : 0.f);
+                    OLA[slot] = v;
+                    if (i < H && gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = v;
+                } else {          // torch.istft(center=True): window, overlap-add, / sum of window^2, trim N/2
+                    float v = y * ldg(aux + A.window + i) + (i < C::CL ? OLA[slot] : 0.f);
+                    OLA[slot] = v;
+                    const long npad = (long)hop * H + i, n = npad - N / 2;
+                    // samples [hop*H, hop*H + H) are final after this frame; the last frame also flushes its tail
+                    if ((i < H || hop == T - 1) && gs < prm.n_streams && n >= 0 && n < (long)H * (T - 1)) {
+                        long t0 = (npad - N + H) / H;                     // ceil((npad - N + 1) / H) for npad >= N - 1
+                        if (npad < N) t0 = 0;
+                        long t1 = npad / H;
+                        if (t1 > T - 1) t1 = T - 1;
+                        float env = 0.f;
+                        for (long t = t0; t <= t1; ++t) env += ldg(aux + A.window_sq + (int)(npad - t * H));
+                        prm.out[(size_t)gs * H * (T - 1) + n] = v / env;
+                    }
+                }
+            }
+        });
+    }
+
     template <class X> FE_DEV static void frame(X& x, int hop) {
         const KParams& prm = x.prm;
         constexpr auto A = P::make_aux();
@@ -751,9 +809,22 @@ template <class P> struct Frame {
         int ci = 0;    // chunk index within the frame
 
         // ================= front end =================
-        if (mode != MODE_SPEC) {
+        if (mode == MODE_ISTFT) {
+            // standalone inverse: spectrum [B][NB][T][2] -> W0 (bins 0..M-1) + real part of the Nyquist bin in SPEC[s]
+            x.phase(PH_COMPRESS, [&](int tid) {
+                for (int idx = tid; idx < S * (M + 1); idx += NT) {
+                    const int s = idx / (M + 1), k = idx % (M + 1), gs = x.s0 + s;
+                    f2 v = mk2(0.f, 0.f);
+                    if (gs < prm.n_streams) v = ld2(prm.in + (((size_t)gs * C::NB + k) * T + hop) * 2);
+                    if (k < M) st2(W0 + s * N + 2 * k, v);
+                    else SPEC[s] = v.x;
+                }
+            });
+            back_end(x, hop);
+            return;
+        } else if (mode != MODE_SPEC) {
             const int wpos = (hop * H) & NMASK;
-            if (mode == MODE_STREAM) {
+            if (mode == MODE_STREAM || mode == MODE_STFT) {
                 x.phase(PH_LOAD, [&](int tid) {
                     for (int idx = tid; idx < S * H; idx += NT) {
                         int s = idx / H, j = idx % H, gs = x.s0 + s;
@@ -767,7 +838,7 @@ template <class P> struct Frame {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
                     float a, b;
-                    if (mode == MODE_STREAM) {
+                    if (mode != MODE_OFFLINE) {
                         a = TIN[s * N + ((wpos + H + n2) & NMASK)];
                         b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
                     } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
@@ -786,6 +857,23 @@ template <class P> struct Frame {
                 }
             });
             float* Z = fft(x, W0, W1, false);
+            if (mode == MODE_STFT) {      // ONNXSTFT.forward: all n_fft/2 + 1 bins, no compression
+                x.phase(PH_COMPRESS, [&](int tid) {
+                    for (int idx = tid; idx < S * M; idx += NT) {
+                        int s = idx / M, k = idx % M, gs = x.s0 + s;
+                        f2 zk = ld2(Z + s * N + 2 * k), zm = ld2(Z + s * N + 2 * ((M - k) & (M - 1)));
+                        float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+                        float dr = 0.5f * (zk.x - zm.x), di = 0.5f * (zk.y + zm.y);
+                        f2 w = ldg2(aux + A.twn + 2 * k);
+                        float re = er + (w.x * di + w.y * dr), im = ei + (w.y * di - w.x * dr);
+                        if (gs < prm.n_streams) {
+                            st2(prm.out + (((size_t)gs * C::NB + k) * T + hop) * 2, mk2(re, im));
+                            if (k == 0) st2(prm.out + (((size_t)gs * C::NB + M) * T + hop) * 2, mk2(zk.x - zk.y, 0.f));   // Nyquist
+                        }
+                    }
+                });
+                return;
+            }
             // unpack the packed real FFT, drop Nyquist, compress, scatter to the 8 virtual channels
             x.phase(PH_COMPRESS, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
@@ -1236,49 +1324,7 @@ template <class P> struct Frame {
         });
         if (mode == MODE_SPEC) return;
 
-        // ================= irFFT (packed), window, overlap-add =================
-        x.phase(PH_PRETW, [&](int tid) {
-            for (int idx = tid; idx < S * M; idx += NT) {
-                const int s = idx / M, k = idx % M;
-                f2 yk = ld2(W0 + s * N + 2 * k), ym;
-                if (k == 0) { yk.y = 0.f; ym = mk2(0.f, 0.f); }        // imag of DC ignored, Nyquist bin is zero
-                else ym = ld2(W0 + s * N + 2 * (M - k));
-                const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
-                const float dr = 0.5f * (yk.x - ym.x), di = 0.5f * (yk.y + ym.y);
-                f2 w = ldg2(aux + A.twn + 2 * k);                        // O = D * conj(w)
-                const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
-                st2(W1 + s * N + 2 * k, mk2(er - oi, ei + orr));         // Z = E + i O
-            }
-        });
-        const float* Y = fft(x, W1, W0, true);
-        const int base = (hop * H) & NMASK;
-        x.phase(PH_OLA, [&](int tid) {
-            const float invM = 1.0f / (float)M;
-            for (int idx = tid; idx < S * N; idx += NT) {
-                const int s = idx / N, i = idx % N, gs = x.s0 + s;
-                const int slot = s * N + ((base + i) & NMASK);
-                float y = Y[s * N + i] * invM;
-                if (mode == MODE_STREAM) {
-                    float v = y * ldg(aux + A.window_istft + i) + (i < C::CL ? OLA[slot] : 0.f);
-                    OLA[slot] = v;
-                    if (i < H && gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = v;
-                } else {          // torch.istft(center=True): window, overlap-add, / sum of window^2, trim N/2
-                    float v = y * ldg(aux + A.window + i) + (i < C::CL ? OLA[slot] : 0.f);
-                    OLA[slot] = v;
-                    const long npad = (long)hop * H + i, n = npad - N / 2;
-                    // samples [hop*H, hop*H + H) are final after this frame; the last frame also flushes its tail
-                    if ((i < H || hop == T - 1) && gs < prm.n_streams && n >= 0 && n < (long)H * (T - 1)) {
-                        long t0 = (npad - N + H) / H;                     // ceil((npad - N + 1) / H) for npad >= N - 1
-                        if (npad < N) t0 = 0;
-                        long t1 = npad / H;
-                        if (t1 > T - 1) t1 = T - 1;
-                        float env = 0.f;
-                        for (long t = t0; t <= t1; ++t) env += ldg(aux + A.window_sq + (int)(npad - t * H));
-                        prm.out[(size_t)gs * H * (T - 1) + n] = v / env;
-                    }
-                }
-            }
-        });
+        back_end(x, hop);
     }
 };
 

@@ -361,8 +361,8 @@ struct Plan {
 struct KParams {
     const float* blob;        // packed weights + tables (device)
     float* state;             // [n_streams][STATE] native layout: cache_stft | cache_istft | h[K][C2][F2]
-    const float* in;          // mode 0: wav [n_streams][ld_in]; mode 1: spec [B][NB][T][2]; mode 2: wav [B][L]
-    float* out;               // mode 0: wav [n_streams][ld_out]; mode 1: spec [B][NB][T][2]; mode 2: wav [B][H*(T-1)]
+    const float* in;          // mode 0/3: wav [n_streams][ld_in]; mode 1/4: spec [B][NB][T][2]; mode 2: wav [B][L]
+    float* out;               // mode 0/4: wav [n_streams][ld_out]; mode 1/3: spec [B][NB][T][2]; mode 2: wav [B][H*(T-1)]
     float* spec_out;          // mode 2 (optional): compressed masked spectrum [B][FIN][T][2]
     float* scratch;           // global scratch [grid][GS_TOTAL]
     float* dbg;               // optional tap dump of stream 0 (oracle tap layout), frame `dbg_hop`
@@ -373,6 +373,8 @@ struct KParams {
     float compression;
 };
 
-enum { MODE_STREAM = 0, MODE_SPEC = 1, MODE_OFFLINE = 2 };
+// MODE_STFT / MODE_ISTFT: the front / back end alone (ONNXSTFT.forward / .inverse, functional/audio_modules.py:243-303);
+// they consume no weights, so the producer warp stays idle.
+enum { MODE_STREAM = 0, MODE_SPEC = 1, MODE_OFFLINE = 2, MODE_STFT = 3, MODE_ISTFT = 4 };
 
 }  // namespace fe

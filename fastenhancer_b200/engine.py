@@ -21,7 +21,7 @@ _lib = None
 ABI_SYMBOLS = (
     "fe_last_error", "fe_weight_count", "fe_state_floats", "fe_create", "fe_destroy", "fe_state_create",
     "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
-    "fe_spec", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
+    "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision",
 )
 
@@ -71,6 +71,8 @@ def load_library(build_if_missing: bool = True):
     lib.fe_stream_host.argtypes = [vp, vp, fp, fp, ip, ll, ll, ip]
     lib.fe_spec.argtypes = [vp, vp, fp, fp, ip, vp]
     lib.fe_offline.argtypes = [vp, fp, ip, ip, fp, fp, vp]
+    lib.fe_stft.argtypes = [vp, vp, fp, fp, ip, ll, vp]
+    lib.fe_istft.argtypes = [vp, vp, fp, fp, ip, ll, vp]
     lib.fe_streams_per_cta.argtypes = [vp, ip]
     lib.fe_set_streams_per_cta.argtypes = [vp, ip]
     lib.fe_kernel_launches.argtypes = [vp]
@@ -261,6 +263,30 @@ class Engine:
         if out is None:
             out = torch.empty_like(x)
         _check(self._lib.fe_spec(self._h, state._h, x.data_ptr(), out.data_ptr(), T, _stream_ptr()), "fe_spec")
+        return out
+
+    def stft(self, state: State, wav_in):
+        """ONNXSTFT.forward for every hop of wav_in [B, n_hops*hop] -> spectrum [B, n_fft/2+1, n_hops, 2]; uses / updates
+        the cache_stft part of ``state``."""
+        import torch
+        x = self._dev(wav_in)
+        B, L = x.shape
+        H = self.cfg.hop_size
+        if B != state.n_streams or L % H:
+            raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(x.shape)}")
+        out = torch.empty((B, self.cfg.n_fft // 2 + 1, L // H, 2), dtype=torch.float32, device=self.device)
+        _check(self._lib.fe_stft(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), _stream_ptr()), "fe_stft")
+        return out
+
+    def istft(self, state: State, spec_in):
+        """ONNXSTFT.inverse: spectrum [B, n_fft/2+1, T, 2] -> wav [B, T*hop]; uses / updates the cache_istft part of ``state``."""
+        import torch
+        x = self._dev(spec_in)
+        B, NB, T, two = x.shape
+        if B != state.n_streams or NB != self.cfg.n_fft // 2 + 1 or two != 2:
+            raise ValueError(f"bad spectrum shape {tuple(x.shape)}")
+        out = torch.empty((B, T * self.cfg.hop_size), dtype=torch.float32, device=self.device)
+        _check(self._lib.fe_istft(self._h, state._h, x.data_ptr(), out.data_ptr(), T, out.stride(0), _stream_ptr()), "fe_istft")
         return out
 
     def offline(self, wav, want_spec: bool = True):

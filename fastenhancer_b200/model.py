@@ -16,6 +16,7 @@ The modules hold the reference's *pre-fold* parameters under the reference's own
 ``load_state_dict(ckpt['model'], strict=True)`` works on a reference checkpoint
 (wrappers/ns.py:308-321).  Parameters are folded (fastenhancer_b200.fold) and packed on first use;
 every forward then is a launch of the fused kernel through the C ABI.  There is no PyTorch compute path.
+``ONNXModel.stft(x, cache)`` / ``.stft.inverse(spec, cache)`` run the front / back end of the same kernel on their own.
 """
 from __future__ import annotations
 
@@ -177,11 +178,22 @@ class ONNXModel(nn.Module):
     # per-hop STFT / iSTFT shims (functional/audio_modules.py:243-303); one fused-kernel launch each
     @torch.no_grad()
     def _stft_forward(self, x: Tensor, cache: tp.Optional[Tensor]):
-        raise NotImplementedError("standalone per-hop STFT is served by StreamingModel (fused wav->wav step)")
+        """ONNXSTFT.forward: x [B, k*hop], cache [B, N-H] -> (spec [B, N/2+1, k, 2], cache)."""
+        B = x.size(0)
+        st = self._state(B)
+        st.load(self._pack_state(B, cache, None, None))
+        spec = self.engine.stft(st, x)
+        return spec.to(x.device), st.export()[:, :self.cfg.cache_len].to(x.device)
 
     @torch.no_grad()
     def _stft_inverse(self, spec: Tensor, cache: tp.Optional[Tensor]):
-        raise NotImplementedError("standalone per-hop iSTFT is served by StreamingModel (fused wav->wav step)")
+        """ONNXSTFT.inverse: spec [B, N/2+1, T, 2], cache [B, N-H] -> (wav [B, T*hop], cache)."""
+        B = spec.size(0)
+        st = self._state(B)
+        st.load(self._pack_state(B, None, cache, None))
+        wav = self.engine.istft(st, spec)
+        cl = self.cfg.cache_len
+        return wav.to(spec.device), st.export()[:, cl:2 * cl].to(spec.device)
 
 
 class Model(ONNXModel):

@@ -82,6 +82,13 @@ int fe_stream_host(fe_engine* e, fe_state* s, const float* wav_in_host, float* w
  * scripts/export_onnx_spec.py:135-142).  spec_in / spec_out: device, [n_streams][n_fft/2+1][T][2]. */
 int fe_spec(fe_engine* e, fe_state* s, const float* spec_in, float* spec_out, int T, void* cuda_stream);
 
+/* Replace: ONNXSTFT.forward(x, cache) / ONNXSTFT.inverse(spec, cache) (functional/audio_modules.py:243-303) on their own,
+ * for callers that compose the streaming graph themselves (scripts/export_onnx.py:53-57).  They use the cache_stft /
+ * cache_istft parts of `s`.  wav: [n_streams][ld] device; spec: [n_streams][n_fft/2+1][n_hops][2] device
+ * (fe_stft writes all n_fft/2+1 bins; fe_istft ignores the imaginary parts of the DC and Nyquist bins, like irfft). */
+int fe_stft(fe_engine* e, fe_state* s, const float* wav_in, float* spec_out, int n_hops, long long ld_in, void* cuda_stream);
+int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, int n_hops, long long ld_out, void* cuda_stream);
+
 /* Replaces: Model.forward(noisy) (model.py:728-735): wav [B][L] -> wav_out [B][hop*(L/hop)] and (optional)
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);

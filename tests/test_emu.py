@@ -71,3 +71,32 @@ def test_spec_and_offline_modes(name, S, tc, canonical):
     emu.run(cfg, S, canon, emu.MODE_OFFLINE, stn, w, w_out, spec_out=sp_out, n_streams=B, n_hops=1 + L // H, L=L, tc=tc)
     assert np.sqrt(np.mean((w_out - w_ref) ** 2)) < TOL[tc]["wav"]
     assert np.abs(sp_out - sp_ref).max() < TOL[tc]["spec_abs"] * max(1.0, np.abs(sp_ref).max())
+
+
+@pytest.mark.parametrize("name,S,tc", [("16k_b", 2, True), ("16k_m", 1, False), ("48k_t", 2, True)])
+def test_standalone_stft_istft_modes(name, S, tc, canonical):
+    """fe_stft / fe_istft kernels (ONNXSTFT.forward / inverse on their own) against numpy's rfft / irfft, including the
+    Nyquist bin that the fused path drops, ragged hops (M: hop 160) and the cache hand-over."""
+    cfg = PRESETS[name]
+    canon = canonical(name)
+    o = Oracle(cfg, canon)
+    B, nh, H, N = 3, 5, cfg.hop_size, cfg.n_fft
+    w, wi = o.windows()
+    x = synthetic_noisy(B, nh * H, cfg.sample_rate)
+    hist = np.concatenate([np.zeros((B, N - H), np.float32), x], axis=1)
+    ref = np.stack([np.fft.rfft(hist[:, t * H:t * H + N].astype(np.float64) * w, axis=1) for t in range(nh)], axis=2)
+    stn = emu.to_native(cfg, o.new_state(B))
+    spec = np.full((B, N // 2 + 1, nh, 2), np.nan, np.float32)
+    emu.run(cfg, S, canon, 3, stn, x, spec, n_streams=B, n_hops=nh, ld_in=nh * H, tc=tc)
+    assert np.abs((spec[..., 0] + 1j * spec[..., 1]) - ref).max() < 1e-6 * np.abs(ref).max()
+    assert np.array_equal(emu.to_canonical(cfg, stn)[:, :N - H], hist[:, -(N - H):])
+    sp = np.random.RandomState(2).standard_normal((B, N // 2 + 1, nh, 2)).astype(np.float32)
+    frames = np.fft.irfft(sp[..., 0].astype(np.float64) + 1j * sp[..., 1], n=N, axis=1) * wi[None, :, None]
+    acc = np.zeros((B, N + H * nh))
+    for t in range(nh):
+        acc[:, t * H:t * H + N] += frames[:, :, t]
+    stn = emu.to_native(cfg, o.new_state(B))
+    wav = np.full((B, nh * H), np.nan, np.float32)
+    emu.run(cfg, S, canon, 4, stn, sp, wav, n_streams=B, n_hops=nh, ld_out=nh * H, tc=tc)
+    assert np.abs(wav - acc[:, :nh * H]).max() < 1e-6
+    assert np.abs(emu.to_canonical(cfg, stn)[:, N - H:2 * (N - H)] - acc[:, nh * H:nh * H + N - H]).max() < 1e-6

@@ -218,3 +218,28 @@ def test_model_classes_drop_in(golden):
         hops.append(y)
     assert rms(torch.cat(hops, dim=1).cpu().numpy() - g["stream_out"]) < 5e-5
     assert rms(sm.run(x).cpu().numpy() - g["stream_out"]) < 5e-5
+
+
+def test_reference_style_composition_with_stft_shims(golden):
+    """The streaming graph composed the reference's way (scripts/export_onnx.py:53-57): stft -> model -> stft.inverse,
+    explicit caches, hop by hop -- three kernel launches per hop through ONNXModel.stft / ONNXModel."""
+    from fastenhancer_b200.model import ONNXModel
+    for name in ("16k_t", "16k_m"):
+        cfg, g = PRESETS[name], golden(name)
+        m = ONNXModel(**cfg.to_model_kwargs()).eval().cuda()
+        H = cfg.hop_size
+        x = torch.from_numpy(synthetic_noisy(2, N_HOPS * H, cfg.sample_rate)).cuda()
+        c_stft, c_istft = m.stft.initialize_cache(x[:, :H])
+        hs = m.initialize_cache(x[:, :H])
+        hops = []
+        for i in range(N_HOPS):
+            spec_in, c_stft = m.stft(x[:, i * H:(i + 1) * H], c_stft)
+            assert spec_in.shape == (2, cfg.n_fft // 2 + 1, 1, 2)
+            spec_out, *hs = m(spec_in, *hs)
+            y, c_istft = m.stft.inverse(spec_out, c_istft)
+            hops.append(y)
+        assert rms(torch.cat(hops, dim=1).cpu().numpy() - g["stream_out"]) < 5e-5, name
+        # the front end alone against torch.fft on the same frames
+        ref = torch.fft.rfft(torch.cat([torch.zeros(2, cfg.n_fft - H, device="cuda"), x[:, :H]], dim=1) * m.stft.window.cuda(), dim=1)
+        got, _ = m.stft(x[:, :H], None)
+        assert (torch.view_as_complex(got[:, :, 0].contiguous()) - ref).abs().max() < 1e-5 * ref.abs().max()

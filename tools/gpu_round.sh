@@ -28,6 +28,11 @@ echo "=== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fe_fused -s 1 -c 1 -o $OUT/prof_fused \
    python tools/gpu_diag.py --time 16k_b 256 60 > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/prof_fused.ncu-rep --page raw --csv > $OUT/prof_fused_raw.csv 2>/dev/null
+echo "=== dram traffic of the bench launch (roofline.traffic)"
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:fe_fused -s 3 -c 1 --csv \
+   --log-file $OUT/bench_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/bench_traffic_run.log 2>&1
+echo "=== batch-1 latency sweep"
+timeout 600 python tools/latency_sweep.py 2000 tf32 2>&1 | tee $OUT/latency_sweep.jsonl
 echo "=== sanitizers"
 timeout 300 compute-sanitizer --tool memcheck --log-file $OUT/memcheck.log python tools/gpu_diag.py 16k_t 2 3 2 > $OUT/memcheck_run.log 2>&1; tail -3 $OUT/memcheck.log
 timeout 300 compute-sanitizer --tool memcheck --log-file $OUT/memcheck_l.log python tools/gpu_diag.py 16k_l 1 2 2 > $OUT/memcheck_l_run.log 2>&1; tail -3 $OUT/memcheck_l.log
