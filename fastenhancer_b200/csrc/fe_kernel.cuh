@@ -285,6 +285,9 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
 // protocol going.  Operand descriptors are built once and advanced by one add per MMA.
 template <class L, class X, class Issue>
 FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
+    // fully unrolled: tile indices, taps and k-steps become compile-time constants, so each MMA costs two adds with
+    // immediates on the descriptors (the tensor front end accepts one small MMA every ~41 cycles; tools/tc_issue_bench.cu)
+#pragma unroll
     for (int c = 0; c < L::NCHUNK; ++c) {
         const int tiles = (c == L::NCHUNK - 1) ? L::NTILE - c * L::TPC : L::TPC;
         x.sub_begin(tid);
@@ -293,7 +296,9 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
         if ((tid >> 5) == 0) {
             x.mma_fence();
             const typename X::Desc wd = x.make_desc(w, L::NP * 4);
-            for (int i = 0; i < tiles; ++i) issue(c * L::TPC + i, x.desc_add(wd, i * L::TILE));
+#pragma unroll
+            for (int i = 0; i < L::TPC; ++i)
+                if (i < tiles) issue(c * L::TPC + i, x.desc_add(wd, i * L::TILE));
         }
         x.release_mma(ci0 + c);
         x.sub_end(tid, PH_TC_ISSUE);
