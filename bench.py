@@ -128,7 +128,7 @@ def run_reference(args, cfg, canon, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_streams = args.streams
+    n_streams = args.streams * max(1, args.gpus)          # the whole job of the N-GPU arm (weak scaling)
     # bounded sample of the same workload: all streams, the first `hops` hops of the utterance
     probe_rate, _ = cpu_oracle_rate(cfg, canon, min(n_streams, threads), 4, threads)
     hops = int(max(2, min(args.ref_seconds * probe_rate / n_streams, workload(cfg, args.seconds)[1])))
@@ -146,7 +146,7 @@ def run_reference(args, cfg, canon, rank, world):
         "rtf": float(np.mean(times) / (hops * cfg.hop_size / cfg.sample_rate)),
         "config": {"workload": f"FastEnhancer_{args.preset.split('_')[1].upper()} {cfg.sample_rate // 1000} kHz streaming wav2wav, "
                                f"{n_streams} streams, hop {cfg.hop_size}, fp32 (bounded sample)", "preset": args.preset,
-                   "streams_per_gpu": n_streams, "hops_per_step": hops},
+                   "streams_per_gpu": args.streams, "streams_total": n_streams, "hops_per_step": hops},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
