@@ -64,6 +64,24 @@ FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=
 }  // namespace fe
 #endif
 
+// FE_FAST_ACT (tensor-core variants only): 0 = ex2/rcp forms; 1 = tanh.approx SiLU in the epilogues; 2 (default) = also the GRU
+// gates.  Measured on B200 (B, 40 hops): waveform RMS error vs oracle 5.93e-6 / 5.92e-6 / 5.91e-6, 4.34 / 4.66 / 4.82 M frames/s.
+#ifndef FE_FAST_ACT
+#define FE_FAST_ACT 2
+#endif
+#if FE_FAST_ACT >= 1
+#define FE_TC_SILU(x) silu_fast(x)
+#else
+#define FE_TC_SILU(x) silu(x)
+#endif
+#if FE_FAST_ACT >= 2
+#define FE_TC_SIGMOID(x) sigmoid_fast(x)
+#define FE_TC_TANH(x) tanh_fast(x)
+#else
+#define FE_TC_SIGMOID(x) sigmoid_acc(x)
+#define FE_TC_TANH(x) tanh_acc(x)
+#endif
+
 namespace fe {
 
 // phase ids for the optional in-kernel profile (KParams::prof): cycles of CTA 0 accumulated per id
@@ -82,6 +100,15 @@ FE_DEV float tanh_acc(float x) {
     const float xc = fminf(fmaxf(x, -15.f), 15.f);
     return 1.0f - fe_div(2.0f, 1.0f + fe_exp(2.0f * xc));
 }
+// Single-MUFU forms for the tensor-core variants' epilogues (tanh.approx.f32, error ~2^-11 -- the same size as the
+// TF32 rounding the value gets right after): silu(x) = h + h tanh(h), sigmoid(x) = 0.5 + 0.5 tanh(h), h = x / 2.
+#if defined(FE_EMU)
+FE_DEV float tanh_fast(float x) { return tanhf(x); }
+#else
+FE_DEV float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+FE_DEV float silu_fast(float x) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+FE_DEV float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 template <int PT> FE_DEV void load_pt(const float* p, float* v) {
     if constexpr (PT == 4) { f4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
@@ -401,7 +428,7 @@ template <class P> struct Frame {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float t = v[e] + bv[e];
-                t = act ? silu(t) : t;
+                t = act ? FE_TC_SILU(t) : t;
                 o[e] = round ? tf32_rna(t) : t;
             }
             const int off = g * SLABF + (S + gp) * 4;
@@ -635,9 +662,9 @@ template <class P> struct Frame {
                         const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float r = sigmoid_acc(vr[e] + br[e]);
-                            const float z = sigmoid_acc(vz[e] + bz[e]);
-                            const float nn = tanh_acc(vx[e] + bi[e] + r * (vh[e] + bh[e]));
+                            const float r = FE_TC_SIGMOID(vr[e] + br[e]);
+                            const float z = FE_TC_SIGMOID(vz[e] + bz[e]);
+                            const float nn = FE_TC_TANH(vx[e] + bi[e] + r * (vh[e] + bh[e]));
                             hn[e] = (1.0f - z) * nn + z * hov[e];
                         }
                         st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed

@@ -14,7 +14,8 @@ import numpy as np
 
 from .config import FEConfig
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfastenhancer_b200.so")
+# FE_LIB overrides the library path (experiments with alternative builds of the same C ABI)
+_LIB_PATH = os.environ.get("FE_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfastenhancer_b200.so")
 _lib = None
 
 #: every symbol include/fastenhancer_b200.h declares (checked by tests/test_abi.py)
