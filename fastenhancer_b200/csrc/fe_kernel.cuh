@@ -584,10 +584,7 @@ template <class P> struct Frame {
         auto store_x = [&](int p, int g, const float* o) {
             st4(XR + g * RSLABF + p * 4, mk4(o[0], o[1], o[2], o[3]));
             if constexpr (P::XT_COPY) st4(XT + g * RSLABF + p * 4, mk4(tf32_rna(o[0]), tf32_rna(o[1]), tf32_rna(o[2]), tf32_rna(o[3])));
-            if (NGP > NGX && g == NGX - 1) {
-                st4(XR + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));
-                if constexpr (P::XT_COPY) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));
-            }
+            if (NGP > NGX && g == NGX - 1) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
         };
 
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
@@ -640,39 +637,46 @@ template <class P> struct Frame {
                     const bool acc = set < 3 ? j > 0 : (set == 5 ? j > 0 : true);
                     x.mma(tid, x.desc_add(set < 3 ? dx : dh, 2 * j * RSLABF), wd, NPG, col, acc, P::RSLOTS);
                 });
-                constexpr int GH = (NGX + 1) / 2;
+                constexpr int GH = (NGX + 1) / 2, GB = 3;              // channel groups per thread, loaded GB at a time
                 const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
                 const int f = p / S, s = p % S, gs = x.s0 + s;
-                for (int i = 0; i < GH; ++i) {
-                    const int g = half * GH + i;
-                    float vr[4], vz[4], vx[4], vh[4];
-                    if (g < NGX) {
-                        x.tmem_ld4(tid, 0 * NPG + 4 * g, vr); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz);
-                        x.tmem_ld4(tid, 2 * NPG + 4 * g, vx); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh);
+                for (int i0 = 0; i0 < GH; i0 += GB) {
+                    float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4];
+#pragma unroll
+                    for (int b = 0; b < GB; ++b) {
+                        const int g = half * GH + i0 + b;
+                        if (i0 + b < GH && g < NGX) {
+                            x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
+                            x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                        }
                     }
                     x.tmem_ld_wait();
-                    if (g < NGX && p < P::RSLOTS) {
-                        float* hp = H + g * RSLABF + p * 4;
-                        const f4 ho = ld4(hp);
-                        const float hov[4] = {ho.x, ho.y, ho.z, ho.w};
-                        float hn[4];
-                        const f4 b4r = ldg4(aux + ab.b_r + 4 * g), b4z = ldg4(aux + ab.b_z + 4 * g);
-                        const f4 b4i = ldg4(aux + ab.b_in + 4 * g), b4h = ldg4(aux + ab.b_hn + 4 * g);
-                        const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w};
-                        const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float r = FE_TC_SIGMOID(vr[e] + br[e]);
-                            const float z = FE_TC_SIGMOID(vz[e] + bz[e]);
-                            const float nn = FE_TC_TANH(vx[e] + bi[e] + r * (vh[e] + bh[e]));
-                            hn[e] = (1.0f - z) * nn + z * hov[e];
-                        }
-                        st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed
-                        if constexpr (!P::H_RES) {
-                            if (gs < prm.n_streams) {
-                                float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)(4 * g) * F2 + f;
+                    for (int b = 0; b < GB; ++b) {
+                        const int g = half * GH + i0 + b;
+                        if (i0 + b < GH && g < NGX && p < P::RSLOTS) {
+                            float* hp = H + g * RSLABF + p * 4;
+                            const f4 ho = ld4(hp);
+                            const float hov[4] = {ho.x, ho.y, ho.z, ho.w};
+                            float hn[4];
+                            const f4 b4r = ldg4(aux + ab.b_r + 4 * g), b4z = ldg4(aux + ab.b_z + 4 * g);
+                            const f4 b4i = ldg4(aux + ab.b_in + 4 * g), b4h = ldg4(aux + ab.b_hn + 4 * g);
+                            const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w};
+                            const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) gp[e * F2] = hn[e];
+                            for (int e = 0; e < 4; ++e) {
+                                const float r = FE_TC_SIGMOID(vr[b][e] + br[e]);
+                                const float z = FE_TC_SIGMOID(vz[b][e] + bz[e]);
+                                const float nn = FE_TC_TANH(vx[b][e] + bi[e] + r * (vh[b][e] + bh[e]));
+                                hn[e] = (1.0f - z) * nn + z * hov[e];
+                            }
+                            st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed
+                            if constexpr (!P::H_RES) {
+                                if (gs < prm.n_streams) {
+                                    float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)(4 * g) * F2 + f;
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) gp[e * F2] = hn[e];
+                                }
                             }
                         }
                     }
@@ -696,45 +700,62 @@ template <class P> struct Frame {
             ci += P::TFc::NCHUNK;
             if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
             // ---- attention over the F2 tokens of the frame, HG heads per round ----
+            // qkv on the tensor cores -> QKV[position][head][q|k|v][HDP] (float4 everywhere), then thread-per-query softmax
             for (int hg = 0; hg < P::NQG; ++hg) {
                 x.phase(PH_QKV, [&](int tid) {
                     const auto a0 = x.make_desc(XT, RSLABF);
                     tc_layer<typename P::TQkv>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
                                                [&](int p, int g, const float* v) {
-                        float* q = QKV + (4 * g) * PR + (p % S) * F2P + p / S;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (4 * g + e < 3 * HD * P::HG) q[e * PR] = v[e] + ldg(aux + ab.qkv_b + hg * 3 * HD * P::HG + 4 * g + e);
+                        const f4 b4 = ldg4(aux + ab.qkv_b + hg * P::QN + 4 * g);
+                        st4(QKV + p * P::QROW + 4 * g, mk4(v[0] + b4.x, v[1] + b4.y, v[2] + b4.z, v[3] + b4.w));
                     });
                 });
                 ci += P::TQkv::NCHUNK;
                 x.phase(PH_ATTN, [&](int tid) {
+                    constexpr int HDP = P::HDP, H4 = P::HDP / 4;
                     const float scale = 1.0f / sqrtf((float)HD);
                     if (hg == 0)
                         for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)       // K-padding channels of the attn_fc operand
                             ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
                     for (int it = tid; it < S * P::HG * F2; it += NT) {
                         const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
-                        const float* qb = QKV + (hh * 3 * HD) * PR + s * F2P;
-                        float q[HD], o[HD];
+                        const float* qb = QKV + s * P::QROW + hh * 3 * HDP;        // row of position (f = 0, s); next f: S * QROW further
+                        float q[HDP], o[HDP];
 #pragma unroll
-                        for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
-                        float mx = -INFINITY;
-                        for (int j = 0; j < F2; ++j) {
-                            float sc = 0.f;
-#pragma unroll
-                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                            mx = fmaxf(mx, sc);
+                        for (int d4 = 0; d4 < H4; ++d4) {
+                            const f4 t = ld4(qb + i * S * P::QROW + 4 * d4);
+                            q[4 * d4] = t.x * scale; q[4 * d4 + 1] = t.y * scale; q[4 * d4 + 2] = t.z * scale; q[4 * d4 + 3] = t.w * scale;
+                            o[4 * d4] = o[4 * d4 + 1] = o[4 * d4 + 2] = o[4 * d4 + 3] = 0.f;
                         }
-                        float den = 0.f;
-                        for (int j = 0; j < F2; ++j) {
-                            float sc = 0.f;
+                        auto score = [&](int j) {
+                            const float* kr = qb + j * S * P::QROW + HDP;
+                            float a = 0.f;
 #pragma unroll
-                            for (int d = 0; d < HD; ++d) sc = fmaf(q[d], qb[(HD + d) * PR + j], sc);
-                            const float pj = fe_exp(sc - mx);
-                            den += pj;
+                            for (int d4 = 0; d4 < H4; ++d4) {
+                                const f4 t = ld4(kr + 4 * d4);
+                                a = fmaf(q[4 * d4 + 3], t.w, fmaf(q[4 * d4 + 2], t.z, fmaf(q[4 * d4 + 1], t.y, fmaf(q[4 * d4], t.x, a))));
+                            }
+                            return a;
+                        };
+                        auto accum = [&](int j, float pj) {
+                            const float* vr = qb + j * S * P::QROW + 2 * HDP;
 #pragma unroll
-                            for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
+                            for (int d4 = 0; d4 < H4; ++d4) {
+                                const f4 t = ld4(vr + 4 * d4);
+                                o[4 * d4] = fmaf(pj, t.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, t.y, o[4 * d4 + 1]);
+                                o[4 * d4 + 2] = fmaf(pj, t.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, t.w, o[4 * d4 + 3]);
+                            }
+                        };
+                        float mx = -INFINITY, den = 0.f;
+                        if constexpr (F2 <= 48) {          // scores stay in registers between the two softmax passes
+                            float sc[F2];
+#pragma unroll
+                            for (int j = 0; j < F2; ++j) { sc[j] = score(j); mx = fmaxf(mx, sc[j]); }
+#pragma unroll
+                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp(sc[j] - mx); den += pj; accum(j, pj); }
+                        } else {
+                            for (int j = 0; j < F2; ++j) mx = fmaxf(mx, score(j));
+                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp(score(j) - mx); den += pj; accum(j, pj); }
                         }
                         const float inv = 1.0f / den;
 #pragma unroll

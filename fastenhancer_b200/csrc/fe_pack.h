@@ -171,7 +171,14 @@ public:
             if (b.pe)
                 for (int f = 0; f < F2; ++f)
                     for (int c = 0; c < C2; ++c) blob_[q.pe + c * F2 + f] = b.pe[f * C2 + c];
-            cp(q.qkv_b, b.qkv_b, 3 * C2);
+            if constexpr (P::TC) {       // padded per-head layout [head][q|k|v][HDP]
+                for (int h = 0; h < C::NH; ++h)
+                    for (int w3 = 0; w3 < 3; ++w3)
+                        for (int d = 0; d < C::HD; ++d)
+                            blob_[q.qkv_b + (h * 3 + w3) * P::HDP + d] = b.qkv_b[(h * 3 + w3) * C::HD + d];
+            } else {
+                cp(q.qkv_b, b.qkv_b, 3 * C2);
+            }
             cp(q.afc_b, b.afc_b, C2);
         }
         cp(A.rf_post_b, cw.rf_post_b, C1);
@@ -219,7 +226,10 @@ public:
                 });
                 tc<typename P::TFc>([&](int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
                 for (int g = 0; g < P::NQG; ++g)
-                    tc<typename P::TQkv>([&](int co, int ci, int) { return b.qkv_w[(g * 3 * C::HD * P::HG + co) * C2 + ci]; });
+                    tc<typename P::TQkv>([&](int co, int ci, int) {      // co = (head-in-round * 3 + q|k|v) * HDP + d, zero for d >= HD
+                        const int d = co % P::HDP, hw = co / P::HDP;
+                        return d < C::HD ? b.qkv_w[((g * P::HG * 3 + hw) * C::HD + d) * C2 + ci] : 0.f;
+                    });
                 tc<typename P::TFc>([&](int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
             }
             rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });

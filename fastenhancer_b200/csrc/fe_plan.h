@@ -201,7 +201,9 @@ struct Plan {
             if (C::NH % hg) continue;
             const int act = (C::C1 / 4) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
             const int f2p = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
-            const int need1 = cmax(3 * C::HD * hg * S * f2p + xts, (C::C1 / 4) * S * C::F2 * 4) + xts;
+            const int qn = hg * 3 * round_up(C::HD, 4), qrow = ((qn / 4) % 2 == 1) ? qn : qn + 4;
+            const int need1 = cmax(S * C::F2 * qrow + xts, (C::C1 / 4) * S * C::F2 * 4) + xts;
+            if (f2p < 0) return 0;
             const int rest = 2 * (C::F1 + 2) * S * 4 + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
             if (cmax(2, cdiv(need1, act)) * act + rest <= 227 * 256) return hg;
         }
@@ -209,7 +211,20 @@ struct Plan {
     }
     static constexpr int HG = TC ? hg_tc() : T::HG, NQG = C::NH / HG;
     static_assert(C::NH % HG == 0, "HG must divide NH");
-    static constexpr int QKVS = 3 * C::HD * HG * PR;
+    // fp32 variants: q/k/v rows channel-major [3*HD*HG][PR].  Tensor-core variants: position-major [RSLOTS][QROW] with every
+    // head's q | k | v padded to HDP = round_up(HD, 4) (the padding rows of the packed weights are zero), so the MMA epilogue
+    // stores and the attention loads are float4; QROW = 4*odd floats keeps both conflict-free.
+    static constexpr int HDP = round_up(C::HD, 4);
+    static constexpr int QN = HG * 3 * HDP;
+    static constexpr int QROW_PAD = ((QN / 4) % 2 == 1) ? QN : QN + 4;
+    // ... unless that padding alone would cost another work buffer (16 kHz B: 192 floats over)
+    static constexpr int rf_need2(int qrow) {      // [QKV | ATT] or Y1T, then XT (padded channels), then XR (real channels only)
+        return cmax(S * C::F2 * qrow + (round_up(C::C2, 8) / 4) * S * C::F2 * 4, (C::C1 / 4) * S * C::F2 * 4) +
+               (round_up(C::C2, 8) / 4) * S * C::F2 * 4 + (C::C2 / 4) * S * C::F2 * 4;
+    }
+    static constexpr int act_tc() { return (C::C1 / 4) * (C::F1 + 2) * S * 4; }
+    static constexpr int QROW = (cdiv(rf_need2(QROW_PAD), act_tc()) > cdiv(rf_need2(QN), act_tc())) ? QN : QROW_PAD;
+    static constexpr int QKVS = TC ? S * C::F2 * QROW : 3 * C::HD * HG * PR;
     // ---- RNNFormer tensor-core geometry ("GeoR", TC variants): [C2P/4][RSLOTS][4], slot = f2*S + s ----
     static constexpr int RSLOTS = S * C::F2;
     static constexpr int RSLABF = RSLOTS * 4;
@@ -223,13 +238,14 @@ struct Plan {
     // XT is a TF32-rounded copy of x for the MMAs; when it does not fit (48 kHz L) the MMAs read the fp32 master
     // (the tensor core then truncates instead of rounding).
     static constexpr int SM_REST = SPECF + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
+    static constexpr int XRT = (C::C2 / 4) * RSLABF;   // fp32 master of x when a separate rounded copy exists: no K-padding group
     static constexpr int RF_NEED1 = cmax(QKVS + XTS, Y1TS) + XTS;
-    static constexpr int RF_NEED2 = RF_NEED1 + XTS;
+    static constexpr int RF_NEED2 = RF_NEED1 + XRT;
     static constexpr int NWORK2 = cmax(2, cdiv(RF_NEED2, ACT));
     static constexpr bool XT_COPY = TC && (NWORK2 * ACT + SM_REST <= 227 * 256);
     static constexpr int NWORK = TC ? (XT_COPY ? NWORK2 : cmax(2, cdiv(RF_NEED1, ACT))) : ((2 * XRS + cmax(XRS, QKVS) > 2 * ACT) ? 3 : 2);
     static constexpr int AB = NWORK * ACT;
-    static constexpr int O_XR = AB - (TC ? XTS : XRS);
+    static constexpr int O_XR = AB - (TC ? (XT_COPY ? XRT : XTS) : XRS);
     static constexpr int O_XT = XT_COPY ? O_XR - XTS : O_XR;
     static constexpr int O_ATT_T = O_XT - XTS, O_HB_T = O_ATT_T;           // TC variants
     static constexpr int O_HB = 0, O_ATT = 0, O_G = XRS, O_QKV = TC ? 0 : XRS;
@@ -283,12 +299,12 @@ struct Plan {
     using TConvT = TcGemm<S * C::F1, 8, C::C1, 3, CHUNK>;
     using TRfPost = TcGemm<S * C::F1, C::C1, C::C2, 1, CHUNK>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
-    static constexpr int TMEMC = pow2ceil(cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(3 * C::HD * HG, 16))));
+    static constexpr int TMEMC = pow2ceil(cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(QN, 16))));
     static_assert(TMEMC <= 512, "TMEM columns");
     using TRfPre = TcGemm<S * C::F2, C::C2, C::C1, 1, CHUNK, 512>;
     using TGru = TcGemm<S * C::F2, C::C2, C::C2, 6, CHUNK, 512>;       // 6 sets: W_ir W_iz W_in W_hr W_hz W_hn
     using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
-    using TQkv = TcGemm<S * C::F2, 3 * C::HD * HG, C::C2, 1, CHUNK, 512>;
+    using TQkv = TcGemm<S * C::F2, QN, C::C2, 1, CHUNK, 512>;
     using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
 
     static constexpr int BLK_CHUNKS = Gru::NCHUNK + 2 * Fc::NCHUNK + NQG * Qkv::NCHUNK;
@@ -344,7 +360,7 @@ struct Plan {
             int r = 0;
             auto rel = [&r](int n) { int q = r; r += round_up(n, 4); return q; };
             a.rel.b_r = rel(C::C2); a.rel.b_z = rel(C::C2); a.rel.b_in = rel(C::C2); a.rel.b_hn = rel(C::C2);
-            a.rel.fc_b = rel(C::C2); a.rel.pe = rel(C::C2 * C::F2); a.rel.qkv_b = rel(3 * C::C2); a.rel.afc_b = rel(C::C2);
+            a.rel.fc_b = rel(C::C2); a.rel.pe = rel(C::C2 * C::F2); a.rel.qkv_b = rel(C::NH * 3 * round_up(C::HD, 4)); a.rel.afc_b = rel(C::C2);
             a.blks = r; a.blk0 = take(C::K * r);
         }
         a.rf_post_b = take(C::C1);
