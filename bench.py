@@ -253,6 +253,23 @@ def main():
     e2e_value = frames_step / e2e_s
     io_bytes = B * n_hops * H * 4
 
+    # the other arithmetic variant, same workload, a few steps (reported beside the headline, not instead of it)
+    other = "fp32" if args.precision == "tf32" else "tf32"
+    eng_o = Engine(cfg, canon, dev, precision=other)
+    st_o = eng_o.new_state(B)
+    for _ in range(2):
+        eng_o.stream(st_o, x, out=y)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o_steps = max(3, args.steps // 3)
+    o0.record()
+    for _ in range(o_steps):
+        eng_o.stream(st_o, x, out=y)
+    o1.record()
+    barrier()
+    other_ms = max_over_ranks(o0.elapsed_time(o1)) / o_steps
+    del eng_o, st_o
+
     if rank == 0:
         peaks = measured_peaks()
         flops_launch = cfg.flops_per_frame() * B * n_hops           # algorithmic FLOP of ONE launch (one rank)
@@ -296,6 +313,10 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "ms_per_step": e2e_s * 1e3, "api": "fe_stream_host via Engine.stream_host (pinned host buffers)"},
+            "variants": {args.precision: {"value": value, "ms_per_step": ms_step},
+                         other: {"value": frames_step / (other_ms * 1e-3), "ms_per_step": other_ms},
+                         "note": "tf32 = contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate, waveform error ~7e-6 RMS vs "
+                                 "the 1e-4 bar); fp32 = every multiply-add on the fp32 FMA pipe (~6e-8 RMS)"},
             "gpu_launches": int(launches), "clocks": clocks, "library": os.path.relpath(library_path(), ROOT),
         }
         print(json.dumps(line), flush=True)

@@ -100,6 +100,10 @@ template <class P> struct GpuCtx {
         return d;
     }
     __device__ __forceinline__ Desc desc_add(Desc d, int floats) const { d.lo += (uint32_t)(floats >> 2); return d; }
+    __device__ __forceinline__ Desc desc_set_lbo(Desc d, int lbo_floats) const {
+        d.lo = (d.lo & 0x0000ffffu) | ((((uint32_t)lbo_floats * 4u) >> 4) << 16);
+        return d;
+    }
     // called by every lane of warp 0 (converged); one elected lane issues
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;

@@ -299,6 +299,48 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
     }
 }
 
+
+// Same, vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
+// layouts, where channels are the innermost index).  xrow(l) -> float4 of k = 0 for lane l (< NLANE); epi(l, o0, acc[4][NO]).
+template <class L, int NLANE, class X, class XRow, class Epi>
+FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
+    constexpr int NO = L::NO;
+    static_assert(NLANE <= 32 && L::RT <= 4, "row gemm (vector form): at most 32 lanes of 4 channels");
+    const int og = tid >> 5, lane = tid & 31;
+    const bool active = og < L::NOG && lane < NLANE;
+    float acc[4][NO];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NO; ++j) acc[i][j] = 0.f;
+    const float* xr = xrow(lane < NLANE ? lane : 0);
+    for (int c = 0; c < L::NCHUNK; ++c) {
+        const int rows = (c == L::NCHUNK - 1) ? L::K - c * L::KC : L::KC;
+        const float* w = x.acquire(ci0 + c, rows * L::ROW);
+        if (active) {
+            const float* wl = w + og * NO;
+#pragma unroll 4
+            for (int kk = 0; kk < rows; ++kk) {
+                const f4 xv = ld4(xr + (c * L::KC + kk) * kstride);
+#pragma unroll
+                for (int j = 0; j < NO; j += 4) {
+                    const f4 wv = ld4(wl + kk * L::ROW + j);
+                    const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc[0][j + e] = fmaf(wj[e], xv.x, acc[0][j + e]);
+                        acc[1][j + e] = fmaf(wj[e], xv.y, acc[1][j + e]);
+                        acc[2][j + e] = fmaf(wj[e], xv.z, acc[2][j + e]);
+                        acc[3][j + e] = fmaf(wj[e], xv.w, acc[3][j + e]);
+                    }
+                }
+            }
+        }
+        x.release(ci0 + c);
+    }
+    if (active) epi(lane, og * NO, acc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tensor-core layer (TcGemm): thread 0 issues one tcgen05.mma (M = 128, N = NP, K = 8, kind::tf32) per
 // (tap, k-step, M tile) as the weight tiles arrive in the ring, releasing each ring stage with a
@@ -521,26 +563,49 @@ template <class P> struct Frame {
         }
     }
 
-    // complex M-point Stockham radix-2 FFT over S streams; returns the buffer holding the result
+    // complex M-point Stockham FFT over S streams (radix-4 stages, one radix-2 stage when log2 M is odd);
+    // returns the buffer holding the result.  tw[t] = exp(-2 pi i t / M), t < M/2.
     template <class X> FE_DEV static float* fft(X& x, float* src, float* dst, bool inverse) {
         const int ph = inverse ? PH_IFFT : PH_FFT;
         const float* tw = x.blob + P::make_aux().tw;
-        int st = 1;
-        for (int stage = 0; stage < LOG2M; ++stage, st <<= 1) {
-            const int lst = stage;
+        const float sgn = inverse ? -1.f : 1.f;
+        int n = M, lst = 0;                      // n: length of the sub-transforms of this stage, stride = 1 << lst
+        while (n >= 4) {
+            const int n1 = n >> 2, l = lst;
             x.phase(ph, [&](int tid) {
+                const int st = 1 << l;
+                for (int j = tid; j < S * (M / 4); j += NT) {
+                    const int s = j / (M / 4), jj = j % (M / 4);
+                    const int p = jj >> l, q = jj & (st - 1);
+                    const float* sp = src + s * N + 2 * (q + st * p);
+                    float* dp = dst + s * N + 2 * (q + st * 4 * p);
+                    const f2 a = ld2(sp), b = ld2(sp + 2 * st * n1), c = ld2(sp + 4 * st * n1), d = ld2(sp + 6 * st * n1);
+                    f2 w1 = ldg2(tw + 2 * (p * st));
+                    w1.y *= sgn;
+                    const f2 w2 = mk2(w1.x * w1.x - w1.y * w1.y, 2.f * w1.x * w1.y);
+                    const f2 w3 = mk2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
+                    const float apcx = a.x + c.x, apcy = a.y + c.y, amcx = a.x - c.x, amcy = a.y - c.y;
+                    const float bpdx = b.x + d.x, bpdy = b.y + d.y;
+                    const float jx = -sgn * (b.y - d.y), jy = sgn * (b.x - d.x);          // (+-) i (b - d)
+                    const float t1x = amcx - jx, t1y = amcy - jy, t2x = apcx - bpdx, t2y = apcy - bpdy, t3x = amcx + jx, t3y = amcy + jy;
+                    st2(dp, mk2(apcx + bpdx, apcy + bpdy));
+                    st2(dp + 2 * st, mk2(t1x * w1.x - t1y * w1.y, t1x * w1.y + t1y * w1.x));
+                    st2(dp + 4 * st, mk2(t2x * w2.x - t2y * w2.y, t2x * w2.y + t2y * w2.x));
+                    st2(dp + 6 * st, mk2(t3x * w3.x - t3y * w3.y, t3x * w3.y + t3y * w3.x));
+                }
+            });
+            float* t = src; src = dst; dst = t;
+            n >>= 2; lst += 2;
+        }
+        if (n == 2) {                            // last stage of an odd log2 M: plain butterflies, twiddle 1
+            const int l = lst;
+            x.phase(ph, [&](int tid) {
+                const int st = 1 << l;
                 for (int j = tid; j < S * (M / 2); j += NT) {
-                    const int s = j / (M / 2), jj = j % (M / 2);
-                    const int p = jj >> lst, q = jj & (st - 1);
-                    const float* sp = src + s * N;
-                    float* dp = dst + s * N;
-                    f2 a = ld2(sp + 2 * (q + st * p));
-                    f2 b = ld2(sp + 2 * (q + st * (p + (M >> (lst + 1)))));
-                    f2 w = ldg2(tw + 2 * (p * st));
-                    if (inverse) w.y = -w.y;
-                    float dr = a.x - b.x, di = a.y - b.y;
-                    st2(dp + 2 * (q + st * 2 * p), mk2(a.x + b.x, a.y + b.y));
-                    st2(dp + 2 * (q + st * (2 * p + 1)), mk2(dr * w.x - di * w.y, dr * w.y + di * w.x));
+                    const int s = j / (M / 2), q = j % (M / 2);
+                    const f2 a = ld2(src + s * N + 2 * q), b = ld2(src + s * N + 2 * (q + st));
+                    st2(dst + s * N + 2 * q, mk2(a.x + b.x, a.y + b.y));
+                    st2(dst + s * N + 2 * (q + st), mk2(a.x - b.x, a.y - b.y));
                 }
             });
             float* t = src; src = dst; dst = t;
@@ -589,12 +654,14 @@ template <class P> struct Frame {
 
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
         x.phase(PH_LIN_PRE, [&](int tid) {
-            row_gemm_k1<typename P::LinPreT>(x, tid, ci, [&](int r) { return enc_last + act_off(r / S, r % S, 0); }, S * 4,
-                                             [&](int r, int o0, const float* v) {
-                float* yr = Y1 + rf_off(r / S, r % S, 0);
+            // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
+            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S>(x, tid, ci, [&](int l) { return enc_last + act_off(4 * (l / S), l % S, 0); }, S * 4,
+                                                          [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
+                float* yr = Y1 + rf_off(4 * (l / S), l % S, 0);
 #pragma unroll
                 for (int j = 0; j < P::LinPreT::NO; ++j)
-                    if (o0 + j < F2) yr[(o0 + j) * S * 4] = tf32_rna(v[j]);
+                    if (o0 + j < F2)
+                        st4(yr + (o0 + j) * S * 4, mk4(tf32_rna(a[0][j]), tf32_rna(a[1][j]), tf32_rna(a[2][j]), tf32_rna(a[3][j])));
             });
         });
         ci += P::LinPreT::NCHUNK;
@@ -629,13 +696,14 @@ template <class P> struct Frame {
             x.phase(PH_GRU, [&](int tid) {
                 using L = typename P::TGru;
                 constexpr int NPG = P::NPG;
-                static_assert(L::NP == NPG, "GRU tile width");
+                static_assert(L::NPG == NPG, "GRU tile width");
+                // x tiles then h tiles; each tile = one MMA into R|Z (x and h accumulate together) + one into NX or NH
                 const auto dx = x.make_desc(XT, RSLABF), dh = x.make_desc(H, RSLABF);
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
-                    const int set = tile / L::NKS, j = tile % L::NKS;
-                    const int col = (set < 3 ? set : (set == 5 ? 3 : set - 3)) * NPG;
-                    const bool acc = set < 3 ? j > 0 : (set == 5 ? j > 0 : true);
-                    x.mma(tid, x.desc_add(set < 3 ? dx : dh, 2 * j * RSLABF), wd, NPG, col, acc, P::RSLOTS);
+                    const int inp = tile / L::NKS, j = tile % L::NKS;
+                    const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
+                    x.mma(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                    x.mma(tid, a, x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4), NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
                 });
                 constexpr int GH = (NGX + 1) / 2, GB = 3;              // channel groups per thread, loaded GB at a time
                 const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
@@ -789,7 +857,7 @@ template <class P> struct Frame {
 
     // ---- irFFT (packed real), synthesis window, overlap-add, emit one hop.  The decompressed spectrum (bins 0..M-1)
     //      is in W0; the Nyquist bin is zero in the fused path and SPEC[s] (real part) for the standalone inverse ----
-    template <class X> FE_DEV static void back_end(X& x, int hop) {
+    template <class X> FE_DEV static void back_end(X& x, int hop, bool have_z) {
         const KParams& prm = x.prm;
         constexpr auto A = P::make_aux();
         const float* aux = x.blob;
@@ -800,7 +868,7 @@ template <class P> struct Frame {
         float* OLA = sm + P::SM_OLA;
         const int mode = prm.mode;
         const int T = prm.n_hops;
-        x.phase(PH_PRETW, [&](int tid) {
+        if (!have_z) x.phase(PH_PRETW, [&](int tid) {      // standalone inverse: bins in W0 -> Z in W1
             for (int idx = tid; idx < S * M; idx += NT) {
                 const int s = idx / M, k = idx % M;
                 f2 yk = ld2(W0 + s * N + 2 * k), ym;
@@ -813,7 +881,7 @@ template <class P> struct Frame {
                 st2(W1 + s * N + 2 * k, mk2(er - oi, ei + orr));         // Z = E + i O
             }
         });
-        const float* Y = fft(x, W1, W0, true);
+        const float* Y = have_z ? fft(x, W0, W1, true) : fft(x, W1, W0, true);
         const int base = (hop * H) & NMASK;
         x.phase(PH_OLA, [&](int tid) {
             const float invM = 1.0f / (float)M;
@@ -873,27 +941,30 @@ template <class P> struct Frame {
                     else SPEC[s] = v.x;
                 }
             });
-            back_end(x, hop);
+            back_end(x, hop, false);
             return;
         } else if (mode != MODE_SPEC) {
             const int wpos = (hop * H) & NMASK;
-            if (mode == MODE_STREAM || mode == MODE_STFT) {
-                x.phase(PH_LOAD, [&](int tid) {
-                    for (int idx = tid; idx < S * H; idx += NT) {
-                        int s = idx / H, j = idx % H, gs = x.s0 + s;
-                        float v = 0.f;
-                        if (gs < prm.n_streams) v = prm.in[(size_t)gs * prm.ld_in + (size_t)hop * H + j];
-                        TIN[s * N + ((wpos + j) & NMASK)] = v;
-                    }
-                });
-            }
             x.phase(PH_WINDOW, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
                     float a, b;
                     if (mode != MODE_OFFLINE) {
-                        a = TIN[s * N + ((wpos + H + n2) & NMASK)];
-                        b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
+                        // frame = [N-H cached samples | the new hop]: the new samples come straight from global memory
+                        // and are filed into the ring on the way (slots disjoint from the cached part)
+                        if (n2 < C::CL) {
+                            a = TIN[s * N + ((wpos + H + n2) & NMASK)];
+                            b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
+                        } else {
+                            const int j = n2 - C::CL;
+                            a = b = 0.f;
+                            if (gs < prm.n_streams) {
+                                const float* src_hop = prm.in + (size_t)gs * prm.ld_in + (size_t)hop * H + j;
+                                a = src_hop[0]; b = src_hop[1];
+                            }
+                            TIN[s * N + ((wpos + j) & NMASK)] = a;
+                            TIN[s * N + ((wpos + j + 1) & NMASK)] = b;
+                        }
                     } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
                         a = b = 0.f;
                         if (gs < prm.n_streams) {
@@ -1228,12 +1299,13 @@ template <class P> struct Frame {
         float* Zb = AB + P::O_Z;
         if constexpr (P::TC) {
             x.phase(PH_LIN_POST, [&](int tid) {
-                row_gemm_k1<typename P::LinPostT>(x, tid, ci, [&](int r) { return XR + rf_off(r / S, r % S, 0); }, S * 4,
-                                                  [&](int r, int o0, const float* v) {
-                    float* zr = Zb + act_off(r / S, r % S, 0);
+                row_gemm_k1v<typename P::LinPostT, (C2 / 4) * S>(x, tid, ci, [&](int l) { return XR + rf_off(4 * (l / S), l % S, 0); }, S * 4,
+                                                              [&](int l, int o0, const float (&a)[4][P::LinPostT::NO]) {
+                    float* zr = Zb + act_off(4 * (l / S), l % S, 0);
 #pragma unroll
                     for (int j = 0; j < P::LinPostT::NO; ++j)
-                        if (o0 + j < F1) zr[(o0 + j) * S * 4] = tf32_rna(v[j]);
+                        if (o0 + j < F1)
+                            st4(zr + (o0 + j) * S * 4, mk4(tf32_rna(a[0][j]), tf32_rna(a[1][j]), tf32_rna(a[2][j]), tf32_rna(a[3][j])));
                 });
                 // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
                 for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {
@@ -1354,30 +1426,55 @@ template <class P> struct Frame {
         x.check_frame(ci);
         if (dbg) dump_spec(MASK, TAP_MASK);
 
-        // ================= mask * spectrum, decompression =================
-        x.phase(PH_MASK, [&](int tid) {
-            for (int idx = tid; idx < S * M; idx += NT) {
-                const int s = idx / M, k = idx % M, gs = x.s0 + s;
-                const int o0 = spec_off(0, s, k), o1 = spec_off(1, s, k);
-                const float xr = SPEC[o0], xi = SPEC[o1], mr = MASK[o0], mi = MASK[o1];
-                const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
-                if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + k] = yr; prm.dbg[TAP_SPECHAT + FIN + k] = yi; }
-                const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);
-                if (mode == MODE_SPEC) {
+        // ================= mask * spectrum, decompression (+ pre-twiddle of the packed inverse FFT) =================
+        if (mode == MODE_SPEC) {
+            x.phase(PH_MASK, [&](int tid) {
+                for (int idx = tid; idx < S * M; idx += NT) {
+                    const int s = idx / M, k = idx % M, gs = x.s0 + s;
+                    const int o0 = spec_off(0, s, k), o1 = spec_off(1, s, k);
+                    const float xr = SPEC[o0], xi = SPEC[o1], mr = MASK[o0], mi = MASK[o1];
+                    const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
+                    if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + k] = yr; prm.dbg[TAP_SPECHAT + FIN + k] = yi; }
+                    const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);
                     if (gs < prm.n_streams) {
                         st2(prm.out + (((size_t)gs * C::NB + k) * T + hop) * 2, mk2(yr * g, yi * g));
                         if (k == 0) st2(prm.out + (((size_t)gs * C::NB + FIN) * T + hop) * 2, mk2(0.f, 0.f));
                     }
-                } else {
+                }
+            });
+            return;
+        }
+        // One thread per bin pair (k, M - k): both masked / decompressed bins, then Z[k] = E + i O and Z[M-k] = conj(E) + i conj(O)
+        // with E = (Y[k] + conj(Y[M-k])) / 2, O = (Y[k] - conj(Y[M-k])) / 2 * exp(+2 pi i k / N); imag of DC ignored, Nyquist = 0.
+        x.phase(PH_MASK, [&](int tid) {
+            for (int idx = tid; idx < S * (M / 2); idx += NT) {          // item 0 takes the two unpaired bins 0 and M/2
+                const int s = idx / (M / 2), k = idx % (M / 2), gs = x.s0 + s;
+                auto bin = [&](int kk) {
+                    const int o0 = spec_off(0, s, kk), o1 = spec_off(1, s, kk);
+                    const float xr = SPEC[o0], xi = SPEC[o1], mr = MASK[o0], mi = MASK[o1];
+                    const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
+                    if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + kk] = yr; prm.dbg[TAP_SPECHAT + FIN + kk] = yi; }
                     if (mode == MODE_OFFLINE && prm.spec_out != nullptr && gs < prm.n_streams)
-                        st2(prm.spec_out + (((size_t)gs * FIN + k) * T + hop) * 2, mk2(yr, yi));
-                    st2(W0 + s * N + 2 * k, mk2(yr * g, yi * g));
+                        st2(prm.spec_out + (((size_t)gs * FIN + kk) * T + hop) * 2, mk2(yr, yi));
+                    const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);
+                    return mk2(yr * g, yi * g);
+                };
+                const f2 ya = bin(k), yb = bin(k == 0 ? M / 2 : M - k);
+                if (k == 0) {
+                    // Z[0] from Y[0] (imag ignored) and the zero Nyquist bin; Z[M/2] = conj(Y[M/2])
+                    st2(W0 + s * N, mk2(0.5f * ya.x, 0.5f * ya.x));
+                    st2(W0 + s * N + M, mk2(yb.x, -yb.y));
+                } else {
+                    const float er = 0.5f * (ya.x + yb.x), ei = 0.5f * (ya.y - yb.y);
+                    const float dr = 0.5f * (ya.x - yb.x), di = 0.5f * (ya.y + yb.y);
+                    const f2 w = ldg2(aux + A.twn + 2 * k);                    // O = D * conj(w)
+                    const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+                    st2(W0 + s * N + 2 * k, mk2(er - oi, ei + orr));
+                    st2(W0 + s * N + 2 * (M - k), mk2(er + oi, orr - ei));
                 }
             }
         });
-        if (mode == MODE_SPEC) return;
-
-        back_end(x, hop);
+        back_end(x, hop, true);
     }
 };
 

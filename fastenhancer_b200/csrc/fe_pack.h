@@ -116,6 +116,29 @@ template <class P> class Packer {
         }
         off_ += L::FLOATS;
     }
+    // fused GRU tiles, w(set, c, k) with sets W_ir W_iz W_in W_hr W_hz W_hn: tile (inp, j) = [R|Z: [2][2*NPG][4] | N: [2][NPG][4]]
+    template <class L, class W> void gru(W w) {
+        for (int c = 0; c < L::NCHUNK; ++c) {
+            int tiles = cmin(L::TPC, L::NTILE - c * L::TPC);
+            table_.push_back((int)(off_ + (long)c * L::TPC * L::TILE));
+            table_.push_back(tiles * L::TILE);
+        }
+        for (int tile = 0; tile < L::NTILE; ++tile) {
+            const int inp = tile / L::NKS, j = tile % L::NKS;
+            float* t = &blob_[off_ + (long)tile * L::TILE];
+            for (int kc2 = 0; kc2 < 2; ++kc2)
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 8 * j + 4 * kc2 + e;
+                    for (int n = 0; n < 2 * L::NPG; ++n) {
+                        const int set = inp * 3 + n / L::NPG, c = n % L::NPG;
+                        t[(kc2 * 2 * L::NPG + n) * 4 + e] = (c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+                    }
+                    for (int n = 0; n < L::NPG; ++n)
+                        t[2 * L::NPG * 8 + (kc2 * L::NPG + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(inp * 3 + 2, n, k)) : 0.f;
+                }
+        }
+        off_ += L::FLOATS;
+    }
     // w(o, k), one ring row per k: [og][NO]
     template <class L, class W> void rowk1(W w) {
         for (int c = 0; c < L::NCHUNK; ++c) {
@@ -221,7 +244,7 @@ public:
             tc<typename P::TRfPre>([&](int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
             for (int k = 0; k < C::K; ++k) {
                 const auto& b = cw.blk[k];
-                tc<typename P::TGru>([&](int c, int ci, int set) {
+                gru<typename P::TGru>([&](int set, int c, int ci) {
                     return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
                 });
                 tc<typename P::TFc>([&](int co, int ci, int) { return b.fc_w[co * C2 + ci]; });

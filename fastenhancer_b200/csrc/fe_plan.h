@@ -138,6 +138,21 @@ struct TcGemm {
     static_assert(NMT * NP <= TMEMC_, "accumulators exceed the TMEM allocation");
 };
 
+// Fused GRU on the tensor cores: per (input x | h, k-step) one weight tile  [ R|Z part: [2][2*NPG][4] | N part: [2][NPG][4] ],
+// i.e. two MMAs: N = 2*NPG into the R|Z accumulator columns (x and h accumulate together) and N = NPG into NX or NH.
+template <int NPOS_, int C2_, int CHUNK_>
+struct TcGru {
+    static constexpr int NPOS = NPOS_, N = C2_, K = C2_;
+    static constexpr int NPG = round_up(C2_, 16), KP = round_up(C2_, 8), NKS = KP / 8;
+    static constexpr int NP = 2 * NPG;                 // rows (LBO) of the R|Z part
+    static constexpr int NTILE = 2 * NKS;              // x tiles, then h tiles
+    static constexpr int TILE = 3 * NPG * 8;
+    static_assert(TILE <= CHUNK_ && NP <= 256, "GRU tile");
+    static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
+    static constexpr int NCHUNK = cdiv(NTILE, TPC);
+    static constexpr int FLOATS = NTILE * TILE;
+};
+
 // Row GEMM reading one k per step (frequency-axis linear on a tensor-core-layout activation, where
 // consecutive frequencies are not contiguous).  Ring rows: one per k: [og][NO].
 template <int NROWS_, int K_, int NOUT_, int NW_, int CHUNK_>
@@ -158,8 +173,14 @@ struct RowGemmK1 {
 // ----------------------------------------------------------------------------------------------
 template <class C, int S> struct Tune {
     static constexpr int NW = 8;                      // consumer warps (one more warp streams weights)
-    static constexpr int CHUNK = 4096;                // floats per ring chunk
-    static constexpr int STAGES = 3;
+#ifndef FE_CHUNK
+#define FE_CHUNK 8192
+#endif
+#ifndef FE_STAGES
+#define FE_STAGES 2
+#endif
+    static constexpr int CHUNK = FE_CHUNK;            // floats per ring chunk
+    static constexpr int STAGES = FE_STAGES;
     static constexpr int CT_CONV = 16;                // max output channels per lane, conv / 1x1 layers
     static constexpr int CT_RF = 8;                   // ... RNNFormer linears
     static constexpr int PT_GRU = 2, CT_GRU = 6;      // GRU tile: 4 accumulators per (channel, position)
@@ -302,7 +323,7 @@ struct Plan {
     static constexpr int TMEMC = pow2ceil(cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(QN, 16))));
     static_assert(TMEMC <= 512, "TMEM columns");
     using TRfPre = TcGemm<S * C::F2, C::C2, C::C1, 1, CHUNK, 512>;
-    using TGru = TcGemm<S * C::F2, C::C2, C::C2, 6, CHUNK, 512>;       // 6 sets: W_ir W_iz W_in W_hr W_hz W_hn
+    using TGru = TcGru<S * C::F2, C::C2, CHUNK>;
     using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
     using TQkv = TcGemm<S * C::F2, QN, C::C2, 1, CHUNK, 512>;
     using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;

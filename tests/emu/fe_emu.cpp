@@ -42,6 +42,7 @@ template <class P> struct EmuCtx {
     struct Desc { const float* p; int lbo; };
     Desc make_desc(const float* p, int lbo_floats) const { return Desc{p, lbo_floats}; }
     Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
+    Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats}; }
     void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
         if (tid != 0) return;                       // one elected lane of warp 0 issues
         for (int m = 0; m < rows; ++m)
