@@ -425,7 +425,7 @@ FE_API int fe_set_precision(fe_engine* e, int fp32_exact) {
     return FE_OK;
 }
 FE_API int fe_get_precision(fe_engine* e) { return e ? (e->tc ? 0 : 1) : fail(FE_ERR_ARG, "fe_get_precision: null engine"); }
-FE_API int fe_profile_slots(void) { return (int)fe::PH_COUNT; }
+FE_API int fe_profile_slots(void) { return (int)(fe::PH_COUNT + fe::PH_COUNT * fe::PH_NSUB); }
 FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_profile: null engine");
     e->prof = counters_device;

@@ -144,9 +144,15 @@ template <class P> struct GpuCtx {
     }
 
     long long t_last, t_sub;
+    int cur_phase;          // phase id being executed (profile only): sub-timers are also filed per phase
     __device__ __forceinline__ void sub_begin(int) { if (prm.prof != nullptr && cta == 0 && tid == 0) t_sub = clock64(); }
     __device__ __forceinline__ void sub_end(int, int id) {
-        if (prm.prof != nullptr && cta == 0 && tid == 0) { const long long t = clock64(); prm.prof[id] += t - t_sub; t_sub = t; }
+        if (prm.prof != nullptr && cta == 0 && tid == 0) {
+            const long long t = clock64();
+            prm.prof[id] += t - t_sub;
+            prm.prof[PH_COUNT + cur_phase * PH_NSUB + (id - PH_TC_WAITW)] += t - t_sub;
+            t_sub = t;
+        }
     }
     __device__ __forceinline__ void stamp(int id) {
         if (prm.prof != nullptr && cta == 0 && tid == 0) {
@@ -155,9 +161,10 @@ template <class P> struct GpuCtx {
             t_last = t;
         }
     }
-    template <class F> __device__ __forceinline__ void phase(int id, F&& f) { f(tid); phase_sync(); stamp(id); }
+    template <class F> __device__ __forceinline__ void phase(int id, F&& f) { cur_phase = id; f(tid); phase_sync(); stamp(id); }
     template <class A, class F1, class F2> __device__ __forceinline__ void phase2(int id, F1&& f1, F2&& f2) {
         A a;
+        cur_phase = id;
         f1(tid, a);
         phase_sync();
         f2(tid, a);
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     GpuCtx<P> x;
     x.sm = sm; x.blob = prm.blob; x.prm = prm; x.cta = blockIdx.x; x.s0 = blockIdx.x * P::S;
     x.gs = prm.scratch + (size_t)blockIdx.x * P::GS_TOTAL;
-    x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64();
+    x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64(); x.cur_phase = 0;
     x.tmem = 0; x.acc_bar = bars + 8u * (2 * P::STAGES); x.acc_uses = 0;
     if constexpr (P::TC) x.tmem = *tmem_slot;
     Frame<P>::run(x);

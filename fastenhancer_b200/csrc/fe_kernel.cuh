@@ -64,6 +64,25 @@ FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=
 }  // namespace fe
 #endif
 
+// FE_F32X2 (tensor-core variants only): packed fp32 math (Blackwell FFMA2 / FADD2 / FMUL2: two lanes per instruction, same
+// rounding per lane) in the attention, the frequency-axis linears and the layer epilogues -- these phases are issue-bound.
+#ifndef FE_F32X2
+#define FE_F32X2 1
+#endif
+namespace fe {
+#if defined(FE_EMU) || !FE_F32X2
+FE_DEV f2 fma2(f2 a, f2 b, f2 c) { f2 d; d.x = fmaf(a.x, b.x, c.x); d.y = fmaf(a.y, b.y, c.y); return d; }
+FE_DEV f2 add2(f2 a, f2 b) { f2 d; d.x = a.x + b.x; d.y = a.y + b.y; return d; }
+FE_DEV f2 mul2(f2 a, f2 b) { f2 d; d.x = a.x * b.x; d.y = a.y * b.y; return d; }
+#else
+FE_DEV unsigned long long pk2(f2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+FE_DEV f2 upk2(unsigned long long r) { f2 d; asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r)); return d; }
+FE_DEV f2 fma2(f2 a, f2 b, f2 c) { unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c))); return upk2(d); }
+FE_DEV f2 add2(f2 a, f2 b) { unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b))); return upk2(d); }
+FE_DEV f2 mul2(f2 a, f2 b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b))); return upk2(d); }
+#endif
+}  // namespace fe
+
 // FE_FAST_ACT (tensor-core variants only): 0 = ex2/rcp forms; 1 = tanh.approx SiLU in the epilogues; 2 (default) = also the GRU
 // gates.  Measured on B200 (B, 40 hops): waveform RMS error vs oracle 5.93e-6 / 5.92e-6 / 5.91e-6, 4.34 / 4.66 / 4.82 M frames/s.
 #ifndef FE_FAST_ACT
@@ -90,6 +109,7 @@ enum PhaseId { PH_INIT = 0, PH_LOAD, PH_WINDOW, PH_FFT, PH_COMPRESS, PH_ENC_PRE,
                PH_PRETW, PH_IFFT, PH_OLA, PH_DBG, PH_STATE,
                // sub-timers of the tensor-core layers (thread 0; overlapping the phase ids above, not additive)
                PH_TC_WAITW, PH_TC_ISSUE, PH_TC_MMA, PH_TC_LD, PH_TC_EPI, PH_COUNT };
+constexpr int PH_NSUB = PH_COUNT - PH_TC_WAITW;      // the profile buffer is [PH_COUNT] totals + [PH_COUNT][PH_NSUB] sub-timers per phase
 
 FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
@@ -109,6 +129,28 @@ FE_DEV float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(
 #endif
 FE_DEV float silu_fast(float x) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
 FE_DEV float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// packed (two lanes per FADD2 / FMUL2 / FFMA2) forms of the epilogue math
+FE_DEV f2 tanh2(f2 x) { f2 y; y.x = FE_TC_TANH(x.x); y.y = FE_TC_TANH(x.y); return y; }
+FE_DEV f2 silu2(f2 x) {
+#if FE_FAST_ACT >= 1
+    f2 hh; hh.x = hh.y = 0.5f;
+    const f2 h = mul2(x, hh);
+    f2 t; t.x = tanh_fast(h.x); t.y = tanh_fast(h.y);
+    return fma2(h, t, h);
+#else
+    f2 y; y.x = silu(x.x); y.y = silu(x.y); return y;
+#endif
+}
+FE_DEV f2 sigmoid2(f2 x) {
+#if FE_FAST_ACT >= 2
+    f2 hh; hh.x = hh.y = 0.5f;
+    const f2 h = mul2(x, hh);
+    f2 t; t.x = tanh_fast(h.x); t.y = tanh_fast(h.y);
+    return fma2(t, hh, hh);
+#else
+    f2 y; y.x = sigmoid_acc(x.x); y.y = sigmoid_acc(x.y); return y;
+#endif
+}
 
 template <int PT> FE_DEV void load_pt(const float* p, float* v) {
     if constexpr (PT == 4) { f4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
@@ -308,11 +350,12 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
     static_assert(NLANE <= 32 && L::RT <= 4, "row gemm (vector form): at most 32 lanes of 4 channels");
     const int og = tid >> 5, lane = tid & 31;
     const bool active = og < L::NOG && lane < NLANE;
-    float acc[4][NO];
+    static_assert(NO % 4 == 0, "outputs per warp come in float4 groups");
+    f2 acc2[4][NO / 2];          // [channel][output pair]: packed fp32 FMAs, the pair runs over outputs
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NO; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NO / 2; ++j) acc2[i][j] = mk2(0.f, 0.f);
     const float* xr = xrow(lane < NLANE ? lane : 0);
     for (int c = 0; c < L::NCHUNK; ++c) {
         const int rows = (c == L::NCHUNK - 1) ? L::K - c * L::KC : L::KC;
@@ -322,22 +365,28 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
 #pragma unroll 4
             for (int kk = 0; kk < rows; ++kk) {
                 const f4 xv = ld4(xr + (c * L::KC + kk) * kstride);
+                f2 xd[4];
+                xd[0].x = xd[0].y = xv.x; xd[1].x = xd[1].y = xv.y; xd[2].x = xd[2].y = xv.z; xd[3].x = xd[3].y = xv.w;
 #pragma unroll
                 for (int j = 0; j < NO; j += 4) {
                     const f4 wv = ld4(wl + kk * L::ROW + j);
-                    const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+                    f2 w01, w23;
+                    w01.x = wv.x; w01.y = wv.y; w23.x = wv.z; w23.y = wv.w;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        acc[0][j + e] = fmaf(wj[e], xv.x, acc[0][j + e]);
-                        acc[1][j + e] = fmaf(wj[e], xv.y, acc[1][j + e]);
-                        acc[2][j + e] = fmaf(wj[e], xv.z, acc[2][j + e]);
-                        acc[3][j + e] = fmaf(wj[e], xv.w, acc[3][j + e]);
+                    for (int ch = 0; ch < 4; ++ch) {
+                        acc2[ch][j / 2] = fma2(w01, xd[ch], acc2[ch][j / 2]);
+                        acc2[ch][j / 2 + 1] = fma2(w23, xd[ch], acc2[ch][j / 2 + 1]);
                     }
                 }
             }
         }
         x.release(ci0 + c);
     }
+    float acc[4][NO];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NO; j += 2) { acc[i][j] = acc2[i][j / 2].x; acc[i][j + 1] = acc2[i][j / 2].y; }
     if (active) epi(lane, og * NO, acc);
 }
 
@@ -466,12 +515,12 @@ template <class P> struct Frame {
         FE_DEV void operator()(int gp, int g, const float* v) const {
             float o[4];
             const f4 b4 = ldg4(bias + 4 * g);
-            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            f2 t01 = add2(mk2(v[0], v[1]), mk2(b4.x, b4.y)), t23 = add2(mk2(v[2], v[3]), mk2(b4.z, b4.w));
+            if (act) { t01 = silu2(t01); t23 = silu2(t23); }
+            o[0] = t01.x; o[1] = t01.y; o[2] = t23.x; o[3] = t23.y;
+            if (round) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float t = v[e] + bv[e];
-                t = act ? FE_TC_SILU(t) : t;
-                o[e] = round ? tf32_rna(t) : t;
+                for (int e = 0; e < 4; ++e) o[e] = tf32_rna(o[e]);
             }
             const int off = g * SLABF + (S + gp) * 4;
             st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
@@ -732,11 +781,14 @@ template <class P> struct Frame {
                             const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w};
                             const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float r = FE_TC_SIGMOID(vr[b][e] + br[e]);
-                                const float z = FE_TC_SIGMOID(vz[b][e] + bz[e]);
-                                const float nn = FE_TC_TANH(vx[b][e] + bi[e] + r * (vh[b][e] + bh[e]));
-                                hn[e] = (1.0f - z) * nn + z * hov[e];
+                            for (int e = 0; e < 4; e += 2) {
+                                const f2 r = sigmoid2(add2(mk2(vr[b][e], vr[b][e + 1]), mk2(br[e], br[e + 1])));
+                                const f2 z = sigmoid2(add2(mk2(vz[b][e], vz[b][e + 1]), mk2(bz[e], bz[e + 1])));
+                                const f2 nn = tanh2(fma2(r, add2(mk2(vh[b][e], vh[b][e + 1]), mk2(bh[e], bh[e + 1])),
+                                                         add2(mk2(vx[b][e], vx[b][e + 1]), mk2(bi[e], bi[e + 1]))));
+                                // (1 - z) n + z h = n + z (h - n)
+                                const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
+                                hn[e] = hv.x; hn[e + 1] = hv.y;
                             }
                             st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed
                             if constexpr (!P::H_RES) {
@@ -788,30 +840,31 @@ template <class P> struct Frame {
                     for (int it = tid; it < S * P::HG * F2; it += NT) {
                         const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
                         const float* qb = QKV + s * P::QROW + hh * 3 * HDP;        // row of position (f = 0, s); next f: S * QROW further
-                        float q[HDP], o[HDP];
+                        f2 q[2 * H4], o[2 * H4];             // packed fp32 pairs (FFMA2)
 #pragma unroll
                         for (int d4 = 0; d4 < H4; ++d4) {
                             const f4 t = ld4(qb + i * S * P::QROW + 4 * d4);
-                            q[4 * d4] = t.x * scale; q[4 * d4 + 1] = t.y * scale; q[4 * d4 + 2] = t.z * scale; q[4 * d4 + 3] = t.w * scale;
-                            o[4 * d4] = o[4 * d4 + 1] = o[4 * d4 + 2] = o[4 * d4 + 3] = 0.f;
+                            q[2 * d4] = mk2(t.x * scale, t.y * scale); q[2 * d4 + 1] = mk2(t.z * scale, t.w * scale);
+                            o[2 * d4] = o[2 * d4 + 1] = mk2(0.f, 0.f);
                         }
                         auto score = [&](int j) {
                             const float* kr = qb + j * S * P::QROW + HDP;
-                            float a = 0.f;
+                            f2 a = mk2(0.f, 0.f);
 #pragma unroll
                             for (int d4 = 0; d4 < H4; ++d4) {
                                 const f4 t = ld4(kr + 4 * d4);
-                                a = fmaf(q[4 * d4 + 3], t.w, fmaf(q[4 * d4 + 2], t.z, fmaf(q[4 * d4 + 1], t.y, fmaf(q[4 * d4], t.x, a))));
+                                a = fma2(q[2 * d4 + 1], mk2(t.z, t.w), fma2(q[2 * d4], mk2(t.x, t.y), a));
                             }
-                            return a;
+                            return a.x + a.y;
                         };
                         auto accum = [&](int j, float pj) {
                             const float* vr = qb + j * S * P::QROW + 2 * HDP;
+                            const f2 pp = mk2(pj, pj);
 #pragma unroll
                             for (int d4 = 0; d4 < H4; ++d4) {
                                 const f4 t = ld4(vr + 4 * d4);
-                                o[4 * d4] = fmaf(pj, t.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, t.y, o[4 * d4 + 1]);
-                                o[4 * d4 + 2] = fmaf(pj, t.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, t.w, o[4 * d4 + 3]);
+                                o[2 * d4] = fma2(pp, mk2(t.x, t.y), o[2 * d4]);
+                                o[2 * d4 + 1] = fma2(pp, mk2(t.z, t.w), o[2 * d4 + 1]);
                             }
                         };
                         float mx = -INFINITY, den = 0.f;
@@ -827,7 +880,8 @@ template <class P> struct Frame {
                         }
                         const float inv = 1.0f / den;
 #pragma unroll
-                        for (int d = 0; d < HD; ++d) ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_rna(o[d] * inv);
+                        for (int d = 0; d < HD; ++d)
+                            ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_rna(((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv);
                     }
                 });
             }

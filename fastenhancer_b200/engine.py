@@ -200,12 +200,14 @@ class Engine:
               "attn", "attn_fc", "lin_post", "rf_post", "skip_load", "pwcat", "dec", "convt", "mask", "pretw", "ifft", "ola",
               "dbg", "state", "tc:wait_weights", "tc:issue", "tc:mma_done", "tc:tmem_ld", "tc:epi_math")
 
+    N_SUB = 5       # sub-timers (the "tc:*" entries), also recorded per phase
+
     def enable_profile(self, on: bool = True):
         """Per-phase SM-cycle counters of CTA 0 (int64 cuda tensor, accumulated over launches) or None."""
         import torch
         if on:
             n = int(self._lib.fe_profile_slots())
-            assert n == len(self.PHASES)
+            assert n == len(self.PHASES) * (1 + self.N_SUB)      # totals, then [phase][sub-timer]
             self._prof = torch.zeros(n, dtype=torch.int64, device=self.device)
             _check(self._lib.fe_set_profile(self._h, self._prof.data_ptr()), "fe_set_profile")
             return self._prof

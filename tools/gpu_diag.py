@@ -47,7 +47,7 @@ def diag(name, S, B=5, nh=6):
     e_s = float(np.abs(state.export().cpu().numpy() - st).max())
     rms = float(np.sqrt(np.mean((y - y_ref) ** 2)))
     print(f"DIAG {name} S={S} {eng.precision}: wav max|d|={e_w:.3e} rms={rms:.3e} state max|d|={e_s:.3e} worst tap rel={worst:.2e} "
-          f"{'OK' if rms < (1e-5 if eng.precision == 'fp32' else 5e-5) and e_s < 5e-4 else 'FAIL'}")
+          f"{'OK' if rms < (1e-5 if eng.precision == 'fp32' else 5e-5) and e_s < (5e-5 if eng.precision == 'fp32' else 2e-3) else 'FAIL'}")
 
 
 def timing(name, B, nh, S=0):
@@ -90,11 +90,17 @@ def profile(name, B, nh, S=0):
     eng.stream(state, x)
     torch.cuda.synchronize()
     p = prof.cpu().numpy().astype(np.float64) / nh
-    tot = p[:-5].sum()        # the last five are sub-timers inside the tensor-core phases
+    nph, nsub = len(eng.PHASES), eng.N_SUB
+    sub = p[nph:].reshape(nph, nsub)      # per phase: wait_weights, issue, mma_done, tmem_ld, epi_math (thread 0)
+    p = p[:nph]
+    tot = p[:-nsub].sum()     # the last five are sub-timers inside the tensor-core phases
     print(f"PROF {name} {eng.precision} B={B} S={eng.streams_per_cta(B)}: {tot:.0f} cycles/hop (CTA 0)")
-    for nm, v in sorted(zip(eng.PHASES, p), key=lambda t: -t[1]):
+    for nm, v, sb in sorted(zip(eng.PHASES, p, sub), key=lambda t: -t[1]):
         if v > 0:
-            print(f"  {nm:10s} {v:9.0f} cyc  {100 * v / tot:5.1f}%")
+            extra = ""
+            if sb.sum() > 0:
+                extra = "   [waitw %5.0f issue %5.0f mma %5.0f ld %5.0f epi %5.0f rest %5.0f]" % (*sb, v - sb.sum())
+            print(f"  {nm:10s} {v:9.0f} cyc  {100 * v / tot:5.1f}%{extra}")
 
 
 if __name__ == "__main__":
