@@ -48,9 +48,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
 }
-// instruction descriptor: D f32, A/B tf32, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D f32, A/B tf32, both K-major, M = m (128 or 64), N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -104,13 +104,15 @@ template <class P> struct GpuCtx {
         d.lo = (d.lo & 0x0000ffffu) | ((((uint32_t)lbo_floats * 4u) >> 4) << 16);
         return d;
     }
-    // called by every lane of warp 0 (converged); one elected lane issues
+    // called by every lane of warp 0 (converged); one elected lane issues.  M64: a 64-row MMA, whose accumulator row r
+    // lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
+    template <bool M64 = false>
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
         asm volatile(
             "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
             "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32_m128(np)), "r"(acc ? 1u : 0u) : "memory");
+            ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
     // the stage, are done); the other warps never touch the stage and arrive at once
@@ -131,6 +133,15 @@ template <class P> struct GpuCtx {
         const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) << 5) << 16) + (uint32_t)col;   // this warp's lane quadrant
         uint32_t r0, r1, r2, r3;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+        v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    }
+    // 16 lanes x 256 bits: thread t of the warp gets (lane t/4, columns col + 2(t%4) + {0,1}) in v[0..1] and (lane t/4 + 8, same
+    // columns) in v[2..3], lanes counted from the start of the warp's quadrant
+    __device__ __forceinline__ void tmem_ld16(int /*tid*/, int col, float* v) const {
+        const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) << 5) << 16) + (uint32_t)col;
+        uint32_t r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
         v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
     }

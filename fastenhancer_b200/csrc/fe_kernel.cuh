@@ -44,6 +44,8 @@ inline f4 ldg4(const float* p) { return ld4(p); }
 inline float fe_exp(float x) { return expf(x); }
 inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
+inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
+inline float tf32_clean(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 }  // namespace fe
 #else
 #define FE_DEV __device__ __forceinline__
@@ -61,6 +63,18 @@ FE_DEV float fe_exp(float x) { return __expf(x); }
 FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
 // round to nearest TF32 so that the tensor core (which reads the top 19 bits) sees the value exactly
 FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+// Rounding for values that only the tensor core reads: the MMA ignores the low 13 bits, so adding half a TF32 ulp to the bit pattern
+// makes its truncation a round-to-nearest -- one integer add instead of the three instructions cvt.rna.tf32 compiles to.  Anything
+// else that reads such a buffer applies tf32_clean (finite activations only: an overflow into the exponent is still the right value).
+#ifndef FE_FAST_RNA
+#define FE_FAST_RNA 1
+#endif
+#if FE_FAST_RNA
+FE_DEV float tf32_pre(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+#else
+FE_DEV float tf32_pre(float x) { return tf32_rna(x); }
+#endif
+FE_DEV float tf32_clean(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 }  // namespace fe
 #endif
 
@@ -156,6 +170,11 @@ template <int PT> FE_DEV void load_pt(const float* p, float* v) {
     if constexpr (PT == 4) { f4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     else if constexpr (PT == 2) { f2 t = ld2(p); v[0] = t.x; v[1] = t.y; }
     else { for (int j = 0; j < PT; ++j) v[j] = p[j]; }
+}
+template <int PT> FE_DEV void ldg_pt(const float* p, float* v) {
+    if constexpr (PT == 4) { f4 t = ldg4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (PT == 2) { f2 t = ldg2(p); v[0] = t.x; v[1] = t.y; }
+    else { for (int j = 0; j < PT; ++j) v[j] = ldg(p + j); }
 }
 template <int PT> FE_DEV void store_pt(float* p, const float* v) {
     if constexpr (PT == 4) st4(p, mk4(v[0], v[1], v[2], v[3]));
@@ -344,7 +363,7 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
 
 // Same, vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
 // layouts, where channels are the innermost index).  xrow(l) -> float4 of k = 0 for lane l (< NLANE); epi(l, o0, acc[4][NO]).
-template <class L, int NLANE, class X, class XRow, class Epi>
+template <class L, int NLANE, bool CLEAN = false, class X, class XRow, class Epi>
 FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
     constexpr int NO = L::NO;
     static_assert(NLANE <= 32 && L::RT <= 4, "row gemm (vector form): at most 32 lanes of 4 channels");
@@ -364,7 +383,8 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
             const float* wl = w + og * NO;
 #pragma unroll 4
             for (int kk = 0; kk < rows; ++kk) {
-                const f4 xv = ld4(xr + (c * L::KC + kk) * kstride);
+                f4 xv = ld4(xr + (c * L::KC + kk) * kstride);
+                if constexpr (CLEAN) { xv.x = tf32_clean(xv.x); xv.y = tf32_clean(xv.y); xv.z = tf32_clean(xv.z); xv.w = tf32_clean(xv.w); }
                 f2 xd[4];
                 xd[0].x = xd[0].y = xv.x; xd[1].x = xd[1].y = xv.y; xd[2].x = xd[2].y = xv.z; xd[3].x = xd[3].y = xv.w;
 #pragma unroll
@@ -452,11 +472,44 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
     }
 }
 
+// M = 64 accumulator (RNNFormer layers with at most 64 positions): row r sits in TMEM lane 32 * (r / 16) + r % 16.  Warp w reads
+// the quadrant w % 4 with 16x256b loads, so all 32 threads work on the quadrant's 16 rows: thread t owns rows 16q + t/4 and +8 and
+// the column pair 8j + 2(t%4) + {0,1} of every 8-column block j; warps w and w + 4 split the blocks.  epi(row, column, values[2]).
+template <class L, class X, class Epi>
+FE_DEV void tc_epilogue64(X& x, int tid, Epi epi) {
+    constexpr int NB8 = (L::N + 7) / 8, BH = (NB8 + 1) / 2, GBK = 6;     // 8-column blocks: total, per warp half, per load batch
+    const int q = (tid >> 5) & 3, half = tid >> 7, t = tid & 31;
+    const int r0 = 16 * q + (t >> 2), r1 = r0 + 8, cc = 2 * (t & 3);
+    if (16 * q < L::NPOS) {                    // warp-uniform: quadrants past the last position hold no rows
+#pragma unroll
+        for (int b0 = 0; b0 < BH; b0 += GBK) {
+            float v[GBK][4];
+#pragma unroll
+            for (int i = 0; i < GBK; ++i) {
+                const int j = half * BH + b0 + i;
+                if (b0 + i < BH && j < NB8) x.tmem_ld16(tid, 8 * j, v[i]);
+            }
+            x.tmem_ld_wait();
+            x.sub_end(tid, PH_TC_LD);
+#pragma unroll
+            for (int i = 0; i < GBK; ++i) {
+                const int j = half * BH + b0 + i, c = 8 * j + cc;
+                if (b0 + i < BH && j < NB8 && c < L::N) {
+                    if (r0 < L::NPOS) epi(r0, c, v[i]);
+                    if (r1 < L::NPOS) epi(r1, c, v[i] + 2);
+                }
+            }
+            x.sub_end(tid, PH_TC_EPI);
+        }
+    }
+}
+
 // a_desc(j) -> descriptor of the A operand of k-step j (two 4-channel slabs, LBO apart), positioned at the first data
 // slot; tap t of a 3-tap layer reads slots shifted by (t - 1) * tapstride (one slot = 16 bytes = 4 floats).
-template <class L, class X, class ADesc, class Epi>
-FE_DEV void tc_layer(X& x, int tid, int ci0, ADesc a_desc, int tapstride, Epi epi) {
-    tc_stream<L>(x, tid, ci0, [&](int tile, typename X::Desc wd) {
+template <class L, bool M64, class X, class ADesc>
+FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride) {
+    static_assert(!M64 || (L::NMT == 1 && L::NPOS <= 64), "M = 64 layers have one M tile");
+    tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
         const int t = tile / L::NKS, j = tile % L::NKS;
         const int shift = (L::TAPS == 3 ? (t - 1) * tapstride : 0);
 #pragma unroll
@@ -464,11 +517,23 @@ FE_DEV void tc_layer(X& x, int tid, int ci0, ADesc a_desc, int tapstride, Epi ep
             const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
 #pragma unroll
             for (int ns = 0; ns < L::NSPLIT; ++ns)
-                x.mma(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
-                      mt * L::NP + ns * L::NPS, tile > 0, rows);
+                x.template mma<M64>(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
+                                    mt * L::NP + ns * L::NPS, tile > 0, rows);
         }
     });
+}
+template <class L, class X, class ADesc, class Epi>
+FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi) {
+    tc_mmas<L, false>(x, tid, ci, a_desc, tapstride);
     tc_epilogue<L>(x, tid, epi);
+}
+template <int W> struct WTag { static constexpr int value = W; };
+// RNNFormer layer (1x1, positions = S * F2): epi(position, first channel, values[W], WTag<W>) with W = 2 (M = 64 path) or 4
+template <class L, bool M64, class X, class ADesc, class Epi>
+FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi) {
+    tc_mmas<L, M64>(x, tid, ci, a_desc, 0);
+    if constexpr (M64) tc_epilogue64<L>(x, tid, [&](int p, int c, const float* v) { epi(p, c, v, WTag<2>{}); });
+    else tc_epilogue<L>(x, tid, [&](int p, int g, const float* v) { epi(p, 4 * g, v, WTag<4>{}); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -520,7 +585,7 @@ template <class P> struct Frame {
             o[0] = t01.x; o[1] = t01.y; o[2] = t23.x; o[3] = t23.y;
             if (round) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = tf32_rna(o[e]);
+                for (int e = 0; e < 4; ++e) o[e] = tf32_pre(o[e]);
             }
             const int off = g * SLABF + (S + gp) * 4;
             st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
@@ -695,33 +760,46 @@ template <class P> struct Frame {
             });
         };
         // x_new -> master + rounded copy; the thread that owns the last real group also zeroes the K-padding group
-        auto store_x = [&](int p, int g, const float* o) {
-            st4(XR + g * RSLABF + p * 4, mk4(o[0], o[1], o[2], o[3]));
-            if constexpr (P::XT_COPY) st4(XT + g * RSLABF + p * 4, mk4(tf32_rna(o[0]), tf32_rna(o[1]), tf32_rna(o[2]), tf32_rna(o[3])));
-            if (NGP > NGX && g == NGX - 1) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
+        // W consecutive channels (first one c, W = 2 or 4) of position p; the thread that owns the last real channels also zeroes the
+        // K-padding group
+        constexpr bool M64 = P::RM64;
+        auto store_x = [&](int p, int c, const float* o, auto wt) {
+            constexpr int W = decltype(wt)::value;
+            const int off = (c >> 2) * RSLABF + p * 4 + (c & 3);
+            store_pt<W>(XR + off, o);
+            if constexpr (P::XT_COPY) {
+                float r[W];
+#pragma unroll
+                for (int e = 0; e < W; ++e) r[e] = tf32_pre(o[e]);
+                store_pt<W>(XT + off, r);
+            }
+            if (NGP > NGX && c + W == C2) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
         };
 
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
         x.phase(PH_LIN_PRE, [&](int tid) {
             // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
-            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S>(x, tid, ci, [&](int l) { return enc_last + act_off(4 * (l / S), l % S, 0); }, S * 4,
+            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, true>(x, tid, ci, [&](int l) { return enc_last + act_off(4 * (l / S), l % S, 0); }, S * 4,
                                                           [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
                 float* yr = Y1 + rf_off(4 * (l / S), l % S, 0);
 #pragma unroll
                 for (int j = 0; j < P::LinPreT::NO; ++j)
                     if (o0 + j < F2)
-                        st4(yr + (o0 + j) * S * 4, mk4(tf32_rna(a[0][j]), tf32_rna(a[1][j]), tf32_rna(a[2][j]), tf32_rna(a[3][j])));
+                        st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
             });
         });
         ci += P::LinPreT::NCHUNK;
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
         x.phase(PH_RF_PRE, [&](int tid) {
             const auto a0 = x.make_desc(Y1, RSLABF);
-            tc_layer<typename P::TRfPre>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
-                                         [&](int p, int g, const float* v) {
-                const f4 b4 = ldg4(aux + A.rf_pre_b + 4 * g);
-                const float o[4] = {v[0] + b4.x, v[1] + b4.y, v[2] + b4.z, v[3] + b4.w};
-                store_x(p, g, o);
+            rf_layer<typename P::TRfPre, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                              [&](int p, int c, const float* v, auto wt) {
+                constexpr int W = decltype(wt)::value;
+                float b[W], o[W];
+                ldg_pt<W>(aux + A.rf_pre_b + c, b);
+#pragma unroll
+                for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
+                store_x(p, c, o, wt);
             });
         });
         ci += P::TRfPre::NCHUNK;
@@ -751,53 +829,84 @@ template <class P> struct Frame {
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
                     const int inp = tile / L::NKS, j = tile % L::NKS;
                     const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
-                    x.mma(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
-                    x.mma(tid, a, x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4), NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                    x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                    x.template mma<M64>(tid, a, x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4), NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
                 });
-                constexpr int GH = (NGX + 1) / 2, GB = 3;              // channel groups per thread, loaded GB at a time
-                const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
-                const int f = p / S, s = p % S, gs = x.s0 + s;
-                for (int i0 = 0; i0 < GH; i0 += GB) {
-                    float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4];
+                // gates + state update of W consecutive channels (first one c) of position p; h is updated in place (every MMA
+                // that read it has completed)
+                auto gru_elem = [&](int p, int c, const float* vr, const float* vz, const float* vx, const float* vh, auto wt) {
+                    constexpr int W = decltype(wt)::value;
+                    float* hp = H + (c >> 2) * RSLABF + p * 4 + (c & 3);
+                    float hov[W], hn[W], br[W], bz[W], bi[W], bh[W];
+                    load_pt<W>(hp, hov);
+                    ldg_pt<W>(aux + ab.b_r + c, br); ldg_pt<W>(aux + ab.b_z + c, bz);
+                    ldg_pt<W>(aux + ab.b_in + c, bi); ldg_pt<W>(aux + ab.b_hn + c, bh);
 #pragma unroll
-                    for (int b = 0; b < GB; ++b) {
-                        const int g = half * GH + i0 + b;
-                        if (i0 + b < GH && g < NGX) {
-                            x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
-                            x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                    for (int e = 0; e < W; e += 2) {
+                        const f2 r = sigmoid2(add2(mk2(vr[e], vr[e + 1]), mk2(br[e], br[e + 1])));
+                        const f2 z = sigmoid2(add2(mk2(vz[e], vz[e + 1]), mk2(bz[e], bz[e + 1])));
+                        const f2 nn = tanh2(fma2(r, add2(mk2(vh[e], vh[e + 1]), mk2(bh[e], bh[e + 1])),
+                                                 add2(mk2(vx[e], vx[e + 1]), mk2(bi[e], bi[e + 1]))));
+                        // (1 - z) n + z h = n + z (h - n)
+                        const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
+                        hn[e] = hv.x; hn[e + 1] = hv.y;
+                    }
+                    store_pt<W>(hp, hn);
+                    if constexpr (!P::H_RES) {
+                        const int gs = x.s0 + p % S;
+                        if (gs < prm.n_streams) {
+                            float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)c * F2 + p / S;
+#pragma unroll
+                            for (int e = 0; e < W; ++e) gp[e * F2] = hn[e];
                         }
                     }
-                    x.tmem_ld_wait();
+                };
+                if constexpr (M64) {
+                    // 16x256b mapping (tc_epilogue64): rows 16q + t/4 (+8), column pair 2(t%4) of each 8-column block, per gate
+                    constexpr int NB8 = (C2 + 7) / 8, BH = (NB8 + 1) / 2, GBK = 3;
+                    const int q = (tid >> 5) & 3, half = tid >> 7, t = tid & 31;
+                    const int r0 = 16 * q + (t >> 2), r1 = r0 + 8, cc = 2 * (t & 3);
+                    if (16 * q < P::RSLOTS) {
 #pragma unroll
-                    for (int b = 0; b < GB; ++b) {
-                        const int g = half * GH + i0 + b;
-                        if (i0 + b < GH && g < NGX && p < P::RSLOTS) {
-                            float* hp = H + g * RSLABF + p * 4;
-                            const f4 ho = ld4(hp);
-                            const float hov[4] = {ho.x, ho.y, ho.z, ho.w};
-                            float hn[4];
-                            const f4 b4r = ldg4(aux + ab.b_r + 4 * g), b4z = ldg4(aux + ab.b_z + 4 * g);
-                            const f4 b4i = ldg4(aux + ab.b_in + 4 * g), b4h = ldg4(aux + ab.b_hn + 4 * g);
-                            const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w};
-                            const float bi[4] = {b4i.x, b4i.y, b4i.z, b4i.w}, bh[4] = {b4h.x, b4h.y, b4h.z, b4h.w};
+                        for (int b0 = 0; b0 < BH; b0 += GBK) {
+                            float vr[GBK][4], vz[GBK][4], vx[GBK][4], vh[GBK][4];
 #pragma unroll
-                            for (int e = 0; e < 4; e += 2) {
-                                const f2 r = sigmoid2(add2(mk2(vr[b][e], vr[b][e + 1]), mk2(br[e], br[e + 1])));
-                                const f2 z = sigmoid2(add2(mk2(vz[b][e], vz[b][e + 1]), mk2(bz[e], bz[e + 1])));
-                                const f2 nn = tanh2(fma2(r, add2(mk2(vh[b][e], vh[b][e + 1]), mk2(bh[e], bh[e + 1])),
-                                                         add2(mk2(vx[b][e], vx[b][e + 1]), mk2(bi[e], bi[e + 1]))));
-                                // (1 - z) n + z h = n + z (h - n)
-                                const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
-                                hn[e] = hv.x; hn[e + 1] = hv.y;
-                            }
-                            st4(hp, mk4(hn[0], hn[1], hn[2], hn[3]));        // in place: every MMA that read H has completed
-                            if constexpr (!P::H_RES) {
-                                if (gs < prm.n_streams) {
-                                    float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)(4 * g) * F2 + f;
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) gp[e * F2] = hn[e];
+                            for (int i = 0; i < GBK; ++i) {
+                                const int j = half * BH + b0 + i;
+                                if (b0 + i < BH && j < NB8) {
+                                    x.tmem_ld16(tid, 0 * NPG + 8 * j, vr[i]); x.tmem_ld16(tid, 1 * NPG + 8 * j, vz[i]);
+                                    x.tmem_ld16(tid, 2 * NPG + 8 * j, vx[i]); x.tmem_ld16(tid, 3 * NPG + 8 * j, vh[i]);
                                 }
                             }
+                            x.tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < GBK; ++i) {
+                                const int j = half * BH + b0 + i, c = 8 * j + cc;
+                                if (b0 + i < BH && j < NB8 && c < C2) {
+                                    if (r0 < P::RSLOTS) gru_elem(r0, c, vr[i], vz[i], vx[i], vh[i], WTag<2>{});
+                                    if (r1 < P::RSLOTS) gru_elem(r1, c, vr[i] + 2, vz[i] + 2, vx[i] + 2, vh[i] + 2, WTag<2>{});
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    constexpr int GH = (NGX + 1) / 2, GB = 3;              // channel groups per thread, loaded GB at a time
+                    const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
+                    for (int i0 = 0; i0 < GH; i0 += GB) {
+                        float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4];
+#pragma unroll
+                        for (int b = 0; b < GB; ++b) {
+                            const int g = half * GH + i0 + b;
+                            if (i0 + b < GH && g < NGX) {
+                                x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
+                                x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                            }
+                        }
+                        x.tmem_ld_wait();
+#pragma unroll
+                        for (int b = 0; b < GB; ++b) {
+                            const int g = half * GH + i0 + b;
+                            if (i0 + b < GH && g < NGX && p < P::RSLOTS) gru_elem(p, 4 * g, vr[b], vz[b], vx[b], vh[b], WTag<4>{});
                         }
                     }
                 }
@@ -806,15 +915,19 @@ template <class P> struct Frame {
             // ---- rnn_fc (+ folded BN) + residual (+ positional embedding in block 0) ----
             x.phase(PH_RNN_FC, [&](int tid) {
                 const auto a0 = x.make_desc(H, RSLABF);
-                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
-                                          [&](int p, int g, const float* v) {
-                    const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.fc_b + 4 * g);
-                    float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
+                rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                               [&](int p, int c, const float* v, auto wt) {
+                    constexpr int W = decltype(wt)::value;
+                    float xo[W], b[W], o[W];
+                    load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
+                    ldg_pt<W>(aux + ab.fc_b + c, b);
+#pragma unroll
+                    for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
                     if (k == 0) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] += ldg(aux + ab.pe + (4 * g + e) * F2 + p / S);
+                        for (int e = 0; e < W; ++e) o[e] += ldg(aux + ab.pe + (c + e) * F2 + p / S);
                     }
-                    store_x(p, g, o);
+                    store_x(p, c, o, wt);
                 });
             });
             ci += P::TFc::NCHUNK;
@@ -824,10 +937,14 @@ template <class P> struct Frame {
             for (int hg = 0; hg < P::NQG; ++hg) {
                 x.phase(PH_QKV, [&](int tid) {
                     const auto a0 = x.make_desc(XT, RSLABF);
-                    tc_layer<typename P::TQkv>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
-                                               [&](int p, int g, const float* v) {
-                        const f4 b4 = ldg4(aux + ab.qkv_b + hg * P::QN + 4 * g);
-                        st4(QKV + p * P::QROW + 4 * g, mk4(v[0] + b4.x, v[1] + b4.y, v[2] + b4.z, v[3] + b4.w));
+                    rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                                    [&](int p, int c, const float* v, auto wt) {
+                        constexpr int W = decltype(wt)::value;
+                        float b[W], o[W];
+                        ldg_pt<W>(aux + ab.qkv_b + hg * P::QN + c, b);
+#pragma unroll
+                        for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
+                        store_pt<W>(QKV + p * P::QROW + c, o);
                     });
                 });
                 ci += P::TQkv::NCHUNK;
@@ -881,17 +998,21 @@ template <class P> struct Frame {
                         const float inv = 1.0f / den;
 #pragma unroll
                         for (int d = 0; d < HD; ++d)
-                            ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_rna(((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv);
+                            ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_pre(((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv);
                     }
                 });
             }
             x.phase(PH_ATTN_FC, [&](int tid) {
                 const auto a0 = x.make_desc(ATT, RSLABF);
-                tc_layer<typename P::TFc>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, 0,
-                                          [&](int p, int g, const float* v) {
-                    const f4 xo = ld4(XR + g * RSLABF + p * 4), b4 = ldg4(aux + ab.afc_b + 4 * g);
-                    const float o[4] = {xo.x + v[0] + b4.x, xo.y + v[1] + b4.y, xo.z + v[2] + b4.z, xo.w + v[3] + b4.w};
-                    store_x(p, g, o);
+                rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                               [&](int p, int c, const float* v, auto wt) {
+                    constexpr int W = decltype(wt)::value;
+                    float xo[W], b[W], o[W];
+                    load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
+                    ldg_pt<W>(aux + ab.afc_b + c, b);
+#pragma unroll
+                    for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
+                    store_x(p, c, o, wt);
                 });
             });
             ci += P::TFc::NCHUNK;
@@ -1096,7 +1217,10 @@ template <class P> struct Frame {
         };
         auto dump_geo1 = [&](const float* buf, int off) {
             x.phase(PH_DBG, [&](int tid) {
-                for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = buf[act_off(idx / F1, 0, idx % F1)];
+                for (int idx = tid; idx < C1 * F1; idx += NT) {
+                    const float v = buf[act_off(idx / F1, 0, idx % F1)];
+                    prm.dbg[off + idx] = P::TC ? tf32_clean(v) : v;       // TC variants: these buffers hold pre-rounded MMA operands
+                }
             });
         };
         auto dump_rf = [&](const float* buf, int off) {
@@ -1359,7 +1483,7 @@ template <class P> struct Frame {
 #pragma unroll
                     for (int j = 0; j < P::LinPostT::NO; ++j)
                         if (o0 + j < F1)
-                            st4(zr + (o0 + j) * S * 4, mk4(tf32_rna(a[0][j]), tf32_rna(a[1][j]), tf32_rna(a[2][j]), tf32_rna(a[3][j])));
+                            st4(zr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
                 });
                 // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
                 for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {

@@ -253,6 +253,13 @@ struct Plan {
     static constexpr int Y1TS = (C::C1 / 4) * RSLABF;  // rf_pre linear output in GeoR
     static constexpr int NPG = round_up(C::C2, 16);    // accumulator columns per GRU gate
     static_assert(RSLOTS <= 128, "RNNFormer positions exceed one M tile: lower S");
+    // RNNFormer MMAs with M = 64 when the positions fit: a 64-row accumulator occupies 16 lanes in each of the four TMEM lane
+    // quadrants, so (with 16x256b loads, where all 32 threads of a warp share 16 rows) the epilogues spread over three or four
+    // schedulers instead of the one or two that own lanes 0..RSLOTS-1 of an M = 128 accumulator.
+#ifndef FE_RM64
+#define FE_RM64 0      // measured on B200 (B, 256 streams): 49.7 vs 47.2 us/hop -- the 2-channel granularity of the 16x256b mapping doubles
+#endif                 // the per-element epilogue overhead, which outweighs the extra warps; kept as an experiment switch
+    static constexpr bool RM64 = TC && FE_RM64 && RSLOTS <= 64;
     // work region AB = [W0 | W1 (| W2)]; RNNFormer: XR at the tail, ATT/HB at 0, G/QKV at XRS.
     // W2 exists only when the RNNFormer scratch needs the room (16 kHz L).
     // TC variants: [QKV | Y1T | Zb from 0 ... | ATT (= h scratch when h is not resident) | XT | XR at the tail].

@@ -43,15 +43,24 @@ template <class P> struct EmuCtx {
     Desc make_desc(const float* p, int lbo_floats) const { return Desc{p, lbo_floats}; }
     Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
     Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats}; }
+    template <bool M64 = false>
     void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
         if (tid != 0) return;                       // one elected lane of warp 0 issues
-        for (int m = 0; m < rows; ++m)
+        if (M64 && rows > 64) throw std::runtime_error("emu: M = 64 MMA with more than 64 rows");
+        for (int m = 0; m < rows; ++m) {
+            const int lane = M64 ? 32 * (m / 16) + m % 16 : m;      // M = 64: 16 rows per TMEM lane quadrant
             for (int n = 0; n < NP; ++n) {
-                float sum = acc ? tmem[m * 512 + col + n] : 0.f;
+                float sum = acc ? tmem[lane * 512 + col + n] : 0.f;
                 for (int k = 0; k < 8; ++k)
                     sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
-                tmem[m * 512 + col + n] = sum;
+                tmem[lane * 512 + col + n] = sum;
             }
+        }
+    }
+    void tmem_ld16(int tid, int col, float* v) const {      // tcgen05.ld.16x256b.x1
+        const int q = (tid >> 5) & 3, t = tid & 31, l0 = 32 * q + t / 4, c = col + 2 * (t % 4);
+        v[0] = tmem[l0 * 512 + c]; v[1] = tmem[l0 * 512 + c + 1];
+        v[2] = tmem[(l0 + 8) * 512 + c]; v[3] = tmem[(l0 + 8) * 512 + c + 1];
     }
     void release_mma(int) const {}
     void acc_commit_wait() const {}
