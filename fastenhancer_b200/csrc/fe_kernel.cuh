@@ -42,6 +42,7 @@ inline float ldg(const float* p) { return *p; }
 inline f2 ldg2(const float* p) { return ld2(p); }
 inline f4 ldg4(const float* p) { return ld4(p); }
 inline float fe_exp(float x) { return expf(x); }
+inline float fe_exp2(float x) { return exp2f(x); }
 inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
@@ -60,6 +61,7 @@ FE_DEV float ldg(const float* p) { return __ldg(p); }
 FE_DEV f2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 FE_DEV f4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 FE_DEV float fe_exp(float x) { return __expf(x); }
+FE_DEV float fe_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
 // round to nearest TF32 so that the tensor core (which reads the top 19 bits) sees the value exactly
 FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
@@ -153,6 +155,15 @@ FE_DEV f2 silu2(f2 x) {
     return fma2(h, t, h);
 #else
     f2 y; y.x = silu(x.x); y.y = silu(x.y); return y;
+#endif
+}
+// SiLU of x given h = x / 2 (the SiLU layers of the tensor-core variants carry pre-halved weights and biases: fe_pack.h)
+FE_DEV f2 silu2_half(f2 h) {
+#if FE_FAST_ACT >= 1
+    f2 t; t.x = tanh_fast(h.x); t.y = tanh_fast(h.y);
+    return fma2(h, t, h);
+#else
+    f2 y; y.x = silu(2.f * h.x); y.y = silu(2.f * h.y); return y;
 #endif
 }
 FE_DEV f2 sigmoid2(f2 x) {
@@ -577,11 +588,12 @@ template <class P> struct Frame {
     // also re-zeroes the S halo slots at both ends of the slab (the buffers are aliased between layers).
     struct TcEpiAct {
         float* dst; const float* bias; float* gdst; bool act; bool round;
+        bool halo;      // re-zero the halo slots: needed only where something else wrote over the buffer since they were last zeroed
         FE_DEV void operator()(int gp, int g, const float* v) const {
             float o[4];
             const f4 b4 = ldg4(bias + 4 * g);
             f2 t01 = add2(mk2(v[0], v[1]), mk2(b4.x, b4.y)), t23 = add2(mk2(v[2], v[3]), mk2(b4.z, b4.w));
-            if (act) { t01 = silu2(t01); t23 = silu2(t23); }
+            if (act) { t01 = silu2_half(t01); t23 = silu2_half(t23); }
             o[0] = t01.x; o[1] = t01.y; o[2] = t23.x; o[3] = t23.y;
             if (round) {
 #pragma unroll
@@ -589,8 +601,10 @@ template <class P> struct Frame {
             }
             const int off = g * SLABF + (S + gp) * 4;
             st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
-            if (gp < S) st4(dst + g * SLABF + gp * 4, mk4(0.f, 0.f, 0.f, 0.f));
-            if (gp >= S * F1 - S) st4(dst + g * SLABF + (gp + 2 * S) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            if (halo) {
+                if (gp < S) st4(dst + g * SLABF + gp * 4, mk4(0.f, 0.f, 0.f, 0.f));
+                if (gp >= S * F1 - S) st4(dst + g * SLABF + (gp + 2 * S) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            }
             if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
         }
     };
@@ -950,7 +964,7 @@ template <class P> struct Frame {
                 ci += P::TQkv::NCHUNK;
                 x.phase(PH_ATTN, [&](int tid) {
                     constexpr int HDP = P::HDP, H4 = P::HDP / 4;
-                    const float scale = 1.0f / sqrtf((float)HD);
+                    const float scale = 1.4426950408889634f / sqrtf((float)HD);     // log2(e) folded in: softmax via ex2
                     if (hg == 0)
                         for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)       // K-padding channels of the attn_fc operand
                             ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
@@ -990,10 +1004,10 @@ template <class P> struct Frame {
 #pragma unroll
                             for (int j = 0; j < F2; ++j) { sc[j] = score(j); mx = fmaxf(mx, sc[j]); }
 #pragma unroll
-                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp(sc[j] - mx); den += pj; accum(j, pj); }
+                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp2(sc[j] - mx); den += pj; accum(j, pj); }
                         } else {
                             for (int j = 0; j < F2; ++j) mx = fmaxf(mx, score(j));
-                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp(score(j) - mx); den += pj; accum(j, pj); }
+                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp2(score(j) - mx); den += pj; accum(j, pj); }
                         }
                         const float inv = 1.0f / den;
 #pragma unroll
@@ -1236,7 +1250,7 @@ template <class P> struct Frame {
             float* dst = skip_dst(x, i);
             const float* bias = aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1));
             if constexpr (P::TC) {
-                TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true};
+                TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true, i >= P::SKIP_SMEM};    // dedicated skip buffers keep their zero halos
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
@@ -1492,7 +1506,7 @@ template <class P> struct Frame {
                 }
             });
             ci += P::LinPostT::NCHUNK;
-            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
+            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true, true};      // W1 was FFT / RNNFormer scratch
             x.phase(PH_RF_POST, [&](int tid) {
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
                 tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
@@ -1532,7 +1546,8 @@ template <class P> struct Frame {
             if constexpr (P::TC) {
                 // 1x1 conv over cat([x, skip]) + SiLU: k-steps 0..C1/8-1 read x (W1), the rest read the skip tensor.
                 // All MMAs complete before any epilogue thread stores, so writing W0 (which may hold the skip) is safe.
-                TcEpiAct epi{W0, b1, nullptr, true, true};
+                // W0 was scratch (i = 0) or has just been loaded from the global skip spill, whose halo slots are never written
+                TcEpiAct epi{W0, b1, nullptr, true, true, i == 0 || sk >= P::SKIP_SMEM};
                 x.phase(PH_PWCAT, [&](int tid) {
                     const auto ax = x.make_desc(W1 + S * 4, SLABF), as = x.make_desc(skip + S * 4, SLABF);
                     tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
@@ -1540,7 +1555,7 @@ template <class P> struct Frame {
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {
-                    TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};
+                    TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true, false};      // rf_post zeroed W1's halos this frame
                     x.phase(PH_DEC, [&](int tid) {
                         const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                         tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2);
@@ -1585,7 +1600,7 @@ template <class P> struct Frame {
         // transposed conv as a 3-tap conv to 8 virtual channels (o*4 + q) -> MASK (in W1)
         float* MASK = W1;
         if constexpr (P::TC) {
-            TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};
+            TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false, false};     // the mask is not a conv input
             x.phase(PH_CONVT, [&](int tid) {
                 const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                 tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);

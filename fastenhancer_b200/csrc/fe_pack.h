@@ -99,7 +99,7 @@ template <class P> class Packer {
         return x;
     }
     // tensor-core tiles, w(n, k, tap): tile (tap, k-step j) = [2][NP][4] holding W[n][8j + 4*kc2 + e][tap]
-    template <class L, class W> void tc(W w) {
+    template <class L, class W> void tc(W w, float scale = 1.f) {
         for (int c = 0; c < L::NCHUNK; ++c) {
             int tiles = cmin(L::TPC, L::NTILE - c * L::TPC);
             table_.push_back((int)(off_ + (long)c * L::TPC * L::TILE));
@@ -111,7 +111,7 @@ template <class P> class Packer {
                 for (int n = 0; n < L::NP; ++n)
                     for (int e = 0; e < 4; ++e) {
                         const int k = 8 * j + 4 * kc2 + e;
-                        blob_[off_ + (long)tile * L::TILE + (kc2 * L::NP + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(n, k, t)) : 0.f;
+                        blob_[off_ + (long)tile * L::TILE + (kc2 * L::NP + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(scale * w(n, k, t)) : 0.f;
                     }
         }
         off_ += L::FLOATS;
@@ -207,6 +207,15 @@ public:
         cp(A.rf_post_b, cw.rf_post_b, C1);
         for (int i = 0; i < C::E; ++i) { cp(A.dec1_b(i), cw.dec_b1[i], C1); cp(A.dec2_b(i), cw.dec_b2[i], C1); }
         cp(A.dp_b, cw.dp_b, C1);
+        // Tensor-core variants: layers followed by SiLU carry weights and bias pre-multiplied by 1/2 (exact), so the accumulator is
+        // h = x / 2 and the epilogue computes silu(x) = h + h tanh(h) without the extra multiply.
+        constexpr float HS = P::TC ? 0.5f : 1.f;
+        if constexpr (P::TC) {
+            auto half = [&](int dst, int n) { for (int i = 0; i < n; ++i) blob_[dst + i] *= 0.5f; };
+            half(A.enc_pre_b, C1);
+            for (int i = 0; i < C::E; ++i) { half(A.enc_b(i), C1); half(A.dec1_b(i), C1); half(A.dec2_b(i), C1); }
+            half(A.dp_b, C1);
+        }
         for (int vo = 0; vo < 8; ++vo) blob_[A.convt_b + vo] = cw.dp_bt[vo / 4];   // entries 8..15 stay zero (tensor-core N padding)
 
         // ---- ring section, execution order (must match fe_kernel.cuh::frame) ----
@@ -237,9 +246,9 @@ public:
             }
         };
         if constexpr (P::TC) {
-            tc<typename P::TEncPre>(w_enc_pre);
+            tc<typename P::TEncPre>(w_enc_pre, HS);
             for (int i = 0; i < C::E; ++i)
-                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; });
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; }, HS);
             rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
             tc<typename P::TRfPre>([&](int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
             for (int k = 0; k < C::K; ++k) {
@@ -258,10 +267,10 @@ public:
             rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
             tc<typename P::TRfPost>([&](int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
             for (int i = 0; i < C::E; ++i) {
-                tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; });
-                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; });
+                tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; }, HS);
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; }, HS);
             }
-            tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; });
+            tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; }, HS);
             tc<typename P::TConvT>(w_convt);
         } else {
             pos<typename P::EncPre>([&](int, int co, int v, int t) { return w_enc_pre(co, v, t); });
