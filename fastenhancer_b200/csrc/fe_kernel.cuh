@@ -459,15 +459,18 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
 // every consumer thread owns accumulator row m (TMEM lane) and half of the NG channel groups
 template <class L, class X, class Epi>
 FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
+    // Straight-line code matters here: a branch inside the unrolled group loop keeps the compiler from interleaving the
+    // groups' dependency chains (measured: ~500 cycles per conv layer), so group validity is a compile-time fact when NG is even.
     constexpr int GH = (L::NG + 1) / 2;
-    const int half = tid >> 7, m = (((tid >> 5) & 3) << 5) + (tid & 31);
+    constexpr bool EVEN = (L::NG % 2 == 0);
+    const int half = (tid >> 7) & 1, m = (((tid >> 5) & 3) << 5) + (tid & 31);
 #pragma unroll
     for (int mt = 0; mt < L::NMT; ++mt) {
         float v[GH][4];
 #pragma unroll
         for (int i = 0; i < GH; ++i) {
             const int g = half * GH + i;
-            if (g < L::NG) x.tmem_ld4(tid, mt * L::NP + 4 * g, v[i]);
+            if (EVEN || g < L::NG) x.tmem_ld4(tid, mt * L::NP + 4 * g, v[i]);
         }
         x.tmem_ld_wait();
         x.sub_end(tid, PH_TC_LD);
@@ -476,7 +479,7 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
 #pragma unroll
             for (int i = 0; i < GH; ++i) {
                 const int g = half * GH + i;
-                if (g < L::NG) epi(gp, g, v[i]);
+                if (EVEN || g < L::NG) epi(gp, g, v[i]);
             }
         }
         x.sub_end(tid, PH_TC_EPI);
@@ -588,7 +591,6 @@ template <class P> struct Frame {
     // also re-zeroes the S halo slots at both ends of the slab (the buffers are aliased between layers).
     struct TcEpiAct {
         float* dst; const float* bias; float* gdst; bool act; bool round;
-        bool halo;      // re-zero the halo slots: needed only where something else wrote over the buffer since they were last zeroed
         FE_DEV void operator()(int gp, int g, const float* v) const {
             float o[4];
             const f4 b4 = ldg4(bias + 4 * g);
@@ -601,13 +603,20 @@ template <class P> struct Frame {
             }
             const int off = g * SLABF + (S + gp) * 4;
             st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
-            if (halo) {
-                if (gp < S) st4(dst + g * SLABF + gp * 4, mk4(0.f, 0.f, 0.f, 0.f));
-                if (gp >= S * F1 - S) st4(dst + g * SLABF + (gp + 2 * S) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            if constexpr (P::SKIP_SMEM < P::NSK) {       // only configs that spill skip tensors ever pass a global destination
+                if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
             }
-            if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
         }
     };
+    // Re-zero the S halo slots at both ends of every slab of a conv-section buffer.  Needed only where something else wrote over
+    // the buffer since the halos were last zeroed (FFT / RNNFormer scratch, skip tensors reloaded from the global spill); kept out
+    // of the epilogue's group loop.  Runs inside the phase of the layer that writes `dst` (halo and data slots are disjoint).
+    FE_DEV static void zero_halo(float* dst, int tid, int nslab) {
+        for (int idx = tid; idx < nslab * 2 * S; idx += NT) {
+            const int g = idx / (2 * S), r = idx % (2 * S);
+            st4(dst + g * SLABF + (r < S ? r : S * F1 + r) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
 
     // Geo1 output row: bias (+SiLU), data columns, the 4 zero pad columns and the buffer tail.
     struct EpiGeo1 {
@@ -777,8 +786,9 @@ template <class P> struct Frame {
         // W consecutive channels (first one c, W = 2 or 4) of position p; the thread that owns the last real channels also zeroes the
         // K-padding group
         constexpr bool M64 = P::RM64;
-        auto store_x = [&](int p, int c, const float* o, auto wt) {
+        auto store_x = [&](int p, int c, const float* o, auto wt, auto zp) {
             constexpr int W = decltype(wt)::value;
+            constexpr bool ZERO_PAD = decltype(zp)::value != 0;       // XT's padding group is scratch of the conv section: rf_pre re-zeroes it
             const int off = (c >> 2) * RSLABF + p * 4 + (c & 3);
             store_pt<W>(XR + off, o);
             if constexpr (P::XT_COPY) {
@@ -787,7 +797,7 @@ template <class P> struct Frame {
                 for (int e = 0; e < W; ++e) r[e] = tf32_pre(o[e]);
                 store_pt<W>(XT + off, r);
             }
-            if (NGP > NGX && c + W == C2) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
+            if (ZERO_PAD && NGP > NGX && c + W == C2) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
         };
 
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
@@ -813,7 +823,7 @@ template <class P> struct Frame {
                 ldg_pt<W>(aux + A.rf_pre_b + c, b);
 #pragma unroll
                 for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
-                store_x(p, c, o, wt);
+                store_x(p, c, o, wt, WTag<1>{});
             });
         });
         ci += P::TRfPre::NCHUNK;
@@ -848,7 +858,7 @@ template <class P> struct Frame {
                 });
                 // gates + state update of W consecutive channels (first one c) of position p; h is updated in place (every MMA
                 // that read it has completed)
-                auto gru_elem = [&](int p, int c, const float* vr, const float* vz, const float* vx, const float* vh, auto wt) {
+                auto gru_elem = [&](int p, int c, const float* vr, const float* vz, const float* vx, const float* vh, bool valid, auto wt) {
                     constexpr int W = decltype(wt)::value;
                     float* hp = H + (c >> 2) * RSLABF + p * 4 + (c & 3);
                     float hov[W], hn[W], br[W], bz[W], bi[W], bh[W];
@@ -865,10 +875,10 @@ template <class P> struct Frame {
                         const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
                         hn[e] = hv.x; hn[e + 1] = hv.y;
                     }
-                    store_pt<W>(hp, hn);
+                    if (valid) store_pt<W>(hp, hn);        // rows past the last position compute on garbage and store nothing
                     if constexpr (!P::H_RES) {
                         const int gs = x.s0 + p % S;
-                        if (gs < prm.n_streams) {
+                        if (valid && gs < prm.n_streams) {
                             float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)c * F2 + p / S;
 #pragma unroll
                             for (int e = 0; e < W; ++e) gp[e * F2] = hn[e];
@@ -897,21 +907,23 @@ template <class P> struct Frame {
                             for (int i = 0; i < GBK; ++i) {
                                 const int j = half * BH + b0 + i, c = 8 * j + cc;
                                 if (b0 + i < BH && j < NB8 && c < C2) {
-                                    if (r0 < P::RSLOTS) gru_elem(r0, c, vr[i], vz[i], vx[i], vh[i], WTag<2>{});
-                                    if (r1 < P::RSLOTS) gru_elem(r1, c, vr[i] + 2, vz[i] + 2, vx[i] + 2, vh[i] + 2, WTag<2>{});
+                                    gru_elem(r0, c, vr[i], vz[i], vx[i], vh[i], r0 < P::RSLOTS, WTag<2>{});
+                                    gru_elem(r1, c, vr[i] + 2, vz[i] + 2, vx[i] + 2, vh[i] + 2, r1 < P::RSLOTS, WTag<2>{});
                                 }
                             }
                         }
                     }
                 } else {
                     constexpr int GH = (NGX + 1) / 2, GB = 3;              // channel groups per thread, loaded GB at a time
-                    const int half = tid >> 7, p = (((tid >> 5) & 3) << 5) + (tid & 31);
+                    constexpr bool EVEN = (NGX % 2 == 0);
+                    const int half = (tid >> 7) & 1, p = (((tid >> 5) & 3) << 5) + (tid & 31);
+#pragma unroll
                     for (int i0 = 0; i0 < GH; i0 += GB) {
                         float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4];
 #pragma unroll
                         for (int b = 0; b < GB; ++b) {
                             const int g = half * GH + i0 + b;
-                            if (i0 + b < GH && g < NGX) {
+                            if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) {
                                 x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
                                 x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
                             }
@@ -920,7 +932,8 @@ template <class P> struct Frame {
 #pragma unroll
                         for (int b = 0; b < GB; ++b) {
                             const int g = half * GH + i0 + b;
-                            if (i0 + b < GH && g < NGX && p < P::RSLOTS) gru_elem(p, 4 * g, vr[b], vz[b], vx[b], vh[b], WTag<4>{});
+                            // straight-line: only the last group of the second half can be past the end (odd group count)
+                            if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) gru_elem(p, 4 * g, vr[b], vz[b], vx[b], vh[b], p < P::RSLOTS, WTag<4>{});
                         }
                     }
                 }
@@ -929,19 +942,19 @@ template <class P> struct Frame {
             // ---- rnn_fc (+ folded BN) + residual (+ positional embedding in block 0) ----
             x.phase(PH_RNN_FC, [&](int tid) {
                 const auto a0 = x.make_desc(H, RSLABF);
+                // positional embedding [F2][C2] of block 0; the other blocks read a row of zeros (no branch in the epilogue)
+                const float* pe = (k == 0) ? aux + ab.pe : aux + A.zeros;
+                const int pfs = (k == 0) ? C2 : 0, pcs = (k == 0) ? 1 : 0;
                 rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
                                                [&](int p, int c, const float* v, auto wt) {
                     constexpr int W = decltype(wt)::value;
-                    float xo[W], b[W], o[W];
+                    float xo[W], b[W], pv[W], o[W];
                     load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
                     ldg_pt<W>(aux + ab.fc_b + c, b);
+                    ldg_pt<W>(pe + (p / S) * pfs + c * pcs, pv);
 #pragma unroll
-                    for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
-                    if (k == 0) {
-#pragma unroll
-                        for (int e = 0; e < W; ++e) o[e] += ldg(aux + ab.pe + (c + e) * F2 + p / S);
-                    }
-                    store_x(p, c, o, wt);
+                    for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + (b[e] + pv[e]);
+                    store_x(p, c, o, wt, WTag<0>{});
                 });
             });
             ci += P::TFc::NCHUNK;
@@ -1026,7 +1039,7 @@ template <class P> struct Frame {
                     ldg_pt<W>(aux + ab.afc_b + c, b);
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
-                    store_x(p, c, o, wt);
+                    store_x(p, c, o, wt, WTag<0>{});
                 });
             });
             ci += P::TFc::NCHUNK;
@@ -1250,15 +1263,18 @@ template <class P> struct Frame {
             float* dst = skip_dst(x, i);
             const float* bias = aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1));
             if constexpr (P::TC) {
-                TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true, i >= P::SKIP_SMEM};    // dedicated skip buffers keep their zero halos
+                TcEpiAct epi{dst, bias, skip_gdst(x, i), true, true};
+                const bool halo = i >= P::SKIP_SMEM;        // dedicated skip buffers keep the zero halos of the one-time init
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
+                        if (halo) zero_halo(dst, tid, C1 / 4);
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
                         tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi);
                     });
                     ci += P::TEncPre::NCHUNK;
                 } else {
                     x.phase(PH_ENC, [&](int tid) {
+                        if (halo) zero_halo(dst, tid, C1 / 4);
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
                         tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
                     });
@@ -1506,8 +1522,9 @@ template <class P> struct Frame {
                 }
             });
             ci += P::LinPostT::NCHUNK;
-            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true, true};      // W1 was FFT / RNNFormer scratch
+            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
             x.phase(PH_RF_POST, [&](int tid) {
+                zero_halo(W1, tid, C1 / 4);          // W1 was FFT / RNNFormer scratch
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
                 tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
             });
@@ -1546,16 +1563,17 @@ template <class P> struct Frame {
             if constexpr (P::TC) {
                 // 1x1 conv over cat([x, skip]) + SiLU: k-steps 0..C1/8-1 read x (W1), the rest read the skip tensor.
                 // All MMAs complete before any epilogue thread stores, so writing W0 (which may hold the skip) is safe.
-                // W0 was scratch (i = 0) or has just been loaded from the global skip spill, whose halo slots are never written
-                TcEpiAct epi{W0, b1, nullptr, true, true, i == 0 || sk >= P::SKIP_SMEM};
+                TcEpiAct epi{W0, b1, nullptr, true, true};
                 x.phase(PH_PWCAT, [&](int tid) {
+                    // W0 was scratch (i = 0) or has just been loaded from the global skip spill, whose halo slots are never written
+                    if (i == 0 || sk >= P::SKIP_SMEM) zero_halo(W0, tid, C1 / 4);
                     const auto ax = x.make_desc(W1 + S * 4, SLABF), as = x.make_desc(skip + S * 4, SLABF);
                     tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
                         return j < C1 / 8 ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - C1 / 8) * SLABF); }, S, epi);
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {
-                    TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true, false};      // rf_post zeroed W1's halos this frame
+                    TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};      // rf_post zeroed W1's halos this frame
                     x.phase(PH_DEC, [&](int tid) {
                         const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                         tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2);
@@ -1600,7 +1618,7 @@ template <class P> struct Frame {
         // transposed conv as a 3-tap conv to 8 virtual channels (o*4 + q) -> MASK (in W1)
         float* MASK = W1;
         if constexpr (P::TC) {
-            TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false, false};     // the mask is not a conv input
+            TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};     // the mask is not a conv input: no halo
             x.phase(PH_CONVT, [&](int tid) {
                 const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                 tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);

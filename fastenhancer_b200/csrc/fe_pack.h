@@ -191,9 +191,9 @@ public:
                 blob_[q.b_hn + c] = b.b_hh[2 * C2 + c];
             }
             cp(q.fc_b, b.fc_b, C2);
-            if (b.pe)
+            if (b.pe)        // fp32 variants read [C2][F2] (4 frequencies per thread), tensor-core variants [F2][C2] (4 channels)
                 for (int f = 0; f < F2; ++f)
-                    for (int c = 0; c < C2; ++c) blob_[q.pe + c * F2 + f] = b.pe[f * C2 + c];
+                    for (int c = 0; c < C2; ++c) blob_[q.pe + (P::TC ? f * C2 + c : c * F2 + f)] = b.pe[f * C2 + c];
             if constexpr (P::TC) {       // padded per-head layout [head][q|k|v][HDP]
                 for (int h = 0; h < C::NH; ++h)
                     for (int w3 = 0; w3 < 3; ++w3)
