@@ -114,6 +114,14 @@ template <class P> struct GpuCtx {
             "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
+    // same, A operand from tensor memory: columns a_col .. a_col + 7 (one fp32 / TF32 element per column, lane = row)
+    __device__ __forceinline__ void mma_ts(int /*tid*/, int a_col, Desc b, int np, int col, bool acc, int /*rows*/) const {
+        const uint64_t db = ((uint64_t)b.hi << 32) | b.lo;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem + (uint32_t)col), "r"(tmem + (uint32_t)a_col), "l"(db), "r"(umma_idesc_tf32(128, np)), "r"(acc ? 1u : 0u) : "memory");
+    }
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
     // the stage, are done); the other warps never touch the stage and arrive at once
     __device__ __forceinline__ void release_mma(int ci) const {
@@ -145,6 +153,15 @@ template <class P> struct GpuCtx {
                      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
         v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
     }
+    // this thread's row (TMEM lane), 4 consecutive columns
+    __device__ __forceinline__ void tmem_st4(int /*tid*/, int col, const float* v) const {
+        const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) << 5) << 16) + (uint32_t)col;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+    }
+    // same for callers that know their row instead of their thread id (the row must be the calling thread's own lane)
+    __device__ __forceinline__ void tmem_st4_row(int /*row*/, int col, const float* v) const { tmem_st4(0, col, v); }
+    __device__ __forceinline__ void tmem_st_wait() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ void tmem_ld_wait() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
     // end of a phase: make generic-proxy shared-memory writes visible to the async proxy (MMA operand reads) and order
     // TMEM accesses across the barrier

@@ -457,7 +457,9 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
 }
 
 // every consumer thread owns accumulator row m (TMEM lane) and half of the NG channel groups
-template <class L, class X, class Epi>
+// ALLROWS: epi(gp, g, v, valid) runs for every lane, rows past the last position included (valid = false): needed when the
+// epilogue contains warp-collective tcgen05.st, which all 32 lanes must execute.
+template <class L, bool ALLROWS = false, class X, class Epi>
 FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
     // Straight-line code matters here: a branch inside the unrolled group loop keeps the compiler from interleaving the
     // groups' dependency chains (measured: ~500 cycles per conv layer), so group validity is a compile-time fact when NG is even.
@@ -475,7 +477,13 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
         x.tmem_ld_wait();
         x.sub_end(tid, PH_TC_LD);
         const int gp = mt * 128 + m;
-        if (gp < L::NPOS) {
+        if constexpr (ALLROWS) {
+#pragma unroll
+            for (int i = 0; i < GH; ++i) {
+                const int g = half * GH + i;
+                if (EVEN || g < L::NG) epi(gp, g, v[i], gp < L::NPOS);      // g is warp-uniform
+            }
+        } else if (gp < L::NPOS) {
 #pragma unroll
             for (int i = 0; i < GH; ++i) {
                 const int g = half * GH + i;
@@ -543,11 +551,26 @@ FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi
 }
 template <int W> struct WTag { static constexpr int value = W; };
 // RNNFormer layer (1x1, positions = S * F2): epi(position, first channel, values[W], WTag<W>) with W = 2 (M = 64 path) or 4
-template <class L, bool M64, class X, class ADesc, class Epi>
+// ALLROWS: see tc_epilogue (rows past the last position reach epi with valid = false).
+template <class L, bool M64, bool ALLROWS = false, class X, class ADesc, class Epi>
 FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi) {
     tc_mmas<L, M64>(x, tid, ci, a_desc, 0);
-    if constexpr (M64) tc_epilogue64<L>(x, tid, [&](int p, int c, const float* v) { epi(p, c, v, WTag<2>{}); });
-    else tc_epilogue<L>(x, tid, [&](int p, int g, const float* v) { epi(p, 4 * g, v, WTag<4>{}); });
+    if constexpr (M64) tc_epilogue64<L>(x, tid, [&](int p, int c, const float* v) { epi(p, c, v, true, WTag<2>{}); });
+    else if constexpr (ALLROWS) tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
+    else tc_epilogue<L>(x, tid, [&](int p, int g, const float* v) { epi(p, 4 * g, v, true, WTag<4>{}); });
+}
+
+// Same with the A operand in tensor memory: k-step j reads columns a_col0 + 8j .. + 7 (TMEM lane = position, M = 128).
+template <class L, class X, class Epi>
+FE_DEV void rf_layer_ts(X& x, int tid, int ci, int a_col0, Epi epi) {
+    static_assert(L::NMT == 1 && L::TAPS == 1, "TMEM A operands: one M tile, no taps");
+    tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
+#pragma unroll
+        for (int ns = 0; ns < L::NSPLIT; ++ns)
+            x.mma_ts(tid, a_col0 + 8 * tile, x.desc_add(wd, ns * L::NPS * 4), L::NPS, ns * L::NPS, tile > 0, L::NPOS);
+    });
+    // every lane runs the epilogue (it may store operands to tensor memory); rows past the end come with valid = false
+    tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -659,7 +682,30 @@ template <class P> struct Frame {
                 }
             });
         }
-        if (P::H_RES && has_model) {    // GRU state of every block stays in shared memory for the whole launch
+        if (P::H_TMEM && has_model) {   // GRU state of every block stays in tensor memory for the whole launch (lane = position)
+            x.phase(PH_STATE, [&](int tid) {
+                constexpr int NGP = P::C2P / 4, GHP = (NGP + 1) / 2;
+                const int half = (tid >> 7) & 1, p = (((tid >> 5) & 3) << 5) + (tid & 31), f = p / S, gs = x.s0 + p % S;
+                const bool live = p < P::RSLOTS && gs < prm.n_streams;
+                for (int i = 0; i < GHP; ++i) {
+                    const int g = half * GHP + i;
+                    if (g < NGP) {       // warp-uniform
+                        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+                        x.tmem_st4(tid, P::TM_XT + 4 * g, z);      // K-padding columns of x stay zero; the others are rewritten every hop
+                        for (int k = 0; k < C::K; ++k) {
+                            float v[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = 4 * g + e;
+                                v[e] = (live && c < C2) ? prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f] : 0.f;
+                            }
+                            x.tmem_st4(tid, P::TM_H + k * P::C2P + 4 * g, v);
+                        }
+                    }
+                }
+                x.tmem_st_wait();
+            });
+        } else if (P::H_RES && has_model) {    // ... or in shared memory
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::K * P::C2P * F2; idx += NT) {
                     const int s = idx / (C::K * P::C2P * F2), r = idx % (C::K * P::C2P * F2);
@@ -674,7 +720,27 @@ template <class P> struct Frame {
             frame(x, hop);
             x.next_frame();
         }
-        if (P::H_RES && has_model) {
+        if (P::H_TMEM && has_model) {
+            x.phase(PH_STATE, [&](int tid) {
+                constexpr int NGX = C2 / 4, GH = (NGX + 1) / 2;
+                const int half = (tid >> 7) & 1, p = (((tid >> 5) & 3) << 5) + (tid & 31), f = p / S, gs = x.s0 + p % S;
+                const bool live = p < P::RSLOTS && gs < prm.n_streams;
+                for (int i = 0; i < GH; ++i) {
+                    const int g = half * GH + i;
+                    if (g < NGX) {
+                        for (int k = 0; k < C::K; ++k) {
+                            float v[4];
+                            x.tmem_ld4(tid, P::TM_H + k * P::C2P + 4 * g, v);
+                            x.tmem_ld_wait();
+                            if (live) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + 4 * g + e) * F2 + f] = v[e];
+                            }
+                        }
+                    }
+                }
+            });
+        } else if (P::H_RES && has_model) {
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::K * C2 * F2; idx += NT) {
                     const int s = idx / (C::K * C2 * F2), r = idx % (C::K * C2 * F2);
@@ -786,18 +852,25 @@ template <class P> struct Frame {
         // W consecutive channels (first one c, W = 2 or 4) of position p; the thread that owns the last real channels also zeroes the
         // K-padding group
         constexpr bool M64 = P::RM64;
-        auto store_x = [&](int p, int c, const float* o, auto wt, auto zp) {
+        auto store_x = [&](int p, int c, const float* o, bool valid, auto wt, auto zp) {
             constexpr int W = decltype(wt)::value;
             constexpr bool ZERO_PAD = decltype(zp)::value != 0;       // XT's padding group is scratch of the conv section: rf_pre re-zeroes it
-            const int off = (c >> 2) * RSLABF + p * 4 + (c & 3);
-            store_pt<W>(XR + off, o);
-            if constexpr (P::XT_COPY) {
-                float r[W];
+            const int off = (c >> 2) * RSLABF + (valid ? p : 0) * 4 + (c & 3);
+            if (valid) store_pt<W>(XR + off, o);
+            if constexpr (P::H_TMEM) {           // the MMAs read x from tensor memory: this thread's lane, columns TM_XT + c ..
+                // (warp-collective: also executed, with garbage, by the lanes past the last position)
+                static_assert(W == 4, "TMEM operand stores are 4 columns wide");
+                const float r[4] = {tf32_pre(o[0]), tf32_pre(o[1]), tf32_pre(o[2]), tf32_pre(o[3])};
+                x.tmem_st4_row(p, P::TM_XT + c, r);          // p is the calling thread's own lane
+            } else {
+                if constexpr (P::XT_COPY) {
+                    float r[W];
 #pragma unroll
-                for (int e = 0; e < W; ++e) r[e] = tf32_pre(o[e]);
-                store_pt<W>(XT + off, r);
+                    for (int e = 0; e < W; ++e) r[e] = tf32_pre(o[e]);
+                    store_pt<W>(XT + off, r);
+                }
+                if (ZERO_PAD && NGP > NGX && c + W == C2) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
             }
-            if (ZERO_PAD && NGP > NGX && c + W == C2) st4(XT + NGX * RSLABF + p * 4, mk4(0.f, 0.f, 0.f, 0.f));   // XT == XR without a copy
         };
 
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
@@ -816,15 +889,16 @@ template <class P> struct Frame {
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
         x.phase(PH_RF_PRE, [&](int tid) {
             const auto a0 = x.make_desc(Y1, RSLABF);
-            rf_layer<typename P::TRfPre, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
-                                              [&](int p, int c, const float* v, auto wt) {
+            rf_layer<typename P::TRfPre, M64, P::H_TMEM>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                              [&](int p, int c, const float* v, bool valid, auto wt) {
                 constexpr int W = decltype(wt)::value;
                 float b[W], o[W];
                 ldg_pt<W>(aux + A.rf_pre_b + c, b);
 #pragma unroll
                 for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
-                store_x(p, c, o, wt, WTag<1>{});
+                store_x(p, c, o, valid, wt, WTag<1>{});
             });
+            if constexpr (P::H_TMEM) x.tmem_st_wait();
         });
         ci += P::TRfPre::NCHUNK;
         if (dbg) dump_rf(XR, TAP_RFPRE);
@@ -850,19 +924,25 @@ template <class P> struct Frame {
                 static_assert(L::NPG == NPG, "GRU tile width");
                 // x tiles then h tiles; each tile = one MMA into R|Z (x and h accumulate together) + one into NX or NH
                 const auto dx = x.make_desc(XT, RSLABF), dh = x.make_desc(H, RSLABF);
+                constexpr int TM_HK0 = P::TM_H;
+                const int tm_h = TM_HK0 + k * P::C2P;                  // this block's state columns (H_TMEM)
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
                     const int inp = tile / L::NKS, j = tile % L::NKS;
-                    const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
-                    x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
-                    x.template mma<M64>(tid, a, x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4), NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                    const auto wn = x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4);
+                    if constexpr (P::H_TMEM) {
+                        const int a_col = (inp == 0 ? P::TM_XT : tm_h) + 8 * j;
+                        x.mma_ts(tid, a_col, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                        x.mma_ts(tid, a_col, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                    } else {
+                        const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
+                        x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                        x.template mma<M64>(tid, a, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                    }
                 });
-                // gates + state update of W consecutive channels (first one c) of position p; h is updated in place (every MMA
-                // that read it has completed)
-                auto gru_elem = [&](int p, int c, const float* vr, const float* vz, const float* vx, const float* vh, bool valid, auto wt) {
+                // gates + new state of W consecutive channels (first one c): hov = h_old, hn = h_new
+                auto gru_gates = [&](int c, const float* vr, const float* vz, const float* vx, const float* vh, const float* hov, float* hn, auto wt) {
                     constexpr int W = decltype(wt)::value;
-                    float* hp = H + (c >> 2) * RSLABF + p * 4 + (c & 3);
-                    float hov[W], hn[W], br[W], bz[W], bi[W], bh[W];
-                    load_pt<W>(hp, hov);
+                    float br[W], bz[W], bi[W], bh[W];
                     ldg_pt<W>(aux + ab.b_r + c, br); ldg_pt<W>(aux + ab.b_z + c, bz);
                     ldg_pt<W>(aux + ab.b_in + c, bi); ldg_pt<W>(aux + ab.b_hn + c, bh);
 #pragma unroll
@@ -875,6 +955,14 @@ template <class P> struct Frame {
                         const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
                         hn[e] = hv.x; hn[e + 1] = hv.y;
                     }
+                };
+                // shared-memory state: updated in place (every MMA that read it has completed)
+                auto gru_elem = [&](int p, int c, const float* vr, const float* vz, const float* vx, const float* vh, bool valid, auto wt) {
+                    constexpr int W = decltype(wt)::value;
+                    float* hp = H + (c >> 2) * RSLABF + p * 4 + (c & 3);
+                    float hov[W], hn[W];
+                    load_pt<W>(hp, hov);
+                    gru_gates(c, vr, vz, vx, vh, hov, hn, wt);
                     if (valid) store_pt<W>(hp, hn);        // rows past the last position compute on garbage and store nothing
                     if constexpr (!P::H_RES) {
                         const int gs = x.s0 + p % S;
@@ -885,6 +973,37 @@ template <class P> struct Frame {
                         }
                     }
                 };
+                if constexpr (P::H_TMEM) {
+                    // tensor-memory state: h_old comes in with the accumulators, h_new goes back to the same columns of this
+                    // thread's lane (rows past the last position carry garbage that nothing reads)
+                    constexpr int GH = (NGX + 1) / 2, GB = 3;
+                    constexpr bool EVEN = (NGX % 2 == 0);
+                    const int half = (tid >> 7) & 1;
+#pragma unroll
+                    for (int i0 = 0; i0 < GH; i0 += GB) {
+                        float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4], vo[GB][4];
+#pragma unroll
+                        for (int b = 0; b < GB; ++b) {
+                            const int g = half * GH + i0 + b;
+                            if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) {
+                                x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
+                                x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                                x.tmem_ld4(tid, tm_h + 4 * g, vo[b]);
+                            }
+                        }
+                        x.tmem_ld_wait();
+#pragma unroll
+                        for (int b = 0; b < GB; ++b) {
+                            const int g = half * GH + i0 + b;
+                            if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) {
+                                float hn[4];
+                                gru_gates(4 * g, vr[b], vz[b], vx[b], vh[b], vo[b], hn, WTag<4>{});
+                                x.tmem_st4(tid, tm_h + 4 * g, hn);
+                            }
+                        }
+                    }
+                    x.tmem_st_wait();
+                } else
                 if constexpr (M64) {
                     // 16x256b mapping (tc_epilogue64): rows 16q + t/4 (+8), column pair 2(t%4) of each 8-column block, per gate
                     constexpr int NB8 = (C2 + 7) / 8, BH = (NB8 + 1) / 2, GBK = 3;
@@ -945,17 +1064,23 @@ template <class P> struct Frame {
                 // positional embedding [F2][C2] of block 0; the other blocks read a row of zeros (no branch in the epilogue)
                 const float* pe = (k == 0) ? aux + ab.pe : aux + A.zeros;
                 const int pfs = (k == 0) ? C2 : 0, pcs = (k == 0) ? 1 : 0;
-                rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
-                                               [&](int p, int c, const float* v, auto wt) {
+                auto epi = [&](int p, int c, const float* v, bool valid, auto wt) {
                     constexpr int W = decltype(wt)::value;
                     float xo[W], b[W], pv[W], o[W];
-                    load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
+                    const int pc = valid ? p : 0;
+                    load_pt<W>(XR + (c >> 2) * RSLABF + pc * 4 + (c & 3), xo);
                     ldg_pt<W>(aux + ab.fc_b + c, b);
-                    ldg_pt<W>(pe + (p / S) * pfs + c * pcs, pv);
+                    ldg_pt<W>(pe + (pc / S) * pfs + c * pcs, pv);
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + (b[e] + pv[e]);
-                    store_x(p, c, o, wt, WTag<0>{});
-                });
+                    store_x(p, c, o, valid, wt, WTag<0>{});
+                };
+                if constexpr (P::H_TMEM) {
+                    rf_layer_ts<typename P::TFc>(x, tid, ci, P::TM_H + k * P::C2P, epi);
+                    x.tmem_st_wait();
+                } else {
+                    rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
+                }
             });
             ci += P::TFc::NCHUNK;
             if (dbg) dump_rf(XR, TAP_BLK + (k * 3 + 0) * F2 * C2);
@@ -964,15 +1089,16 @@ template <class P> struct Frame {
             for (int hg = 0; hg < P::NQG; ++hg) {
                 x.phase(PH_QKV, [&](int tid) {
                     const auto a0 = x.make_desc(XT, RSLABF);
-                    rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
-                                                    [&](int p, int c, const float* v, auto wt) {
+                    auto epi = [&](int p, int c, const float* v, bool valid, auto wt) {
                         constexpr int W = decltype(wt)::value;
                         float b[W], o[W];
                         ldg_pt<W>(aux + ab.qkv_b + hg * P::QN + c, b);
 #pragma unroll
                         for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
-                        store_pt<W>(QKV + p * P::QROW + c, o);
-                    });
+                        if (valid) store_pt<W>(QKV + p * P::QROW + c, o);
+                    };
+                    if constexpr (P::H_TMEM) rf_layer_ts<typename P::TQkv>(x, tid, ci, P::TM_XT, epi);
+                    else rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
                 });
                 ci += P::TQkv::NCHUNK;
                 x.phase(PH_ATTN, [&](int tid) {
@@ -1031,25 +1157,42 @@ template <class P> struct Frame {
             }
             x.phase(PH_ATTN_FC, [&](int tid) {
                 const auto a0 = x.make_desc(ATT, RSLABF);
-                rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
-                                               [&](int p, int c, const float* v, auto wt) {
+                rf_layer<typename P::TFc, M64, P::H_TMEM>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); },
+                                               [&](int p, int c, const float* v, bool valid, auto wt) {
                     constexpr int W = decltype(wt)::value;
                     float xo[W], b[W], o[W];
-                    load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
+                    load_pt<W>(XR + (c >> 2) * RSLABF + (valid ? p : 0) * 4 + (c & 3), xo);
                     ldg_pt<W>(aux + ab.afc_b + c, b);
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
-                    store_x(p, c, o, wt, WTag<0>{});
+                    store_x(p, c, o, valid, wt, WTag<0>{});
                 });
+                if constexpr (P::H_TMEM) x.tmem_st_wait();
             });
             ci += P::TFc::NCHUNK;
             if (dbg) {
                 dump_rf(XR, TAP_BLK + (k * 3 + 1) * F2 * C2);
                 x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
-                    for (int idx = tid; idx < F2 * C2; idx += NT) {
-                        const int c = idx % C2, f = idx / C2;
-                        prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
-                            P::H_RES ? H[rf_off(c, 0, f)] : prm.state[(size_t)x.s0 * C::STATE + hoff + c * F2 + f];
+                    if constexpr (P::H_TMEM) {       // every thread reads its own lane; the rows of stream 0 are dumped
+                        const int half = (tid >> 7) & 1, p = (((tid >> 5) & 3) << 5) + (tid & 31);
+                        constexpr int GH = (NGX + 1) / 2;
+                        for (int i = 0; i < GH; ++i) {
+                            const int g = half * GH + i;
+                            if (g < NGX) {
+                                float v[4];
+                                x.tmem_ld4(tid, P::TM_H + k * P::C2P + 4 * g, v);
+                                x.tmem_ld_wait();
+                                if (p < P::RSLOTS && p % S == 0) {
+                                    for (int e = 0; e < 4; ++e) prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + (p / S) * C2 + 4 * g + e] = v[e];
+                                }
+                            }
+                        }
+                    } else {
+                        for (int idx = tid; idx < F2 * C2; idx += NT) {
+                            const int c = idx % C2, f = idx / C2;
+                            prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
+                                P::H_RES ? H[rf_off(c, 0, f)] : prm.state[(size_t)x.s0 * C::STATE + hoff + c * F2 + f];
+                        }
                     }
                 });
             }

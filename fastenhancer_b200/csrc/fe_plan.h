@@ -289,11 +289,22 @@ struct Plan {
     static constexpr int SM_FIXED = AB + SM_REST;
     static_assert(SM_FIXED <= 227 * 256, "shared memory plan exceeds 227 KB even with every skip tensor spilled");
     static constexpr int SKIP_SMEM = cmax(0, cmin(cmin(NSK, T::SKIP_SMEM_MAX), (227 * 256 - SM_FIXED) / ACT));
-    // TC variants keep the GRU state of all K blocks resident in shared memory across hops when it fits
-    static constexpr bool H_RES = TC && (SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
+    // ---- tensor memory (TC variants): accumulators, and -- when the columns fit -- the MMA A operands of the RNNFormer:
+    //      the TF32 copy of x and the GRU state of all K blocks (one fp32 column per channel, TMEM lane = position).  An MMA whose
+    //      A operand comes from TMEM costs ~33 cycles against ~100 from shared memory (tools/tc_bench2.cu), the epilogue threads
+    //      already own the rows (lanes) they write, and TMEM is never aliased, so the K-padding columns are zeroed once. ----
+    static constexpr int ACCW = cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(QN, 16)));
+#ifndef FE_HTMEM
+#define FE_HTMEM 1
+#endif
+    static constexpr bool H_TMEM = TC && FE_HTMEM && !RM64 && (ACCW + C2P * (C::K + 1) <= 512);
+    static constexpr int TM_XT = ACCW;                 // C2P columns: TF32-rounded x
+    static constexpr int TM_H = ACCW + C2P;            // K x C2P columns: GRU state, resident for the whole launch
+    // TC variants keep the GRU state of all K blocks on chip across hops: in TMEM, else in shared memory when it fits
+    static constexpr bool H_RES = TC && (H_TMEM || SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
     static constexpr int SM_SK = 0;
-    static constexpr int SM_HST = SM_SK + SKIP_SMEM * ACT;          // [K][XTS] resident GRU state (GeoR)
-    static constexpr int SM_W = SM_HST + (H_RES ? C::K * XTS : 0);
+    static constexpr int SM_HST = SM_SK + SKIP_SMEM * ACT;          // [K][XTS] resident GRU state (GeoR) unless it lives in TMEM
+    static constexpr int SM_W = SM_HST + ((H_RES && !H_TMEM) ? C::K * XTS : 0);
     static constexpr int SM_SPEC = SM_W + AB;
     static constexpr int SM_TIN = SM_SPEC + SPECF;             // last N input samples per stream (circular)
     static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
@@ -327,7 +338,7 @@ struct Plan {
     using TConvT = TcGemm<S * C::F1, 8, C::C1, 3, CHUNK>;
     using TRfPost = TcGemm<S * C::F1, C::C1, C::C2, 1, CHUNK>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
-    static constexpr int TMEMC = pow2ceil(cmax(cmax(32, 4 * NPG), cmax(cdiv(S * C::F1, 128) * round_up(C::C1, 16), round_up(QN, 16))));
+    static constexpr int TMEMC = pow2ceil(H_TMEM ? ACCW + C2P * (C::K + 1) : ACCW);
     static_assert(TMEMC <= 512, "TMEM columns");
     using TRfPre = TcGemm<S * C::F2, C::C2, C::C1, 1, CHUNK, 512>;
     using TGru = TcGru<S * C::F2, C::C2, CHUNK>;

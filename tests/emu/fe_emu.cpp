@@ -57,6 +57,21 @@ template <class P> struct EmuCtx {
             }
         }
     }
+    void mma_ts(int tid, int a_col, Desc b, int NP, int col, bool acc, int rows) {      // A operand from tensor memory
+        if (tid != 0) return;
+        for (int m = 0; m < rows; ++m)
+            for (int n = 0; n < NP; ++n) {
+                float sum = acc ? tmem[m * 512 + col + n] : 0.f;
+                for (int k = 0; k < 8; ++k) sum += tf32_trunc(tmem[m * 512 + a_col + k]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
+                tmem[m * 512 + col + n] = sum;
+            }
+    }
+    void tmem_st4(int tid, int col, const float* v) {
+        const int row = (((tid >> 5) & 3) << 5) + (tid & 31);
+        for (int e = 0; e < 4; ++e) tmem[row * 512 + col + e] = v[e];
+    }
+    void tmem_st4_row(int row, int col, const float* v) { for (int e = 0; e < 4; ++e) tmem[row * 512 + col + e] = v[e]; }
+    void tmem_st_wait() const {}
     void tmem_ld16(int tid, int col, float* v) const {      // tcgen05.ld.16x256b.x1
         const int q = (tid >> 5) & 3, t = tid & 31, l0 = 32 * q + t / 4, c = col + 2 * (t % 4);
         v[0] = tmem[l0 * 512 + c]; v[1] = tmem[l0 * 512 + c + 1];
