@@ -104,22 +104,36 @@ template <class P> struct GpuCtx {
         d.lo = (d.lo & 0x0000ffffu) | ((((uint32_t)lbo_floats * 4u) >> 4) << 16);
         return d;
     }
-    // called by every lane of warp 0 (converged); one elected lane issues.  M64: a 64-row MMA, whose accumulator row r
-    // lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
+    // FE_ELECT_ONCE (default): tc_stream elects one lane of warp 0 per weight chunk and that lane alone runs the unrolled MMA
+    // sequence; 0 = every lane runs it and each MMA elects (13 instead of ~8 instructions per MMA in the issue loop).
+#ifndef FE_ELECT_ONCE
+#define FE_ELECT_ONCE 0      // measured on B200 (B, 256 streams): 41.9 vs 39.8 us/hop -- a lone diverged lane issues MMAs more slowly
+#endif
+#if FE_ELECT_ONCE
+#define FE_MMA_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+#define FE_MMA_PRED ""
+    __device__ __forceinline__ bool elect(int) const { return elect_one(); }
+#else
+#define FE_MMA_ELECT ".reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+#define FE_MMA_PRED "@q "
+    __device__ __forceinline__ bool elect(int) const { return true; }
+#endif
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    // M64: a 64-row MMA, whose accumulator row r lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
     template <bool M64 = false>
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
         asm volatile(
-            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            "{\n\t" FE_MMA_ELECT
+            FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // same, A operand from tensor memory: columns a_col .. a_col + 7 (one fp32 / TF32 element per column, lane = row)
     __device__ __forceinline__ void mma_ts(int /*tid*/, int a_col, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t db = ((uint64_t)b.hi << 32) | b.lo;
         asm volatile(
-            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+            "{\n\t" FE_MMA_ELECT
+            FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
             ::"r"(tmem + (uint32_t)col), "r"(tmem + (uint32_t)a_col), "l"(db), "r"(umma_idesc_tf32(128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
@@ -131,9 +145,19 @@ template <class P> struct GpuCtx {
             if (elect_one()) umma_commit(bars + 8u * (P::STAGES + stage));      // the lane that issued this warp's MMAs
         } else if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
     }
+    // FE_ACC_PARK: only warp 0 polls the accumulator-ready mbarrier; the other consumer warps park on a hardware named barrier
+    // (no issue slots, no shared-memory polling next to the MMA issue) that warp 0 joins once the MMAs are done.
+#ifndef FE_ACC_PARK
+#define FE_ACC_PARK 0        // measured on B200 (B, 256 streams): 41.4 vs 39.9 us/hop -- the named barrier costs more than the polling
+#endif
     __device__ __forceinline__ void acc_commit_wait() {
         if (tid < 32) { __syncwarp(); if (elect_one()) umma_commit(acc_bar); }
+#if FE_ACC_PARK
+        if (tid < 32) { mbar_wait(acc_bar, acc_uses & 1u); tc_fence_after(); tc_fence_before(); }   // observe, then publish across the barrier
+        asm volatile("bar.sync 2, %0;" ::"n"(P::NT) : "memory");
+#else
         mbar_wait(acc_bar, acc_uses & 1u);
+#endif
         ++acc_uses;
         tc_fence_after();
     }

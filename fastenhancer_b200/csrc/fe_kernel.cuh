@@ -445,9 +445,13 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
         if ((tid >> 5) == 0) {
             x.mma_fence();
             const typename X::Desc wd = x.make_desc(w, L::NP * 4);
+            // one election per chunk: the elected lane issues the whole unrolled MMA sequence (x.mma itself does not elect)
+            if (x.elect(tid)) {
 #pragma unroll
-            for (int i = 0; i < L::TPC; ++i)
-                if (i < tiles) issue(c * L::TPC + i, x.desc_add(wd, i * L::TILE));
+                for (int i = 0; i < L::TPC; ++i)
+                    if (i < tiles) issue(c * L::TPC + i, x.desc_add(wd, i * L::TILE));
+            }
+            x.warp_sync();
         }
         x.release_mma(ci0 + c);
         x.sub_end(tid, PH_TC_ISSUE);
@@ -854,7 +858,7 @@ template <class P> struct Frame {
         constexpr bool M64 = P::RM64;
         auto store_x = [&](int p, int c, const float* o, bool valid, auto wt, auto zp) {
             constexpr int W = decltype(wt)::value;
-            constexpr bool ZERO_PAD = decltype(zp)::value != 0;       // XT's padding group is scratch of the conv section: rf_pre re-zeroes it
+            [[maybe_unused]] constexpr bool ZERO_PAD = decltype(zp)::value != 0;       // XT's padding group is scratch of the conv section: rf_pre re-zeroes it
             const int off = (c >> 2) * RSLABF + (valid ? p : 0) * 4 + (c & 3);
             if (valid) store_pt<W>(XR + off, o);
             if constexpr (P::H_TMEM) {           // the MMAs read x from tensor memory: this thread's lane, columns TM_XT + c ..

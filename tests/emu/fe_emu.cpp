@@ -37,6 +37,8 @@ template <class P> struct EmuCtx {
     std::vector<float> tmem = std::vector<float>(128 * 512, std::nanf(""));
     static float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
     void mma_fence() const {}
+    bool elect(int tid) const { return tid == 0; }
+    void warp_sync() const {}
     void sub_begin(int) const {}
     void sub_end(int, int) const {}
     struct Desc { const float* p; int lbo; };
