@@ -199,7 +199,12 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     e->canonical.assign(canonical, canonical + n_floats);
     e->variants = std::move(vs);
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
-    if (const char* env = std::getenv("FE_PRECISION")) e->tc = std::strcmp(env, "fp32") == 0 ? 0 : 1;
+    if (const char* env = std::getenv("FE_PRECISION")) {
+        e->tc = std::strcmp(env, "fp32") == 0 ? 0 : 1;
+        if (std::strcmp(env, "f16") == 0) {      // only if this model has fp16 variants
+            for (const Variant& v : e->variants) if (v.ops.tc == 2) e->tc = 2;
+        }
+    }
     *out = e;
     return FE_OK;
 }
@@ -419,12 +424,19 @@ FE_API int fe_set_streams_per_cta(fe_engine* e, int s) {
     e->forced_s = s;
     return FE_OK;
 }
-FE_API int fe_set_precision(fe_engine* e, int fp32_exact) {
+FE_API int fe_set_precision(fe_engine* e, int mode) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_precision: null engine");
-    e->tc = fp32_exact ? 0 : 1;
+    if (mode < 0 || mode > 2) return fail(FE_ERR_ARG, "fe_set_precision: mode must be 0 (tf32), 1 (fp32) or 2 (f16)");
+    const int tc = mode == 1 ? 0 : (mode == 2 ? 2 : 1);
+    bool ok = false;
+    for (const Variant& v : e->variants) ok = ok || (v.ops.tc == tc && (e->forced_s == 0 || v.ops.S == e->forced_s));
+    if (!ok) return fail(FE_ERR_UNSUPPORTED, "fe_set_precision: this model has no kernel variant for the requested mode");
+    e->tc = tc;
     return FE_OK;
 }
-FE_API int fe_get_precision(fe_engine* e) { return e ? (e->tc ? 0 : 1) : fail(FE_ERR_ARG, "fe_get_precision: null engine"); }
+FE_API int fe_get_precision(fe_engine* e) {
+    return e ? (e->tc == 0 ? 1 : (e->tc == 2 ? 2 : 0)) : fail(FE_ERR_ARG, "fe_get_precision: null engine");
+}
 FE_API int fe_profile_slots(void) { return (int)(fe::PH_COUNT + fe::PH_COUNT * fe::PH_NSUB); }
 FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_profile: null engine");

@@ -18,9 +18,11 @@ using C48M = Cfg< 1024, 320,  96, 3, 72, 72, 4>;
 using C48L = Cfg< 1024, 200, 128, 4, 96, 96, 5>;
 }  // namespace fe
 
-// X(config id, Cfg type, S, TC)   TC = conv-type contractions on tcgen05 (TF32); false = everything on the fp32 FMA pipe
-#define FE_VARIANTS_16T(X) X(0, C16T, 1, false) X(0, C16T, 2, false) X(0, C16T, 4, false) X(0, C16T, 1, true) X(0, C16T, 2, true) X(0, C16T, 4, true)
-#define FE_VARIANTS_16B(X) X(1, C16B, 1, false) X(1, C16B, 2, false) X(1, C16B, 1, true) X(1, C16B, 2, true)
+// X(config id, Cfg type, S, PREC)   PREC: false / 0 = everything on the fp32 FMA pipe; true / 1 = contractions on tcgen05 (TF32);
+// 2 = as 1 with the conv section's operands in fp16 (K = 16 per MMA, half the shared memory)
+#define FE_VARIANTS_16T(X) X(0, C16T, 1, false) X(0, C16T, 2, false) X(0, C16T, 4, false) X(0, C16T, 1, true) X(0, C16T, 2, true) X(0, C16T, 4, true) \
+    X(0, C16T, 2, 2)
+#define FE_VARIANTS_16B(X) X(1, C16B, 1, false) X(1, C16B, 2, false) X(1, C16B, 1, true) X(1, C16B, 2, true) X(1, C16B, 1, 2) X(1, C16B, 2, 2)
 #define FE_VARIANTS_16S(X) X(2, C16S, 1, false) X(2, C16S, 1, true)
 #define FE_VARIANTS_16M(X) X(3, C16M, 1, false) X(3, C16M, 1, true)
 #define FE_VARIANTS_16L(X) X(4, C16L, 1, false) X(4, C16L, 1, true)

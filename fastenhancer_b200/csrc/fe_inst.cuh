@@ -48,9 +48,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
 }
-// instruction descriptor: D f32, A/B tf32, both K-major, M = m (128 or 64), N = n
+// instruction descriptor: D f32, A/B tf32 (format 2) or f16 (format 0), both K-major, M = m (128 or 64), N = n
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -120,13 +123,20 @@ template <class P> struct GpuCtx {
 #endif
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     // M64: a 64-row MMA, whose accumulator row r lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
-    template <bool M64 = false>
+    // F16: kind::f16 -- operands are halves (8 per 16-byte row: K = 16 per MMA), same descriptors.
+    template <bool M64 = false, bool F16 = false>
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
-        asm volatile(
-            "{\n\t" FE_MMA_ELECT
-            FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
+        if constexpr (F16)
+            asm volatile(
+                "{\n\t" FE_MMA_ELECT
+                FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_f16(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
+        else
+            asm volatile(
+                "{\n\t" FE_MMA_ELECT
+                FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // same, A operand from tensor memory: columns a_col .. a_col + 7 (one fp32 / TF32 element per column, lane = row)
     __device__ __forceinline__ void mma_ts(int /*tid*/, int a_col, Desc b, int np, int col, bool acc, int /*rows*/) const {
@@ -295,7 +305,7 @@ template <class P> struct VariantImpl {
     static VariantOps ops(int cfg_id) {
         using C = typename P::Cf;
         VariantOps v{};
-        v.cfg_id = cfg_id; v.S = P::S; v.tc = P::TC ? 1 : 0;
+        v.cfg_id = cfg_id; v.S = P::S; v.tc = P::PREC;
         v.shape = ShapeKey{C::N_FFT, C::HOP, C::C1, C::E, C::C2, C::F2, C::K, C::NH};
         v.smem_bytes = P::SMEM_BYTES; v.nthreads = P::NTHREADS; v.gs_floats = P::GS_TOTAL; v.state_floats = C::STATE;
         v.tap_floats = Frame<P>::TAP_TOTAL; v.nchunk_frame = P::NCHUNK_FRAME; v.blob_floats = P::make_aux().total;

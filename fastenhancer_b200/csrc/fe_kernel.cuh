@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include "fe_half.h"
 #define FE_DEV inline
 namespace fe {
 struct f4 { float x, y, z, w; };
@@ -46,6 +47,9 @@ inline float fe_exp2(float x) { return exp2f(x); }
 inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
+// two floats -> two fp16 in one 32-bit word (a in the low half), and back
+inline float pack_h2(float a, float b) { uint32_t u = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(b) << 16); float r; std::memcpy(&r, &u, 4); return r; }
+inline f2 unpack_h2(float p) { uint32_t u; std::memcpy(&u, &p, 4); f2 r; r.x = f16_bits_to_f32((uint16_t)(u & 0xffffu)); r.y = f16_bits_to_f32((uint16_t)(u >> 16)); return r; }
 inline float tf32_clean(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 }  // namespace fe
 #else
@@ -77,6 +81,13 @@ FE_DEV float tf32_pre(float x) { return __uint_as_float(__float_as_uint(x) + 0x1
 FE_DEV float tf32_pre(float x) { return tf32_rna(x); }
 #endif
 FE_DEV float tf32_clean(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// two floats -> two fp16 in one 32-bit word (a in the low half, round to nearest even: one cvt.rn.f16x2.f32), and back
+FE_DEV float pack_h2(float a, float b) { uint32_t u; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a)); return __uint_as_float(u); }
+FE_DEV f2 unpack_h2(float p) {
+    f2 r;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(__float_as_uint(p)));
+    return r;
+}
 }  // namespace fe
 #endif
 
@@ -374,7 +385,9 @@ FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi)
 
 // Same, vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
 // layouts, where channels are the innermost index).  xrow(l) -> float4 of k = 0 for lane l (< NLANE); epi(l, o0, acc[4][NO]).
-template <class L, int NLANE, bool CLEAN = false, class X, class XRow, class Epi>
+// CLEAN: the input holds pre-rounded TF32 MMA operands (tf32_pre): mask the low bits.  XH16: the input holds halves (8 bytes = the
+// lane's 4 channels).
+template <class L, int NLANE, bool CLEAN = false, bool XH16 = false, class X, class XRow, class Epi>
 FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
     constexpr int NO = L::NO;
     static_assert(NLANE <= 32 && L::RT <= 4, "row gemm (vector form): at most 32 lanes of 4 channels");
@@ -394,7 +407,14 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
             const float* wl = w + og * NO;
 #pragma unroll 4
             for (int kk = 0; kk < rows; ++kk) {
-                f4 xv = ld4(xr + (c * L::KC + kk) * kstride);
+                f4 xv;
+                if constexpr (XH16) {
+                    const f2 raw = ld2(xr + (c * L::KC + kk) * kstride);
+                    const f2 lo = unpack_h2(raw.x), hi = unpack_h2(raw.y);
+                    xv = mk4(lo.x, lo.y, hi.x, hi.y);
+                } else {
+                    xv = ld4(xr + (c * L::KC + kk) * kstride);
+                }
                 if constexpr (CLEAN) { xv.x = tf32_clean(xv.x); xv.y = tf32_clean(xv.y); xv.z = tf32_clean(xv.z); xv.w = tf32_clean(xv.w); }
                 f2 xd[4];
                 xd[0].x = xd[0].y = xv.x; xd[1].x = xd[1].y = xv.y; xd[2].x = xd[2].y = xv.z; xd[3].x = xd[3].y = xv.w;
@@ -543,8 +563,8 @@ FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride) {
             const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
 #pragma unroll
             for (int ns = 0; ns < L::NSPLIT; ++ns)
-                x.template mma<M64>(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
-                                    mt * L::NP + ns * L::NPS, tile > 0, rows);
+                x.template mma<M64, L::KE == 16>(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
+                                                 mt * L::NP + ns * L::NPS, tile > 0, rows);
         }
     });
 }
@@ -614,6 +634,17 @@ template <class P> struct Frame {
         else return c * CP1 + s * P1 + 4 + f;
     }
 
+    // H16 variants: float offset of the 8-byte unit holding channels c..c+3 (c % 4 == 0) of (stream s, position f) in a conv-section
+    // operand buffer [C/8][SLOTS][8 halves]; the same for an RNNFormer-position buffer (rf_pre linear output)
+    FE_DEV static int act_off16(int c, int s, int f) { return (c >> 3) * SLABF + ((f + 1) * S + s) * 4 + ((c >> 2) & 1) * 2; }
+    FE_DEV static int rf_off16(int c, int s, int f) { return (c >> 3) * P::RSLABF + (f * S + s) * 4 + ((c >> 2) & 1) * 2; }
+    // one activation element as fp32, whatever the storage format (taps / debug only)
+    FE_DEV static float act_get(const float* buf, int c, int s, int f) {
+        if constexpr (P::H16) { const f2 v = unpack_h2(buf[act_off16(c & ~3, s, f) + ((c >> 1) & 1)]); return (c & 1) ? v.y : v.x; }
+        else if constexpr (P::TC) return tf32_clean(buf[act_off(c, s, f)]);       // pre-rounded MMA operands
+        else return buf[act_off(c, s, f)];
+    }
+
     // Tensor-core layer epilogue: bias (+SiLU), TF32 rounding for the next MMA, one float4 per 4-channel group;
     // also re-zeroes the S halo slots at both ends of the slab (the buffers are aliased between layers).
     struct TcEpiAct {
@@ -624,24 +655,43 @@ template <class P> struct Frame {
             f2 t01 = add2(mk2(v[0], v[1]), mk2(b4.x, b4.y)), t23 = add2(mk2(v[2], v[3]), mk2(b4.z, b4.w));
             if (act) { t01 = silu2_half(t01); t23 = silu2_half(t23); }
             o[0] = t01.x; o[1] = t01.y; o[2] = t23.x; o[3] = t23.y;
-            if (round) {
+            if constexpr (P::H16) {
+                if (round) {         // operand of a later MMA: four halves (8 bytes) of the 8-channel row
+                    const int off = (g >> 1) * SLABF + (S + gp) * 4 + (g & 1) * 2;
+                    const f2 h = mk2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+                    st2(dst + off, h);
+                    if constexpr (P::SKIP_SMEM < P::NSK) {
+                        if (gdst) st2(gdst + off, h);
+                    }
+                } else {             // the mask: fp32, the spectrum's layout
+                    st4(dst + g * SLABF + (S + gp) * 4, mk4(o[0], o[1], o[2], o[3]));
+                }
+            } else {
+                if (round) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = tf32_pre(o[e]);
-            }
-            const int off = g * SLABF + (S + gp) * 4;
-            st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
-            if constexpr (P::SKIP_SMEM < P::NSK) {       // only configs that spill skip tensors ever pass a global destination
-                if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
+                    for (int e = 0; e < 4; ++e) o[e] = tf32_pre(o[e]);
+                }
+                const int off = g * SLABF + (S + gp) * 4;
+                st4(dst + off, mk4(o[0], o[1], o[2], o[3]));
+                if constexpr (P::SKIP_SMEM < P::NSK) {       // only configs that spill skip tensors ever pass a global destination
+                    if (gdst) st4(gdst + off, mk4(o[0], o[1], o[2], o[3]));
+                }
             }
         }
     };
     // Re-zero the S halo slots at both ends of every slab of a conv-section buffer.  Needed only where something else wrote over
     // the buffer since the halos were last zeroed (FFT / RNNFormer scratch, skip tensors reloaded from the global spill); kept out
     // of the epilogue's group loop.  Runs inside the phase of the layer that writes `dst` (halo and data slots are disjoint).
-    FE_DEV static void zero_halo(float* dst, int tid, int nslab) {
-        for (int idx = tid; idx < nslab * 2 * S; idx += NT) {
+    // It also clears the slab that pads the channels to a whole k-step (fp16 variants of configs with C1 % 16 != 0).
+    static constexpr int NSLAB = P::C1P / P::CG;         // slabs of a conv-section operand buffer
+    FE_DEV static void zero_halo(float* dst, int tid) {
+        for (int idx = tid; idx < NSLAB * 2 * S; idx += NT) {
             const int g = idx / (2 * S), r = idx % (2 * S);
             st4(dst + g * SLABF + (r < S ? r : S * F1 + r) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+        }
+        if constexpr (P::C1P > C1) {
+            static_assert(P::C1P - C1 == P::CG, "channel padding is one whole slab");
+            for (int idx = tid; idx < P::SLOTS; idx += NT) st4(dst + (NSLAB - 1) * SLABF + idx * 4, mk4(0.f, 0.f, 0.f, 0.f));
         }
     }
 
@@ -880,14 +930,20 @@ template <class P> struct Frame {
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
         x.phase(PH_LIN_PRE, [&](int tid) {
             // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
-            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, true>(x, tid, ci, [&](int l) { return enc_last + act_off(4 * (l / S), l % S, 0); }, S * 4,
-                                                          [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
-                float* yr = Y1 + rf_off(4 * (l / S), l % S, 0);
+            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, !P::H16, P::H16>(x, tid, ci,
+                [&](int l) { return enc_last + (P::H16 ? act_off16(4 * (l / S), l % S, 0) : act_off(4 * (l / S), l % S, 0)); }, S * 4,
+                [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
+                float* yr = Y1 + (P::H16 ? rf_off16(4 * (l / S), l % S, 0) : rf_off(4 * (l / S), l % S, 0));
 #pragma unroll
                 for (int j = 0; j < P::LinPreT::NO; ++j)
-                    if (o0 + j < F2)
-                        st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
+                    if (o0 + j < F2) {
+                        if constexpr (P::H16) st2(yr + (o0 + j) * S * 4, mk2(pack_h2(a[0][j], a[1][j]), pack_h2(a[2][j], a[3][j])));
+                        else st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
+                    }
             });
+            if constexpr (P::H16 && P::C1P > C1) {      // the slab that pads the channels to a whole k-step (scratch: re-zeroed every hop)
+                for (int idx = tid; idx < P::RSLOTS; idx += NT) st4(Y1 + (P::C1P / 8 - 1) * RSLABF + idx * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            }
         });
         ci += P::LinPreT::NCHUNK;
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
@@ -1391,10 +1447,7 @@ template <class P> struct Frame {
         };
         auto dump_geo1 = [&](const float* buf, int off) {
             x.phase(PH_DBG, [&](int tid) {
-                for (int idx = tid; idx < C1 * F1; idx += NT) {
-                    const float v = buf[act_off(idx / F1, 0, idx % F1)];
-                    prm.dbg[off + idx] = P::TC ? tf32_clean(v) : v;       // TC variants: these buffers hold pre-rounded MMA operands
-                }
+                for (int idx = tid; idx < C1 * F1; idx += NT) prm.dbg[off + idx] = act_get(buf, idx / F1, 0, idx % F1);
             });
         };
         auto dump_rf = [&](const float* buf, int off) {
@@ -1414,14 +1467,14 @@ template <class P> struct Frame {
                 const bool halo = i >= P::SKIP_SMEM;        // dedicated skip buffers keep the zero halos of the one-time init
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
-                        if (halo) zero_halo(dst, tid, C1 / 4);
+                        if (halo) zero_halo(dst, tid);
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
                         tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi);
                     });
                     ci += P::TEncPre::NCHUNK;
                 } else {
                     x.phase(PH_ENC, [&](int tid) {
-                        if (halo) zero_halo(dst, tid, C1 / 4);
+                        if (halo) zero_halo(dst, tid);
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
                         tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
                     });
@@ -1656,22 +1709,31 @@ template <class P> struct Frame {
             x.phase(PH_LIN_POST, [&](int tid) {
                 row_gemm_k1v<typename P::LinPostT, (C2 / 4) * S>(x, tid, ci, [&](int l) { return XR + rf_off(4 * (l / S), l % S, 0); }, S * 4,
                                                               [&](int l, int o0, const float (&a)[4][P::LinPostT::NO]) {
-                    float* zr = Zb + act_off(4 * (l / S), l % S, 0);
+                    float* zr = Zb + (P::H16 ? act_off16(4 * (l / S), l % S, 0) : act_off(4 * (l / S), l % S, 0));
 #pragma unroll
                     for (int j = 0; j < P::LinPostT::NO; ++j)
-                        if (o0 + j < F1)
-                            st4(zr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
+                        if (o0 + j < F1) {
+                            if constexpr (P::H16) st2(zr + (o0 + j) * S * 4, mk2(pack_h2(a[0][j], a[1][j]), pack_h2(a[2][j], a[3][j])));
+                            else st4(zr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
+                        }
                 });
                 // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
-                for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {
-                    const int c = C2 + idx / (S * F1), r = idx % (S * F1);
-                    Zb[act_off(c, r % S, r / S)] = 0.f;
+                if constexpr (P::H16) {
+                    for (int idx = tid; idx < ((P::C2Z - C2) / 4) * S * F1; idx += NT) {        // one 8-byte unit = 4 channels
+                        const int c = C2 + 4 * (idx / (S * F1)), r = idx % (S * F1);
+                        st2(Zb + act_off16(c, r % S, r / S), mk2(0.f, 0.f));
+                    }
+                } else {
+                    for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {
+                        const int c = C2 + idx / (S * F1), r = idx % (S * F1);
+                        Zb[act_off(c, r % S, r / S)] = 0.f;
+                    }
                 }
             });
             ci += P::LinPostT::NCHUNK;
             TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
             x.phase(PH_RF_POST, [&](int tid) {
-                zero_halo(W1, tid, C1 / 4);          // W1 was FFT / RNNFormer scratch
+                zero_halo(W1, tid);          // W1 was FFT / RNNFormer scratch
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
                 tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
             });
@@ -1713,10 +1775,10 @@ template <class P> struct Frame {
                 TcEpiAct epi{W0, b1, nullptr, true, true};
                 x.phase(PH_PWCAT, [&](int tid) {
                     // W0 was scratch (i = 0) or has just been loaded from the global skip spill, whose halo slots are never written
-                    if (i == 0 || sk >= P::SKIP_SMEM) zero_halo(W0, tid, C1 / 4);
+                    if (i == 0 || sk >= P::SKIP_SMEM) zero_halo(W0, tid);
                     const auto ax = x.make_desc(W1 + S * 4, SLABF), as = x.make_desc(skip + S * 4, SLABF);
                     tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
-                        return j < C1 / 8 ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - C1 / 8) * SLABF); }, S, epi);
+                        return j < P::C1P / P::KEC ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - P::C1P / P::KEC) * SLABF); }, S, epi);
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {

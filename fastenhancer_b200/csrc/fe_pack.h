@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "fe_half.h"
 #include "fe_plan.h"
 
 namespace fe {
@@ -98,7 +99,8 @@ template <class P> class Packer {
         std::memcpy(&x, &u, 4);
         return x;
     }
-    // tensor-core tiles, w(n, k, tap): tile (tap, k-step j) = [2][NP][4] holding W[n][8j + 4*kc2 + e][tap]
+    // tensor-core tiles, w(n, k, tap): tile (tap, k-step j) = [2][NP][4] holding W[n][8j + 4*kc2 + e][tap] (TF32), or
+    // [2][NP][8 halves] holding W[n][16j + 8*kc2 + e][tap] (fp16 layers: KE = 16)
     template <class L, class W> void tc(W w, float scale = 1.f) {
         for (int c = 0; c < L::NCHUNK; ++c) {
             int tiles = cmin(L::TPC, L::NTILE - c * L::TPC);
@@ -107,12 +109,22 @@ template <class P> class Packer {
         }
         for (int tile = 0; tile < L::NTILE; ++tile) {
             const int t = tile / L::NKS, j = tile % L::NKS;
-            for (int kc2 = 0; kc2 < 2; ++kc2)
-                for (int n = 0; n < L::NP; ++n)
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = 8 * j + 4 * kc2 + e;
-                        blob_[off_ + (long)tile * L::TILE + (kc2 * L::NP + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(scale * w(n, k, t)) : 0.f;
-                    }
+            if constexpr (L::KE == 16) {
+                uint16_t* h = reinterpret_cast<uint16_t*>(&blob_[off_ + (long)tile * L::TILE]);
+                for (int kc2 = 0; kc2 < 2; ++kc2)
+                    for (int n = 0; n < L::NP; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = 16 * j + 8 * kc2 + e;
+                            h[(kc2 * L::NP + n) * 8 + e] = f32_to_f16_bits((n < L::N && k < L::K) ? scale * w(n, k, t) : 0.f);
+                        }
+            } else {
+                for (int kc2 = 0; kc2 < 2; ++kc2)
+                    for (int n = 0; n < L::NP; ++n)
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = 8 * j + 4 * kc2 + e;
+                            blob_[off_ + (long)tile * L::TILE + (kc2 * L::NP + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(scale * w(n, k, t)) : 0.f;
+                        }
+            }
         }
         off_ += L::FLOATS;
     }
@@ -248,9 +260,9 @@ public:
         if constexpr (P::TC) {
             tc<typename P::TEncPre>(w_enc_pre, HS);
             for (int i = 0; i < C::E; ++i)
-                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.enc_w[i][(co * C1 + ci) * 3 + t]; }, HS);
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return ci < C1 ? cw.enc_w[i][(co * C1 + ci) * 3 + t] : 0.f; }, HS);
             rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
-            tc<typename P::TRfPre>([&](int co, int ci, int) { return cw.rf_pre_w[co * C1 + ci]; });
+            tc<typename P::TRfPre>([&](int co, int ci, int) { return ci < C1 ? cw.rf_pre_w[co * C1 + ci] : 0.f; });
             for (int k = 0; k < C::K; ++k) {
                 const auto& b = cw.blk[k];
                 gru<typename P::TGru>([&](int set, int c, int ci) {
@@ -265,13 +277,20 @@ public:
                 tc<typename P::TFc>([&](int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
             }
             rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
-            tc<typename P::TRfPost>([&](int co, int ci, int) { return cw.rf_post_w[co * C2 + ci]; });
+            tc<typename P::TRfPost>([&](int co, int ci, int) { return ci < C2 ? cw.rf_post_w[co * C2 + ci] : 0.f; });
             for (int i = 0; i < C::E; ++i) {
-                tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dec_w1[i][co * 2 * C1 + ci]; }, HS);
-                tc<typename P::TConv3>([&](int co, int ci, int t) { return cw.dec_w2[i][(co * C1 + ci) * 3 + t]; }, HS);
+                // cat([x, skip]) with each half padded to C1P channels: k < C1P is x channel k, k >= C1P is skip channel k - C1P
+                auto cat = [&](const float* w1, int co, int k) {
+                    const int half = k / P::C1P, c = k % P::C1P;
+                    return c < C1 ? w1[co * 2 * C1 + half * C1 + c] : 0.f;
+                };
+                tc<typename P::TPwCat>([&](int co, int k, int) { return cat(cw.dec_w1[i], co, k); }, HS);
+                tc<typename P::TConv3>([&](int co, int ci, int t) { return ci < C1 ? cw.dec_w2[i][(co * C1 + ci) * 3 + t] : 0.f; }, HS);
             }
-            tc<typename P::TPwCat>([&](int co, int ci, int) { return cw.dp_w[co * 2 * C1 + ci]; }, HS);
-            tc<typename P::TConvT>(w_convt);
+            tc<typename P::TPwCat>([&](int co, int k, int) {
+                const int half = k / P::C1P, c = k % P::C1P;
+                return c < C1 ? cw.dp_w[co * 2 * C1 + half * C1 + c] : 0.f; }, HS);
+            tc<typename P::TConvT>([&](int vo, int ci, int t) { return ci < C1 ? w_convt(vo, ci, t) : 0.f; });
         } else {
             pos<typename P::EncPre>([&](int, int co, int v, int t) { return w_enc_pre(co, v, t); });
             for (int i = 0; i < C::E; ++i)

@@ -119,13 +119,15 @@ struct RowGemm {
 // Weights stream through the ring as tiles of one (tap, 8-wide k-step):  [2][NP][4]  (K-major B operand),
 // NP = N rounded up to 16, zero rows / zero k beyond the real sizes, values pre-rounded to TF32.
 // ----------------------------------------------------------------------------------------------
-template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_, int TMEMC_ = 256>
+// KE = 16: kind::f16 -- the operands are halves, 8 per 16-byte row, so a tile [2][NP][8 halves] has the same bytes and covers K = 16.
+template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_, int TMEMC_ = 256, int KE_ = 8>
 struct TcGemm {
     static constexpr int NPOS = NPOS_, N = N_, K = K_, TAPS = TAPS_;   // TAPS doubles as "weight sets" for the GRU (6)
-    static constexpr int NP = round_up(N, 16), KP = round_up(K, 8);
-    static constexpr int NKS = KP / 8;                 // k-steps per tap
+    static constexpr int KE = KE_;                     // contraction length of one MMA
+    static constexpr int NP = round_up(N, 16), KP = round_up(K, KE);
+    static constexpr int NKS = KP / KE;                // k-steps per tap
     static constexpr int NTILE = TAPS * NKS;
-    static constexpr int TILE = NP * 8;                // floats per tile
+    static constexpr int TILE = NP * 8;                // floats per tile (32 bytes per output row)
     static_assert(TILE <= CHUNK_, "one weight tile must fit a ring chunk");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
     static constexpr int NCHUNK = cdiv(NTILE, TPC);
@@ -191,11 +193,19 @@ template <class C, int S> struct Tune {
     static constexpr int SKIP_SMEM_MAX = C::E + 1;
 };
 
-template <class C, int S_, bool TC_ = false>
+// PREC: 0 = everything on the fp32 FMA pipe; 1 = contractions on tcgen05 with TF32 operands; 2 = as 1, with the conv section's
+// activations and weights stored as fp16 (kind::f16: 11-bit significand like TF32, K = 16 per MMA, half the shared memory).
+template <class C, int S_, int PREC_ = 0>
 struct Plan {
     using Cf = C;
     static constexpr int S = S_;
-    static constexpr bool TC = TC_;                    // conv-type contractions on tcgen05 (TF32) instead of the FMA pipe
+    static constexpr int PREC = PREC_;
+    static constexpr bool TC = PREC_ != 0;             // conv-type contractions on tcgen05 instead of the FMA pipe
+    static constexpr bool H16 = PREC_ == 2;            // conv-section operands in fp16
+    static constexpr int CG = H16 ? 8 : 4;             // channels per 16-byte row of a conv-section operand buffer
+    static constexpr int KEC = H16 ? 16 : 8;           // contraction length of one conv-section MMA
+    static constexpr int C1P = H16 ? round_up(C::C1, 16) : C::C1;                 // conv channels padded to a k-step
+    static constexpr int C2Z = H16 ? round_up(C::C2, 16) : round_up(C::C2, 8);    // rf_post conv input channels padded to a k-step
     using T = Tune<C, S_>;
     static constexpr int NW = T::NW, NT = NW * 32, NTHREADS = NT + 32;
     static constexpr int CHUNK = T::CHUNK, STAGES = T::STAGES;
@@ -207,10 +217,11 @@ struct Plan {
     static constexpr int SLOTS = (C::F1 + 2) * S;
     static constexpr int SLABF = SLOTS * 4;            // floats per 4-channel slab
     static constexpr int C2P = round_up(C::C2, 8);     // rf_post conv input channels padded to a k-step
-    static constexpr int ACT = TC ? (C::C1 / 4) * SLABF : C::C1 * CP1 + 4;
-    static constexpr int SPECF = TC ? 2 * SLABF : 8 * CP1 + 4;   // compressed spectrum: 8 virtual channels (c*4+q)
-    static constexpr int ZBF = TC ? (C2P / 4) * SLABF : C::C2 * CP1;   // rf_post linear output
+    static constexpr int ACT = TC ? (C1P / CG) * SLABF : C::C1 * CP1 + 4;
+    static constexpr int SPECF = TC ? 2 * SLABF : 8 * CP1 + 4;   // compressed spectrum: 8 virtual channels (c*4+q), fp32 in every variant
+    static constexpr int ZBF = TC ? (C2Z / CG) * SLABF : C::C2 * CP1;   // rf_post linear output
     static_assert(C::C1 % 8 == 0, "C1 must be a multiple of 8");
+    static_assert(2 * SLABF <= ACT, "the fp32 mask (two 4-channel slabs) must fit an activation buffer");
     // ---- RNNFormer geometry: [C2][S][F2P] channel-major, F2P = 4*odd ----
     static constexpr int F2P = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
     static constexpr int PR = S * F2P;
@@ -220,10 +231,10 @@ struct Plan {
     static constexpr int hg_tc() {
         for (int hg = C::NH; hg > 1; hg /= 2) {
             if (C::NH % hg) continue;
-            const int act = (C::C1 / 4) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
+            const int act = (C1P / CG) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
             const int f2p = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
             const int qn = hg * 3 * round_up(C::HD, 4), qrow = ((qn / 4) % 2 == 1) ? qn : qn + 4;
-            const int need1 = cmax(S * C::F2 * qrow + xts, (C::C1 / 4) * S * C::F2 * 4) + xts;
+            const int need1 = cmax(S * C::F2 * qrow + xts, (C1P / CG) * S * C::F2 * 4) + xts;
             if (f2p < 0) return 0;
             const int rest = 2 * (C::F1 + 2) * S * 4 + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
             if (cmax(2, cdiv(need1, act)) * act + rest <= 227 * 256) return hg;
@@ -240,17 +251,17 @@ struct Plan {
     static constexpr int QROW_PAD = ((QN / 4) % 2 == 1) ? QN : QN + 4;
     // ... unless that padding alone would cost another work buffer (16 kHz B: 192 floats over)
     static constexpr int rf_need2(int qrow) {      // [QKV | ATT] or Y1T, then XT (padded channels), then XR (real channels only)
-        return cmax(S * C::F2 * qrow + (round_up(C::C2, 8) / 4) * S * C::F2 * 4, (C::C1 / 4) * S * C::F2 * 4) +
+        return cmax(S * C::F2 * qrow + (round_up(C::C2, 8) / 4) * S * C::F2 * 4, (C1P / CG) * S * C::F2 * 4) +
                (round_up(C::C2, 8) / 4) * S * C::F2 * 4 + (C::C2 / 4) * S * C::F2 * 4;
     }
-    static constexpr int act_tc() { return (C::C1 / 4) * (C::F1 + 2) * S * 4; }
+    static constexpr int act_tc() { return (C1P / CG) * (C::F1 + 2) * S * 4; }
     static constexpr int QROW = (cdiv(rf_need2(QROW_PAD), act_tc()) > cdiv(rf_need2(QN), act_tc())) ? QN : QROW_PAD;
     static constexpr int QKVS = TC ? S * C::F2 * QROW : 3 * C::HD * HG * PR;
     // ---- RNNFormer tensor-core geometry ("GeoR", TC variants): [C2P/4][RSLOTS][4], slot = f2*S + s ----
     static constexpr int RSLOTS = S * C::F2;
     static constexpr int RSLABF = RSLOTS * 4;
     static constexpr int XTS = (C2P / 4) * RSLABF;     // one RNNFormer activation in GeoR (x, h, attention output)
-    static constexpr int Y1TS = (C::C1 / 4) * RSLABF;  // rf_pre linear output in GeoR
+    static constexpr int Y1TS = (C1P / CG) * RSLABF;   // rf_pre linear output in GeoR (fp16 in the H16 variants)
     static constexpr int NPG = round_up(C::C2, 16);    // accumulator columns per GRU gate
     static_assert(RSLOTS <= 128, "RNNFormer positions exceed one M tile: lower S");
     // RNNFormer MMAs with M = 64 when the positions fit: a 64-row accumulator occupies 16 lanes in each of the four TMEM lane
@@ -332,15 +343,16 @@ struct Plan {
     static_assert(PwCat::NPASS == 1, "the concatenating 1x1 conv stores in place after a barrier: one pass only");
 
     // tensor-core versions of the conv-type layers (TC variants only)
-    using TEncPre = TcGemm<S * C::F1, C::C1, 8, 3, CHUNK>;
-    using TConv3 = TcGemm<S * C::F1, C::C1, C::C1, 3, CHUNK>;
-    using TPwCat = TcGemm<S * C::F1, C::C1, 2 * C::C1, 1, CHUNK>;
-    using TConvT = TcGemm<S * C::F1, 8, C::C1, 3, CHUNK>;
-    using TRfPost = TcGemm<S * C::F1, C::C1, C::C2, 1, CHUNK>;
+    // (K = padded input channels: the packer fills the padding with zero weights)
+    using TEncPre = TcGemm<S * C::F1, C::C1, 8, 3, CHUNK>;                            // reads the fp32 spectrum: TF32 in every variant
+    using TConv3 = TcGemm<S * C::F1, C::C1, C1P, 3, CHUNK, 256, KEC>;
+    using TPwCat = TcGemm<S * C::F1, C::C1, 2 * C1P, 1, CHUNK, 256, KEC>;
+    using TConvT = TcGemm<S * C::F1, 8, C1P, 3, CHUNK, 256, KEC>;
+    using TRfPost = TcGemm<S * C::F1, C::C1, C2Z, 1, CHUNK, 256, KEC>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
     static constexpr int TMEMC = pow2ceil(H_TMEM ? ACCW + C2P * (C::K + 1) : ACCW);
     static_assert(TMEMC <= 512, "TMEM columns");
-    using TRfPre = TcGemm<S * C::F2, C::C2, C::C1, 1, CHUNK, 512>;
+    using TRfPre = TcGemm<S * C::F2, C::C2, C1P, 1, CHUNK, 512, KEC>;
     using TGru = TcGru<S * C::F2, C::C2, CHUNK>;
     using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
     using TQkv = TcGemm<S * C::F2, QN, C::C2, 1, CHUNK, 512>;

@@ -134,8 +134,9 @@ class Engine:
 
     def __init__(self, cfg: FEConfig, canonical: np.ndarray, device: tp.Union[int, str, None] = None,
                  precision: tp.Optional[str] = None):
-        """``precision``: "tf32" (default; conv-type contractions on tcgen05 tensor cores with TF32 operands, fp32
-        accumulate) or "fp32" (everything on the fp32 FMA pipe).  ``FE_PRECISION`` in the environment sets the default."""
+        """``precision``: "tf32" (default; contractions on tcgen05 tensor cores with TF32 operands, fp32 accumulate), "fp32"
+        (everything on the fp32 FMA pipe) or "f16" (as tf32 with the conv section's operands stored as fp16; only for models
+        that have such a kernel variant).  ``FE_PRECISION`` in the environment sets the default."""
         import torch
         cfg.validate()
         if not torch.cuda.is_available():
@@ -175,13 +176,14 @@ class Engine:
         return t
 
     def set_precision(self, precision: str) -> None:
-        if precision not in ("tf32", "fp32"):
-            raise ValueError("precision must be 'tf32' or 'fp32'")
-        _check(self._lib.fe_set_precision(self._h, 1 if precision == "fp32" else 0), "fe_set_precision")
+        modes = {"tf32": 0, "fp32": 1, "f16": 2}
+        if precision not in modes:
+            raise ValueError("precision must be 'tf32', 'fp32' or 'f16'")
+        _check(self._lib.fe_set_precision(self._h, modes[precision]), "fe_set_precision")
 
     @property
     def precision(self) -> str:
-        return "fp32" if self._lib.fe_get_precision(self._h) == 1 else "tf32"
+        return {0: "tf32", 1: "fp32", 2: "f16"}[int(self._lib.fe_get_precision(self._h))]
 
     def new_state(self, n_streams: int) -> State:
         return State(self, n_streams)

@@ -93,14 +93,17 @@ int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, in
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
 
-/* Arithmetic of the channel contractions of the conv-type layers (encoder, decoder, 1x1 convs, mask head):
- *   fp32_exact = 0 (default): tcgen05 tensor cores, TF32 operands (round-to-nearest), fp32 accumulation in TMEM --
- *                what PyTorch itself does for cuDNN convolutions by default (allow_tf32); waveform error vs the
- *                fp32 reference ~7e-6 RMS, against the 1e-4 RMS bar;
- *   fp32_exact = 1: every multiply-add on the fp32 FMA pipe (~6e-8 RMS).
- * GRU, attention, FFTs, (de)compression and all state are fp32 in both modes. */
-int fe_set_precision(fe_engine* e, int fp32_exact);
-int fe_get_precision(fe_engine* e);               /* 1 = fp32 exact, 0 = TF32 tensor-core contractions */
+/* Arithmetic of the channel contractions (conv-type layers, RNNFormer linears, GRU matrix products):
+ *   mode = 0 (default): tcgen05 tensor cores, TF32 operands (round-to-nearest), fp32 accumulation in TMEM --
+ *             what PyTorch itself does for cuDNN convolutions by default (allow_tf32); waveform error vs the
+ *             fp32 reference ~7e-6 RMS, against the 1e-4 RMS bar;
+ *   mode = 1: every multiply-add on the fp32 FMA pipe (~6e-8 RMS);
+ *   mode = 2: as 0, with the activations and weights of the conv section (encoder, decoder, 1x1 convs, mask head)
+ *             stored as fp16 -- the same 11-bit significand as TF32, twice the contraction length per MMA and half the
+ *             shared memory; the RNNFormer stays TF32.  FE_ERR_UNSUPPORTED for models without such a kernel variant.
+ * Attention, FFTs, (de)compression, the residual stream and all state are fp32 in every mode. */
+int fe_set_precision(fe_engine* e, int mode);
+int fe_get_precision(fe_engine* e);               /* 0 = TF32 tensor-core contractions, 1 = fp32 exact, 2 = fp16 conv section */
 
 /* Introspection used by the host wrapper, tests and bench. */
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */

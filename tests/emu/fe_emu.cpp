@@ -45,7 +45,12 @@ template <class P> struct EmuCtx {
     Desc make_desc(const float* p, int lbo_floats) const { return Desc{p, lbo_floats}; }
     Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
     Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats}; }
-    template <bool M64 = false>
+    // element (row r, k) of a K-major / no-swizzle fp16 operand: 8 halves per 16-byte row, k-chunks of 8 LBO apart
+    static float h16(const float* p, int lbo, int r, int k) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(p + (k / 8) * lbo + r * 4);
+        return f16_bits_to_f32(h[k % 8]);
+    }
+    template <bool M64 = false, bool F16 = false>
     void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
         if (tid != 0) return;                       // one elected lane of warp 0 issues
         if (M64 && rows > 64) throw std::runtime_error("emu: M = 64 MMA with more than 64 rows");
@@ -53,8 +58,12 @@ template <class P> struct EmuCtx {
             const int lane = M64 ? 32 * (m / 16) + m % 16 : m;      // M = 64: 16 rows per TMEM lane quadrant
             for (int n = 0; n < NP; ++n) {
                 float sum = acc ? tmem[lane * 512 + col + n] : 0.f;
-                for (int k = 0; k < 8; ++k)
-                    sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
+                if (F16) {
+                    for (int k = 0; k < 16; ++k) sum += h16(a.p, a.lbo, m, k) * h16(b.p, b.lbo, n, k);
+                } else {
+                    for (int k = 0; k < 8; ++k)
+                        sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
+                }
                 tmem[lane * 512 + col + n] = sum;
             }
         }
@@ -120,7 +129,7 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
     prm.ld_in = ld_in; prm.ld_out = ld_out; prm.n_streams = n_streams; prm.n_hops = n_hops; prm.mode = mode; prm.L = L;
     prm.dbg_hop = dbg_hop; prm.compression = compression;
     try {
-#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key) && S == SV && (tc != 0) == TCV) return fe::run_variant<fe::Plan<fe::CFG, SV, TCV>>(canonical, prm);
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key) && S == SV && tc == (int)(TCV)) return fe::run_variant<fe::Plan<fe::CFG, SV, TCV>>(canonical, prm);
         FE_ALL_VARIANTS(X)
 #undef X
     } catch (const std::exception& e) {
