@@ -167,9 +167,10 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU work per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams-per-cta", type=int, default=0)
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
-                    help="tf32: conv-type contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate; parity 7e-6 RMS "
-                         "vs the 1e-4 bar); fp32: every multiply-add on the fp32 FMA pipe")
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"],
+                    help="f16 (default): contractions on tcgen05 tensor cores, conv-section operands stored as fp16 and RNNFormer operands "
+                         "as TF32 (both 11-bit significands), fp32 accumulate -- parity 7e-6 RMS vs the 1e-4 bar; tf32: TF32 operands "
+                         "everywhere (same parity); fp32: every multiply-add on the fp32 FMA pipe (6e-8 RMS)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -253,22 +254,25 @@ def main():
     e2e_value = frames_step / e2e_s
     io_bytes = B * n_hops * H * 4
 
-    # the other arithmetic variant, same workload, a few steps (reported beside the headline, not instead of it)
-    other = "fp32" if args.precision == "tf32" else "tf32"
-    eng_o = Engine(cfg, canon, dev, precision=other)
-    st_o = eng_o.new_state(B)
-    for _ in range(2):
-        eng_o.stream(st_o, x, out=y)
-    barrier()
-    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    o_steps = max(3, args.steps // 3)
-    o0.record()
-    for _ in range(o_steps):
-        eng_o.stream(st_o, x, out=y)
-    o1.record()
-    barrier()
-    other_ms = max_over_ranks(o0.elapsed_time(o1)) / o_steps
-    del eng_o, st_o
+    # the other arithmetic variants, same workload, a few steps (reported beside the headline, not instead of it)
+    other_ms = {}
+    for other in ("f16", "tf32", "fp32"):
+        if other == args.precision:
+            continue
+        eng_o = Engine(cfg, canon, dev, precision=other)
+        st_o = eng_o.new_state(B)
+        for _ in range(2):
+            eng_o.stream(st_o, x, out=y)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_steps = max(3, args.steps // 3)
+        o0.record()
+        for _ in range(o_steps):
+            eng_o.stream(st_o, x, out=y)
+        o1.record()
+        barrier()
+        other_ms[other] = max_over_ranks(o0.elapsed_time(o1)) / o_steps
+        del eng_o, st_o
 
     if rank == 0:
         peaks = measured_peaks()
@@ -302,7 +306,8 @@ def main():
         line = {
             "metric": "frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 contractions (fp32 accumulate), f32 elsewhere" if args.precision == "tf32" else "f32",
+            "dtype": {"f16": "f16 (conv section) / tf32 (RNNFormer) tensor-core operands, f32 accumulate, f32 elsewhere",
+                      "tf32": "tf32 contractions (fp32 accumulate), f32 elsewhere", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "rtf": (ms_step * 1e-3) / (n_hops * H / cfg.sample_rate),
             "config": {"workload": f"FastEnhancer_{size} {cfg.sample_rate // 1000} kHz streaming wav2wav, {B} streams/GPU x {args.seconds:g} s "
@@ -314,9 +319,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "ms_per_step": e2e_s * 1e3, "api": "fe_stream_host via Engine.stream_host (pinned host buffers)"},
             "variants": {args.precision: {"value": value, "ms_per_step": ms_step},
-                         other: {"value": frames_step / (other_ms * 1e-3), "ms_per_step": other_ms},
-                         "note": "tf32 = contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate, waveform error ~7e-6 RMS vs "
-                                 "the 1e-4 bar); fp32 = every multiply-add on the fp32 FMA pipe (~6e-8 RMS)"},
+                         **{o: {"value": frames_step / (ms * 1e-3), "ms_per_step": ms} for o, ms in other_ms.items()},
+                         "note": "f16 / tf32 = contractions on tcgen05 tensor cores (fp16 or TF32 operands: 11-bit significands, fp32 "
+                                 "accumulate; waveform error ~7e-6 RMS vs the 1e-4 bar, tests/test_gpu_parity.py); fp32 = every "
+                                 "multiply-add on the fp32 FMA pipe (~6e-8 RMS)"},
             "gpu_launches": int(launches), "clocks": clocks, "library": os.path.relpath(library_path(), ROOT),
         }
         print(json.dumps(line), flush=True)

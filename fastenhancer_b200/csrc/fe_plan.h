@@ -327,6 +327,7 @@ struct Plan {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
     // global scratch per CTA: spilled skip tensors
     static constexpr int GS_TOTAL = (NSK - SKIP_SMEM) * ACT + 4;
+    static_assert(C1P == C::C1 || SKIP_SMEM == NSK, "a channel-padding slab and spilled skip tensors do not mix (the spill never holds the zero slab)");
 
     // ---- layers (weight-stream order) ----
     using EncPre = PosGemm<S * C::F1, C::F1, C::C1, 8, 3, 4, T::CT_CONV, NW, CHUNK>;

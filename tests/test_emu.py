@@ -18,7 +18,7 @@ VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 1), ("16k_m", 1), ("48k_t", 2)
 # precision 2: as True, with the conv section's operands stored as fp16 (same 11-bit significand as TF32)
 TOL = {False: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4), True: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
        2: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
-F16_VARIANTS = [("16k_t", 2), ("16k_b", 2), ("16k_b", 1)]       # (config, S) pairs built with fp16 conv-section operands
+F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_s", 2), ("16k_m", 1), ("48k_t", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
 
 
 @pytest.mark.parametrize("name,S,tc", [(n, s, t) for n, s in VARIANTS for t in (False, True)] + [(n, s, 2) for n, s in F16_VARIANTS])
