@@ -1149,16 +1149,27 @@ template <class P> struct Frame {
             for (int hg = 0; hg < P::NQG; ++hg) {
                 x.phase(PH_QKV, [&](int tid) {
                     const auto a0 = x.make_desc(XT, RSLABF);
-                    auto epi = [&](int p, int c, const float* v, bool valid, auto wt) {
-                        constexpr int W = decltype(wt)::value;
-                        float b[W], o[W];
-                        ldg_pt<W>(aux + ab.qkv_b + hg * P::QN + c, b);
-#pragma unroll
-                        for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
-                        if (valid) store_pt<W>(QKV + p * P::QROW + c, o);
+                    // the bias is all zeros in every shipped config (attn_bias: False): the packer says so and the epilogue then
+                    // is a plain store (uniform branch, taken outside the unrolled group loop)
+                    auto run = [&](auto epi) {
+                        if constexpr (P::H_TMEM) rf_layer_ts<typename P::TQkv>(x, tid, ci, P::TM_XT, epi);
+                        else rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
                     };
-                    if constexpr (P::H_TMEM) rf_layer_ts<typename P::TQkv>(x, tid, ci, P::TM_XT, epi);
-                    else rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
+                    if (ldg(aux + A.flags) != 0.f) {
+                        run([&](int p, int c, const float* v, bool valid, auto wt) {
+                            constexpr int W = decltype(wt)::value;
+                            float b[W], o[W];
+                            ldg_pt<W>(aux + ab.qkv_b + hg * P::QN + c, b);
+#pragma unroll
+                            for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
+                            if (valid) store_pt<W>(QKV + p * P::QROW + c, o);
+                        });
+                    } else {
+                        run([&](int p, int c, const float* v, bool valid, auto wt) {
+                            constexpr int W = decltype(wt)::value;
+                            if (valid) store_pt<W>(QKV + p * P::QROW + c, v);
+                        });
+                    }
                 });
                 ci += P::TQkv::NCHUNK;
                 x.phase(PH_ATTN, [&](int tid) {

@@ -216,6 +216,12 @@ public:
             }
             cp(q.afc_b, b.afc_b, C2);
         }
+        {
+            bool any = false;
+            for (int k = 0; k < C::K; ++k)
+                for (int i = 0; i < 3 * C2; ++i) any = any || cw.blk[k].qkv_b[i] != 0.f;
+            blob_[A.flags] = any ? 1.f : 0.f;
+        }
         cp(A.rf_post_b, cw.rf_post_b, C1);
         for (int i = 0; i < C::E; ++i) { cp(A.dec1_b(i), cw.dec_b1[i], C1); cp(A.dec2_b(i), cw.dec_b2[i], C1); }
         cp(A.dp_b, cw.dp_b, C1);

@@ -389,6 +389,7 @@ struct Plan {
         int dec_b0, dec_bs, dec2_rel;          // decoder[i]: 1x1 bias at dec_b0 + i*dec_bs, k=3 bias dec2_rel after it
         int dp_b, convt_b;
         int zeros;                             // 4 zeros (stand-in for the positional embedding in blocks > 0)
+        int flags;                             // [4]: flags[0] != 0 <=> some attention qkv bias is non-zero (attn_bias: False in every shipped config)
         int table;                             // int32[2*NCHUNK_FRAME] : (float offset from blob start, floats)
         int ring;                              // start of the ring section
         int total;
@@ -420,6 +421,7 @@ struct Plan {
         a.dec2_rel = round_up(C::C1, 4); a.dec_bs = 2 * a.dec2_rel; a.dec_b0 = take(C::E * a.dec_bs);
         a.dp_b = take(C::C1); a.convt_b = take(16);
         a.zeros = take(4);
+        a.flags = take(4);
         a.table = take(2 * NCHUNK_FRAME);
         a.ring = o;
         a.total = o + (int)RING_FLOATS;

@@ -42,6 +42,7 @@ def test_streaming_and_state_round_trip(name, S, tc, canonical):
     got = np.concatenate([y1, y2], axis=1)
     assert np.sqrt(np.mean((got - want) ** 2)) < TOL[tc]["wav"]
     assert np.abs(emu.to_canonical(cfg, stn) - st).max() < TOL[tc]["state"]
+    assert np.abs(emu.to_canonical(cfg, stn) - st).max() < TOL[tc]["state"]
     off = 0
     for nm, shp in tap_schema(cfg):
         n = int(np.prod(shp))
@@ -101,3 +102,28 @@ def test_standalone_stft_istft_modes(name, S, tc, canonical):
     emu.run(cfg, S, canon, 4, stn, sp, wav, n_streams=B, n_hops=nh, ld_out=nh * H, tc=tc)
     assert np.abs(wav - acc[:, :nh * H]).max() < 1e-6
     assert np.abs(emu.to_canonical(cfg, stn)[:, N - H:2 * (N - H)] - acc[:, nh * H:nh * H + N - H]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name,S,tc", [("16k_b", 2, True), ("16k_b", 2, 2), ("16k_m", 1, True), ("16k_t", 2, False)])
+def test_nonzero_attention_bias(name, S, tc, canonical):
+    """attn_bias is False in every shipped config, so the packed qkv bias is all zeros and the tensor-core epilogue skips it;
+    a model with a bias must take the other branch and still match the oracle."""
+    from fastenhancer_b200.schema import flatten_canonical, split_canonical
+    cfg = PRESETS[name]
+    parts = split_canonical(cfg, canonical(name))
+    rs = np.random.RandomState(5)
+    for k in range(cfg.rf_blocks):
+        parts[f"blk.{k}.qkv.b"] = (1.0 * rs.standard_normal(parts[f"blk.{k}.qkv.b"].shape)).astype(np.float32)
+    canon = flatten_canonical(cfg, parts)
+    o = Oracle(cfg, canon)
+    B, nh, H = 3, 3, cfg.hop_size
+    x = synthetic_noisy(B, nh * H, cfg.sample_rate)
+    st = o.new_state(B)
+    want = o.stream(st, x)
+    base = Oracle(cfg, canonical(name)).stream(Oracle(cfg, canonical(name)).new_state(B), x)
+    assert np.abs(want - base).max() > 0           # the bias changes the output (by how much depends on the config)
+    stn = emu.to_native(cfg, o.new_state(B))
+    got = np.zeros_like(x)
+    emu.run(cfg, S, canon, emu.MODE_STREAM, stn, x, got, n_streams=B, n_hops=nh, ld_in=nh * H, ld_out=nh * H, tc=tc)
+    assert np.sqrt(np.mean((got - want) ** 2)) < TOL[tc]["wav"]
+    assert np.abs(emu.to_canonical(cfg, stn) - st).max() < TOL[tc]["state"]
