@@ -331,59 +331,8 @@ FE_DEV void row_gemm(X& x, int tid, int ci0, const float* xbase, int row_pitch, 
 
 
 // ---------------------------------------------------------------------------------------------
-// Row GEMM, one k per step (frequency-axis linear over a tensor-core-layout activation).
-// xrow(r) -> address of element k = 0 of row r; consecutive k are kstride floats apart.  epi(row, o0, values[NO]).
-// ---------------------------------------------------------------------------------------------
-template <class L, class X, class XRow, class Epi>
-FE_DEV void row_gemm_k1(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
-    constexpr int RT = L::RT, NO = L::NO;
-    const int og = tid >> 5, lane = tid & 31;
-    const bool active = og < L::NOG;
-    float acc[RT][NO];
-#pragma unroll
-    for (int i = 0; i < RT; ++i)
-#pragma unroll
-        for (int j = 0; j < NO; ++j) acc[i][j] = 0.f;
-    const float* xr[RT];
-#pragma unroll
-    for (int i = 0; i < RT; ++i) { int r = lane + 32 * i; xr[i] = xrow(r < L::NROWS ? r : 0); }
-    for (int c = 0; c < L::NCHUNK; ++c) {
-        const int rows = (c == L::NCHUNK - 1) ? L::K - c * L::KC : L::KC;
-        const float* w = x.acquire(ci0 + c, rows * L::ROW);
-        if (active) {
-            const float* wl = w + og * NO;
-#pragma unroll 4
-            for (int kk = 0; kk < rows; ++kk) {
-                const int k = c * L::KC + kk;
-                float xv[RT];
-#pragma unroll
-                for (int i = 0; i < RT; ++i) xv[i] = xr[i][k * kstride];
-#pragma unroll
-                for (int j = 0; j < NO; j += 4) {
-                    f4 wv = ld4(wl + kk * L::ROW + j);
-#pragma unroll
-                    for (int i = 0; i < RT; ++i) {
-                        acc[i][j] = fmaf(wv.x, xv[i], acc[i][j]);
-                        acc[i][j + 1] = fmaf(wv.y, xv[i], acc[i][j + 1]);
-                        acc[i][j + 2] = fmaf(wv.z, xv[i], acc[i][j + 2]);
-                        acc[i][j + 3] = fmaf(wv.w, xv[i], acc[i][j + 3]);
-                    }
-                }
-            }
-        }
-        x.release(ci0 + c);
-    }
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < RT; ++i) {
-            int r = lane + 32 * i;
-            if (r < L::NROWS) epi(r, og * NO, acc[i]);
-        }
-    }
-}
-
-
-// Same, vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
+// Row GEMM, one k per step (frequency-axis linear over a tensor-core-layout activation, where consecutive frequencies are not
+// contiguous), vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
 // layouts, where channels are the innermost index).  xrow(l) -> float4 of k = 0 for lane l (< NLANE); epi(l, o0, acc[4][NO]).
 // CLEAN: the input holds pre-rounded TF32 MMA operands (tf32_pre): mask the low bits.  XH16: the input holds halves (8 bytes = the
 // lane's 4 channels).
@@ -394,7 +343,9 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
     const int og = tid >> 5, lane = tid & 31;
     const bool active = og < L::NOG && lane < NLANE;
     static_assert(NO % 4 == 0, "outputs per warp come in float4 groups");
-    f2 acc2[4][NO / 2];          // [channel][output pair]: packed fp32 FMAs, the pair runs over outputs
+    // packed fp32 FMAs, the pair runs over two outputs (x duplicated per channel).  Storing every weight twice in the ring so that
+    // the pair can run over channels without the duplication moves was measured slower (+1.4 % per hop: more LDS).
+    f2 acc2[4][NO / 2];          // [channel][output pair]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1216,8 +1167,25 @@ template <class P> struct Frame {
 #pragma unroll
                             for (int j = 0; j < F2; ++j) { const float pj = fe_exp2(sc[j] - mx); den += pj; accum(j, pj); }
                         } else {
-                            for (int j = 0; j < F2; ++j) mx = fmaxf(mx, score(j));
-                            for (int j = 0; j < F2; ++j) { const float pj = fe_exp2(score(j) - mx); den += pj; accum(j, pj); }
+                            // more keys than registers for the scores: online softmax over chunks of 16 keys (one pass; the running
+                            // output is rescaled once per chunk) instead of computing every score twice
+                            constexpr int CH = 16;
+#pragma unroll
+                            for (int j0 = 0; j0 < F2; j0 += CH) {
+                                float sc[CH], cm = mx;
+#pragma unroll
+                                for (int jj = 0; jj < CH; ++jj)
+                                    if (j0 + jj < F2) { sc[jj] = score(j0 + jj); cm = fmaxf(cm, sc[jj]); }
+                                const float corr = fe_exp2(mx - cm);            // first chunk: exp2(-inf) = 0 on zeros
+                                const f2 cc = mk2(corr, corr);
+                                den *= corr;
+#pragma unroll
+                                for (int d2 = 0; d2 < 2 * H4; ++d2) o[d2] = mul2(o[d2], cc);
+                                mx = cm;
+#pragma unroll
+                                for (int jj = 0; jj < CH; ++jj)
+                                    if (j0 + jj < F2) { const float pj = fe_exp2(sc[jj] - mx); den += pj; accum(j0 + jj, pj); }
+                            }
                         }
                         const float inv = 1.0f / den;
 #pragma unroll

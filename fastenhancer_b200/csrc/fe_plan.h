@@ -358,6 +358,10 @@ struct Plan {
     using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
     using TQkv = TcGemm<S * C::F2, QN, C::C2, 1, CHUNK, 512>;
     using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
+    // Open issue: an experimental layout that gave these two FMA-pipe layers four ring chunks -- more than the
+    // ring has stages -- produced intermittently wrong rf_pre outputs on the GPU for 48 kHz L (the CPU emulation, which has no ring
+    // timing, was exact).  Every validated tensor-core variant keeps them within STAGES chunks; keep it that way until it is explained.
+    static_assert(!TC || (LinPreT::NCHUNK <= STAGES && LinPostT::NCHUNK <= STAGES), "frequency-axis linear: more ring chunks than stages");
 
     static constexpr int BLK_CHUNKS = Gru::NCHUNK + 2 * Fc::NCHUNK + NQG * Qkv::NCHUNK;
     static constexpr long BLK_FLOATS = (long)Gru::FLOATS + 2 * Fc::FLOATS + NQG * Qkv::FLOATS;
