@@ -938,16 +938,31 @@ template <class P> struct Frame {
                 constexpr int TM_HK0 = P::TM_H;
                 const int tm_h = TM_HK0 + k * P::C2P;                  // this block's state columns (H_TMEM)
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
-                    const int inp = tile / L::NKS, j = tile % L::NKS;
-                    const auto wn = x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4);
-                    if constexpr (P::H_TMEM) {
-                        const int a_col = (inp == 0 ? P::TM_XT : tm_h) + 8 * j;
-                        x.mma_ts(tid, a_col, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
-                        x.mma_ts(tid, a_col, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                    if constexpr (L::MERGED) {
+                        // one MMA per (input, k-step): h tiles first (k-step 0 overwrites all four accumulator blocks, zeroing NX), then x
+                        const int inp = tile < L::NKS ? 1 : 0, j = tile % L::NKS;
+                        const bool first = tile == 0;
+                        const int row0 = (inp == 1 && !first) ? NPG : 0;           // first weight row = first accumulator column
+                        const int n = first ? 4 * NPG : 3 * NPG;
+                        const auto wsub = x.desc_add(wd, row0 * 4);
+                        if constexpr (P::H_TMEM) {
+                            x.mma_ts(tid, (inp == 0 ? P::TM_XT : tm_h) + 8 * j, wsub, n, row0, !first, P::RSLOTS);
+                        } else {
+                            const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
+                            x.template mma<M64>(tid, a, wsub, n, row0, !first, P::RSLOTS);
+                        }
                     } else {
-                        const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
-                        x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
-                        x.template mma<M64>(tid, a, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                        const int inp = tile / L::NKS, j = tile % L::NKS;
+                        const auto wn = x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4);
+                        if constexpr (P::H_TMEM) {
+                            const int a_col = (inp == 0 ? P::TM_XT : tm_h) + 8 * j;
+                            x.mma_ts(tid, a_col, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                            x.mma_ts(tid, a_col, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                        } else {
+                            const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
+                            x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                            x.template mma<M64>(tid, a, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                        }
                     }
                 });
                 // gates + new state of W consecutive channels (first one c): hov = h_old, hn = h_new
@@ -997,8 +1012,8 @@ template <class P> struct Frame {
                         for (int b = 0; b < GB; ++b) {
                             const int g = half * GH + i0 + b;
                             if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) {
-                                x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
-                                x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                                x.tmem_ld4(tid, L::COL_R + 4 * g, vr[b]); x.tmem_ld4(tid, L::COL_Z + 4 * g, vz[b]);
+                                x.tmem_ld4(tid, L::COL_NX + 4 * g, vx[b]); x.tmem_ld4(tid, L::COL_NH + 4 * g, vh[b]);
                                 x.tmem_ld4(tid, tm_h + 4 * g, vo[b]);
                             }
                         }
@@ -1028,8 +1043,8 @@ template <class P> struct Frame {
                             for (int i = 0; i < GBK; ++i) {
                                 const int j = half * BH + b0 + i;
                                 if (b0 + i < BH && j < NB8) {
-                                    x.tmem_ld16(tid, 0 * NPG + 8 * j, vr[i]); x.tmem_ld16(tid, 1 * NPG + 8 * j, vz[i]);
-                                    x.tmem_ld16(tid, 2 * NPG + 8 * j, vx[i]); x.tmem_ld16(tid, 3 * NPG + 8 * j, vh[i]);
+                                    x.tmem_ld16(tid, L::COL_R + 8 * j, vr[i]); x.tmem_ld16(tid, L::COL_Z + 8 * j, vz[i]);
+                                    x.tmem_ld16(tid, L::COL_NX + 8 * j, vx[i]); x.tmem_ld16(tid, L::COL_NH + 8 * j, vh[i]);
                                 }
                             }
                             x.tmem_ld_wait();
@@ -1054,8 +1069,8 @@ template <class P> struct Frame {
                         for (int b = 0; b < GB; ++b) {
                             const int g = half * GH + i0 + b;
                             if (i0 + b < GH && (EVEN || i0 + b < GH - 1 || g < NGX)) {
-                                x.tmem_ld4(tid, 0 * NPG + 4 * g, vr[b]); x.tmem_ld4(tid, 1 * NPG + 4 * g, vz[b]);
-                                x.tmem_ld4(tid, 2 * NPG + 4 * g, vx[b]); x.tmem_ld4(tid, 3 * NPG + 4 * g, vh[b]);
+                                x.tmem_ld4(tid, L::COL_R + 4 * g, vr[b]); x.tmem_ld4(tid, L::COL_Z + 4 * g, vz[b]);
+                                x.tmem_ld4(tid, L::COL_NX + 4 * g, vx[b]); x.tmem_ld4(tid, L::COL_NH + 4 * g, vh[b]);
                             }
                         }
                         x.tmem_ld_wait();

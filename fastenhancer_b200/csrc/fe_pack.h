@@ -136,18 +136,33 @@ template <class P> class Packer {
             table_.push_back(tiles * L::TILE);
         }
         for (int tile = 0; tile < L::NTILE; ++tile) {
-            const int inp = tile / L::NKS, j = tile % L::NKS;
             float* t = &blob_[off_ + (long)tile * L::TILE];
-            for (int kc2 = 0; kc2 < 2; ++kc2)
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 8 * j + 4 * kc2 + e;
-                    for (int n = 0; n < 2 * L::NPG; ++n) {
-                        const int set = inp * 3 + n / L::NPG, c = n % L::NPG;
-                        t[(kc2 * 2 * L::NPG + n) * 4 + e] = (c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+            if constexpr (L::MERGED) {
+                // h tiles first; rows [ W_in | W_r | W_z | W_hn ], the set that does not belong to this input is zero
+                const int inp = tile < L::NKS ? 1 : 0, j = tile % L::NKS;
+                for (int kc2 = 0; kc2 < 2; ++kc2)
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 8 * j + 4 * kc2 + e;
+                        for (int n = 0; n < 4 * L::NPG; ++n) {
+                            const int blk = n / L::NPG, c = n % L::NPG;             // 0: in, 1: r, 2: z, 3: hn
+                            const int set = blk == 0 ? 2 : (blk == 1 ? inp * 3 + 0 : (blk == 2 ? inp * 3 + 1 : 5));
+                            const bool mine = (blk == 0) ? inp == 0 : (blk == 3 ? inp == 1 : true);
+                            t[(kc2 * 4 * L::NPG + n) * 4 + e] = (mine && c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+                        }
                     }
-                    for (int n = 0; n < L::NPG; ++n)
-                        t[2 * L::NPG * 8 + (kc2 * L::NPG + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(inp * 3 + 2, n, k)) : 0.f;
-                }
+            } else {
+                const int inp = tile / L::NKS, j = tile % L::NKS;
+                for (int kc2 = 0; kc2 < 2; ++kc2)
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 8 * j + 4 * kc2 + e;
+                        for (int n = 0; n < 2 * L::NPG; ++n) {
+                            const int set = inp * 3 + n / L::NPG, c = n % L::NPG;
+                            t[(kc2 * 2 * L::NPG + n) * 4 + e] = (c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+                        }
+                        for (int n = 0; n < L::NPG; ++n)
+                            t[2 * L::NPG * 8 + (kc2 * L::NPG + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(inp * 3 + 2, n, k)) : 0.f;
+                    }
+            }
         }
         off_ += L::FLOATS;
     }
