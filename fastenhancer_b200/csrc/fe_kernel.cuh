@@ -1156,14 +1156,13 @@ template <class P> struct Frame {
                         }
                         auto score = [&](int j) {
                             const float* kr = qb + j * S * P::QROW + HDP;
-                            f2 a = mk2(0.f, 0.f), b = mk2(0.f, 0.f);           // two chains: half the dependent-FMA latency per score
+                            f2 a = mk2(0.f, 0.f);
 #pragma unroll
                             for (int d4 = 0; d4 < H4; ++d4) {
                                 const f4 t = ld4(kr + 4 * d4);
-                                a = fma2(q[2 * d4], mk2(t.x, t.y), a);
-                                b = fma2(q[2 * d4 + 1], mk2(t.z, t.w), b);
+                                a = fma2(q[2 * d4 + 1], mk2(t.z, t.w), fma2(q[2 * d4], mk2(t.x, t.y), a));
                             }
-                            return (a.x + b.x) + (a.y + b.y);
+                            return a.x + a.y;
                         };
                         auto accum = [&](int j, float pj) {
                             const float* vr = qb + j * S * P::QROW + 2 * HDP;
