@@ -139,12 +139,20 @@ template <class P> struct GpuCtx {
                 ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_tf32(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // same, A operand from tensor memory: columns a_col .. a_col + 7 (one fp32 / TF32 element per column, lane = row)
+    // (F16: columns a_col .. a_col + 7 hold 16 halves, two per column, the even channel in the low half)
+    template <bool F16 = false>
     __device__ __forceinline__ void mma_ts(int /*tid*/, int a_col, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t db = ((uint64_t)b.hi << 32) | b.lo;
-        asm volatile(
-            "{\n\t" FE_MMA_ELECT
-            FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-            ::"r"(tmem + (uint32_t)col), "r"(tmem + (uint32_t)a_col), "l"(db), "r"(umma_idesc_tf32(128, np)), "r"(acc ? 1u : 0u) : "memory");
+        if constexpr (F16)
+            asm volatile(
+                "{\n\t" FE_MMA_ELECT
+                FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                ::"r"(tmem + (uint32_t)col), "r"(tmem + (uint32_t)a_col), "l"(db), "r"(umma_idesc_f16(128, np)), "r"(acc ? 1u : 0u) : "memory");
+        else
+            asm volatile(
+                "{\n\t" FE_MMA_ELECT
+                FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                ::"r"(tmem + (uint32_t)col), "r"(tmem + (uint32_t)a_col), "l"(db), "r"(umma_idesc_tf32(128, np)), "r"(acc ? 1u : 0u) : "memory");
     }
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
     // the stage, are done); the other warps never touch the stage and arrive at once
@@ -193,6 +201,12 @@ template <class P> struct GpuCtx {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
     }
+    __device__ __forceinline__ void tmem_st2(int /*tid*/, int col, const float* v) const {       // 2 consecutive columns
+        const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) << 5) << 16) + (uint32_t)col;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                     ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])) : "memory");
+    }
+    __device__ __forceinline__ void tmem_st2_row(int /*row*/, int col, const float* v) const { tmem_st2(0, col, v); }
     // same for callers that know their row instead of their thread id (the row must be the calling thread's own lane)
     __device__ __forceinline__ void tmem_st4_row(int /*row*/, int col, const float* v) const { tmem_st4(0, col, v); }
     __device__ __forceinline__ void tmem_st_wait() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

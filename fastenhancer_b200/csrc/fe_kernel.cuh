@@ -47,6 +47,7 @@ inline float fe_exp2(float x) { return exp2f(x); }
 inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
+inline void sth(float* base, int idx, float v) { reinterpret_cast<uint16_t*>(base)[idx] = f32_to_f16_bits(v); }      // store one half
 // two floats -> two fp16 in one 32-bit word (a in the low half), and back
 inline float pack_h2(float a, float b) { uint32_t u = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(b) << 16); float r; std::memcpy(&r, &u, 4); return r; }
 inline f2 unpack_h2(float p) { uint32_t u; std::memcpy(&u, &p, 4); f2 r; r.x = f16_bits_to_f32((uint16_t)(u & 0xffffu)); r.y = f16_bits_to_f32((uint16_t)(u >> 16)); return r; }
@@ -83,6 +84,11 @@ FE_DEV float tf32_pre(float x) { return tf32_rna(x); }
 FE_DEV float tf32_clean(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // two floats -> two fp16 in one 32-bit word (a in the low half, round to nearest even: one cvt.rn.f16x2.f32), and back
 FE_DEV float pack_h2(float a, float b) { uint32_t u; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a)); return __uint_as_float(u); }
+FE_DEV void sth(float* base, int idx, float v) {       // store one half (round to nearest even)
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    reinterpret_cast<unsigned short*>(base)[idx] = h;
+}
 FE_DEV f2 unpack_h2(float p) {
     f2 r;
     asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(__float_as_uint(p)));
@@ -542,7 +548,7 @@ FE_DEV void rf_layer_ts(X& x, int tid, int ci, int a_col0, Epi epi) {
     tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
 #pragma unroll
         for (int ns = 0; ns < L::NSPLIT; ++ns)
-            x.mma_ts(tid, a_col0 + 8 * tile, x.desc_add(wd, ns * L::NPS * 4), L::NPS, ns * L::NPS, tile > 0, L::NPOS);
+            x.template mma_ts<L::KE == 16>(tid, a_col0 + 8 * tile, x.desc_add(wd, ns * L::NPS * 4), L::NPS, ns * L::NPS, tile > 0, L::NPOS);
     });
     // every lane runs the epilogue (it may store operands to tensor memory); rows past the end come with valid = false
     tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
@@ -696,7 +702,7 @@ template <class P> struct Frame {
                     const int g = half * GHP + i;
                     if (g < NGP) {       // warp-uniform
                         const float z[4] = {0.f, 0.f, 0.f, 0.f};
-                        x.tmem_st4(tid, P::TM_XT + 4 * g, z);      // K-padding columns of x stay zero; the others are rewritten every hop
+                        if constexpr (!P::RF16) x.tmem_st4(tid, P::TM_XT + 4 * g, z);      // K-padding columns of x stay zero; the others are rewritten every hop
                         for (int k = 0; k < C::K; ++k) {
                             float v[4];
 #pragma unroll
@@ -705,6 +711,22 @@ template <class P> struct Frame {
                                 v[e] = (live && c < C2) ? prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f] : 0.f;
                             }
                             x.tmem_st4(tid, P::TM_H + k * P::C2P + 4 * g, v);
+                            if constexpr (P::RF16) {         // the MMA operand copy: packed halves, two channels per column
+                                const float h2[2] = {pack_h2(v[0], v[1]), pack_h2(v[2], v[3])};
+                                x.tmem_st2(tid, P::TM_H16 + k * (P::C2H / 2) + 2 * g, h2);
+                            }
+                        }
+                    }
+                }
+                if constexpr (P::RF16) {     // zero x and the K-padding groups of the packed state (channels C2 .. C2H - 1)
+                    constexpr int NG16 = P::C2H / 4, GH16 = (NG16 + 1) / 2;
+                    for (int i = 0; i < GH16; ++i) {
+                        const int g = half * GH16 + i;
+                        if (g < NG16) {
+                            const float z2[2] = {0.f, 0.f};
+                            x.tmem_st2(tid, P::TM_XT + 2 * g, z2);
+                            if (g >= NGP)
+                                for (int k = 0; k < C::K; ++k) x.tmem_st2(tid, P::TM_H16 + k * (P::C2H / 2) + 2 * g, z2);
                         }
                     }
                 }
@@ -864,9 +886,14 @@ template <class P> struct Frame {
             if (valid) store_pt<W>(XR + off, o);
             if constexpr (P::H_TMEM) {           // the MMAs read x from tensor memory: this thread's lane, columns TM_XT + c ..
                 // (warp-collective: also executed, with garbage, by the lanes past the last position)
-                static_assert(W == 4, "TMEM operand stores are 4 columns wide");
-                const float r[4] = {tf32_pre(o[0]), tf32_pre(o[1]), tf32_pre(o[2]), tf32_pre(o[3])};
-                x.tmem_st4_row(p, P::TM_XT + c, r);          // p is the calling thread's own lane
+                static_assert(W == 4, "TMEM operand stores cover 4 channels");
+                if constexpr (P::RF16) {
+                    const float r[2] = {pack_h2(o[0], o[1]), pack_h2(o[2], o[3])};
+                    x.tmem_st2_row(p, P::TM_XT + c / 2, r);       // p is the calling thread's own lane
+                } else {
+                    const float r[4] = {tf32_pre(o[0]), tf32_pre(o[1]), tf32_pre(o[2]), tf32_pre(o[3])};
+                    x.tmem_st4_row(p, P::TM_XT + c, r);
+                }
             } else {
                 if constexpr (P::XT_COPY) {
                     float r[W];
@@ -936,7 +963,8 @@ template <class P> struct Frame {
                 // x tiles then h tiles; each tile = one MMA into R|Z (x and h accumulate together) + one into NX or NH
                 const auto dx = x.make_desc(XT, RSLABF), dh = x.make_desc(H, RSLABF);
                 constexpr int TM_HK0 = P::TM_H;
-                const int tm_h = TM_HK0 + k * P::C2P;                  // this block's state columns (H_TMEM)
+                const int tm_h = TM_HK0 + k * P::C2P;                  // this block's fp32 state columns (H_TMEM)
+                const int tm_ha = P::RF16 ? P::TM_H16 + k * (P::C2H / 2) : tm_h;      // ... and the columns the MMAs read
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
                     if constexpr (L::MERGED) {
                         // one MMA per (input, k-step): h tiles first (k-step 0 overwrites all four accumulator blocks, zeroing NX), then x
@@ -946,7 +974,7 @@ template <class P> struct Frame {
                         const int n = first ? 4 * NPG : 3 * NPG;
                         const auto wsub = x.desc_add(wd, row0 * 4);
                         if constexpr (P::H_TMEM) {
-                            x.mma_ts(tid, (inp == 0 ? P::TM_XT : tm_h) + 8 * j, wsub, n, row0, !first, P::RSLOTS);
+                            x.template mma_ts<P::RF16>(tid, (inp == 0 ? P::TM_XT : tm_ha) + 8 * j, wsub, n, row0, !first, P::RSLOTS);
                         } else {
                             const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
                             x.template mma<M64>(tid, a, wsub, n, row0, !first, P::RSLOTS);
@@ -955,9 +983,9 @@ template <class P> struct Frame {
                         const int inp = tile / L::NKS, j = tile % L::NKS;
                         const auto wn = x.desc_set_lbo(x.desc_add(wd, 2 * NPG * 8), NPG * 4);
                         if constexpr (P::H_TMEM) {
-                            const int a_col = (inp == 0 ? P::TM_XT : tm_h) + 8 * j;
-                            x.mma_ts(tid, a_col, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
-                            x.mma_ts(tid, a_col, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
+                            const int a_col = (inp == 0 ? P::TM_XT : tm_ha) + 8 * j;
+                            x.template mma_ts<P::RF16>(tid, a_col, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
+                            x.template mma_ts<P::RF16>(tid, a_col, wn, NPG, (2 + inp) * NPG, j > 0, P::RSLOTS);
                         } else {
                             const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
                             x.template mma<M64>(tid, a, wd, 2 * NPG, 0, inp == 1 || j > 0, P::RSLOTS);
@@ -1025,6 +1053,10 @@ template <class P> struct Frame {
                                 float hn[4];
                                 gru_gates(4 * g, vr[b], vz[b], vx[b], vh[b], vo[b], hn, WTag<4>{});
                                 x.tmem_st4(tid, tm_h + 4 * g, hn);
+                                if constexpr (P::RF16) {
+                                    const float h2[2] = {pack_h2(hn[0], hn[1]), pack_h2(hn[2], hn[3])};
+                                    x.tmem_st2(tid, tm_ha + 2 * g, h2);
+                                }
                             }
                         }
                     }
@@ -1102,7 +1134,7 @@ template <class P> struct Frame {
                     store_x(p, c, o, valid, wt, WTag<0>{});
                 };
                 if constexpr (P::H_TMEM) {
-                    rf_layer_ts<typename P::TFc>(x, tid, ci, P::TM_H + k * P::C2P, epi);
+                    rf_layer_ts<typename P::TFc>(x, tid, ci, P::RF16 ? P::TM_H16 + k * (P::C2H / 2) : P::TM_H + k * P::C2P, epi);
                     x.tmem_st_wait();
                 } else {
                     rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
@@ -1141,9 +1173,17 @@ template <class P> struct Frame {
                 x.phase(PH_ATTN, [&](int tid) {
                     constexpr int HDP = P::HDP, H4 = P::HDP / 4;
                     const float scale = 1.4426950408889634f / sqrtf((float)HD);     // log2(e) folded in: softmax via ex2
-                    if (hg == 0)
-                        for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)       // K-padding channels of the attn_fc operand
-                            ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
+                    // attn_fc operand: TF32 in GeoR, or (RF16) halves [C2H / 8][RSLOTS][8]; its K-padding channels are re-zeroed per block
+                    auto att_off16 = [&](int c, int s, int f) { return (c >> 3) * (RSLABF * 2) + (f * S + s) * 8 + (c & 7); };
+                    if (hg == 0) {
+                        if constexpr (P::RF16) {
+                            for (int idx = tid; idx < (P::C2H - C2) * P::RSLOTS; idx += NT)
+                                sth(ATT, att_off16(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S), 0.f);
+                        } else {
+                            for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)
+                                ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
+                        }
+                    }
                     for (int it = tid; it < S * P::HG * F2; it += NT) {
                         const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
                         const float* qb = QKV + s * P::QROW + hh * 3 * HDP;        // row of position (f = 0, s); next f: S * QROW further
@@ -1204,8 +1244,11 @@ template <class P> struct Frame {
                         }
                         const float inv = 1.0f / den;
 #pragma unroll
-                        for (int d = 0; d < HD; ++d)
-                            ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_pre(((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv);
+                        for (int d = 0; d < HD; ++d) {
+                            const float ov = ((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv;
+                            if constexpr (P::RF16) sth(ATT, att_off16((hg * P::HG + hh) * HD + d, s, i), ov);
+                            else ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_pre(ov);
+                        }
                     }
                 });
             }

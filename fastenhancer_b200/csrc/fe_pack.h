@@ -135,32 +135,38 @@ template <class P> class Packer {
             table_.push_back((int)(off_ + (long)c * L::TPC * L::TILE));
             table_.push_back(tiles * L::TILE);
         }
+        constexpr int KH = L::KE / 2;           // k's per 16-byte row chunk: 4 floats (TF32) or 8 halves
         for (int tile = 0; tile < L::NTILE; ++tile) {
             float* t = &blob_[off_ + (long)tile * L::TILE];
+            // element (k-chunk kc2, row n of a part with `rows` rows starting `base` floats into the tile, e) <- value
+            auto put = [&](int base, int rows, int kc2, int n, int e, float v) {
+                if constexpr (L::KE == 16) reinterpret_cast<uint16_t*>(t + base)[(kc2 * rows + n) * 8 + e] = f32_to_f16_bits(v);
+                else t[base + (kc2 * rows + n) * 4 + e] = tf32_rna(v);
+            };
             if constexpr (L::MERGED) {
                 // h tiles first; rows [ W_in | W_r | W_z | W_hn ], the set that does not belong to this input is zero
                 const int inp = tile < L::NKS ? 1 : 0, j = tile % L::NKS;
                 for (int kc2 = 0; kc2 < 2; ++kc2)
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = 8 * j + 4 * kc2 + e;
+                    for (int e = 0; e < KH; ++e) {
+                        const int k = L::KE * j + KH * kc2 + e;
                         for (int n = 0; n < 4 * L::NPG; ++n) {
                             const int blk = n / L::NPG, c = n % L::NPG;             // 0: in, 1: r, 2: z, 3: hn
                             const int set = blk == 0 ? 2 : (blk == 1 ? inp * 3 + 0 : (blk == 2 ? inp * 3 + 1 : 5));
                             const bool mine = (blk == 0) ? inp == 0 : (blk == 3 ? inp == 1 : true);
-                            t[(kc2 * 4 * L::NPG + n) * 4 + e] = (mine && c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+                            put(0, 4 * L::NPG, kc2, n, e, (mine && c < L::N && k < L::K) ? w(set, c, k) : 0.f);
                         }
                     }
             } else {
                 const int inp = tile / L::NKS, j = tile % L::NKS;
                 for (int kc2 = 0; kc2 < 2; ++kc2)
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = 8 * j + 4 * kc2 + e;
+                    for (int e = 0; e < KH; ++e) {
+                        const int k = L::KE * j + KH * kc2 + e;
                         for (int n = 0; n < 2 * L::NPG; ++n) {
                             const int set = inp * 3 + n / L::NPG, c = n % L::NPG;
-                            t[(kc2 * 2 * L::NPG + n) * 4 + e] = (c < L::N && k < L::K) ? tf32_rna(w(set, c, k)) : 0.f;
+                            put(0, 2 * L::NPG, kc2, n, e, (c < L::N && k < L::K) ? w(set, c, k) : 0.f);
                         }
                         for (int n = 0; n < L::NPG; ++n)
-                            t[2 * L::NPG * 8 + (kc2 * L::NPG + n) * 4 + e] = (n < L::N && k < L::K) ? tf32_rna(w(inp * 3 + 2, n, k)) : 0.f;
+                            put(2 * L::NPG * 8, L::NPG, kc2, n, e, (n < L::N && k < L::K) ? w(inp * 3 + 2, n, k) : 0.f);
                     }
             }
         }
@@ -289,13 +295,14 @@ public:
                 gru<typename P::TGru>([&](int set, int c, int ci) {
                     return set < 3 ? b.w_ih[(set * C2 + c) * C2 + ci] : b.w_hh[((set - 3) * C2 + c) * C2 + ci];
                 });
-                tc<typename P::TFc>([&](int co, int ci, int) { return b.fc_w[co * C2 + ci]; });
+                // (ci >= C2: channels that pad the contraction to a whole fp16 k-step)
+                tc<typename P::TFc>([&](int co, int ci, int) { return ci < C2 ? b.fc_w[co * C2 + ci] : 0.f; });
                 for (int g = 0; g < P::NQG; ++g)
                     tc<typename P::TQkv>([&](int co, int ci, int) {      // co = (head-in-round * 3 + q|k|v) * HDP + d, zero for d >= HD
                         const int d = co % P::HDP, hw = co / P::HDP;
-                        return d < C::HD ? b.qkv_w[((g * P::HG * 3 + hw) * C::HD + d) * C2 + ci] : 0.f;
+                        return (d < C::HD && ci < C2) ? b.qkv_w[((g * P::HG * 3 + hw) * C::HD + d) * C2 + ci] : 0.f;
                     });
-                tc<typename P::TFc>([&](int co, int ci, int) { return b.afc_w[co * C2 + ci]; });
+                tc<typename P::TFc>([&](int co, int ci, int) { return ci < C2 ? b.afc_w[co * C2 + ci] : 0.f; });
             }
             rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
             tc<typename P::TRfPost>([&](int co, int ci, int) { return ci < C2 ? cw.rf_post_w[co * C2 + ci] : 0.f; });

@@ -147,10 +147,11 @@ struct TcGemm {
 // (rows NPG ..), and the x tiles accumulate onto columns 0 .. 3 NPG - 1 (rows 0 ..).  Half the MMAs of the split form.
 // Split form (M, L): per (input x | h, k-step) one tile [ R|Z part: [2][2 NPG][4] | N part: [2][NPG][4] ], i.e. two MMAs: N = 2 NPG into
 // the R|Z accumulator columns (x and h accumulate together) and N = NPG into NX or NH; x tiles first; columns [ R | Z | NX | NH ].
-template <int NPOS_, int C2_, int CHUNK_>
+// KE = 16: fp16 operands (x and h as packed halves), tiles [2][rows][8 halves].
+template <int NPOS_, int C2_, int CHUNK_, int KE_ = 8>
 struct TcGru {
-    static constexpr int NPOS = NPOS_, N = C2_, K = C2_;
-    static constexpr int NPG = round_up(C2_, 16), KP = round_up(C2_, 8), NKS = KP / 8;
+    static constexpr int NPOS = NPOS_, N = C2_, K = C2_, KE = KE_;
+    static constexpr int NPG = round_up(C2_, 16), KP = round_up(C2_, KE_), NKS = KP / KE_;
 #ifndef FE_GRU_MERGE
 #define FE_GRU_MERGE 1
 #endif
@@ -321,9 +322,20 @@ struct Plan {
 #ifndef FE_HTMEM
 #define FE_HTMEM 1
 #endif
-    static constexpr bool H_TMEM = TC && FE_HTMEM && !RM64 && (ACCW + C2P * (C::K + 1) <= 512);
-    static constexpr int TM_XT = ACCW;                 // C2P columns: TF32-rounded x
-    static constexpr int TM_H = ACCW + C2P;            // K x C2P columns: GRU state, resident for the whole launch
+#ifndef FE_RF16
+#define FE_RF16 1
+#endif
+    // fp16 variants with TMEM operands run the RNNFormer MMAs on fp16 too (RF16): x and h as packed halves (two channels per column,
+    // K = 16 per MMA), beside an fp32 master of h for the state update.
+    static constexpr int C2H = round_up(C::C2, 16);
+    static constexpr int TM_COLS_TF32 = ACCW + C2P * (C::K + 1);
+    static constexpr int TM_COLS_F16 = ACCW + C2H / 2 + C::K * (C2P + C2H / 2);
+    static constexpr bool H_TMEM = TC && FE_HTMEM && !RM64 && ((H16 && FE_RF16) ? TM_COLS_F16 : TM_COLS_TF32) <= 512;
+    static constexpr bool RF16 = H16 && FE_RF16 && H_TMEM;
+    static constexpr int TM_XT = ACCW;                 // x as MMA operand: C2P columns (TF32) or C2H / 2 columns (packed halves)
+    static constexpr int TM_H = ACCW + (RF16 ? C2H / 2 : C2P);     // K x C2P columns: fp32 GRU state, resident for the whole launch
+    static constexpr int TM_H16 = TM_H + C::K * C2P;   // RF16: K x C2H / 2 columns: the state as packed halves (MMA operand)
+    static constexpr int TM_COLS = RF16 ? TM_COLS_F16 : TM_COLS_TF32;
     // TC variants keep the GRU state of all K blocks on chip across hops: in TMEM, else in shared memory when it fits
     static constexpr bool H_RES = TC && (H_TMEM || SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
     static constexpr int SM_SK = 0;
@@ -364,12 +376,13 @@ struct Plan {
     using TConvT = TcGemm<S * C::F1, 8, C1P, 3, CHUNK, 256, KEC>;
     using TRfPost = TcGemm<S * C::F1, C::C1, C2Z, 1, CHUNK, 256, KEC>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
-    static constexpr int TMEMC = pow2ceil(H_TMEM ? ACCW + C2P * (C::K + 1) : ACCW);
+    static constexpr int TMEMC = pow2ceil(H_TMEM ? TM_COLS : ACCW);
     static_assert(TMEMC <= 512, "TMEM columns");
     using TRfPre = TcGemm<S * C::F2, C::C2, C1P, 1, CHUNK, 512, KEC>;
-    using TGru = TcGru<S * C::F2, C::C2, CHUNK>;
-    using TFc = TcGemm<S * C::F2, C::C2, C::C2, 1, CHUNK, 512>;
-    using TQkv = TcGemm<S * C::F2, QN, C::C2, 1, CHUNK, 512>;
+    static constexpr int KER = RF16 ? 16 : 8;          // contraction length of one RNNFormer MMA
+    using TGru = TcGru<S * C::F2, C::C2, CHUNK, KER>;
+    using TFc = TcGemm<S * C::F2, C::C2, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER>;
+    using TQkv = TcGemm<S * C::F2, QN, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER>;
     using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
     // (An experimental variant of these two layers that stored every weight twice gave intermittently wrong rf_pre outputs on the GPU
     // for 48 kHz L while the CPU emulation was exact.  It was slower anyway and is gone; the ring itself is not the cause -- capping

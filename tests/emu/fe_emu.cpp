@@ -68,15 +68,28 @@ template <class P> struct EmuCtx {
             }
         }
     }
+    template <bool F16 = false>
     void mma_ts(int tid, int a_col, Desc b, int NP, int col, bool acc, int rows) {      // A operand from tensor memory
         if (tid != 0) return;
         for (int m = 0; m < rows; ++m)
             for (int n = 0; n < NP; ++n) {
                 float sum = acc ? tmem[m * 512 + col + n] : 0.f;
-                for (int k = 0; k < 8; ++k) sum += tf32_trunc(tmem[m * 512 + a_col + k]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
+                if (F16) {          // 16 halves in 8 columns, the even k in the low half
+                    for (int k = 0; k < 16; ++k) {
+                        uint32_t u; std::memcpy(&u, &tmem[m * 512 + a_col + k / 2], 4);
+                        sum += f16_bits_to_f32((uint16_t)((k & 1) ? (u >> 16) : (u & 0xffffu))) * h16(b.p, b.lbo, n, k);
+                    }
+                } else {
+                    for (int k = 0; k < 8; ++k) sum += tf32_trunc(tmem[m * 512 + a_col + k]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
+                }
                 tmem[m * 512 + col + n] = sum;
             }
     }
+    void tmem_st2(int tid, int col, const float* v) {
+        const int row = (((tid >> 5) & 3) << 5) + (tid & 31);
+        tmem[row * 512 + col] = v[0]; tmem[row * 512 + col + 1] = v[1];
+    }
+    void tmem_st2_row(int row, int col, const float* v) { tmem[row * 512 + col] = v[0]; tmem[row * 512 + col + 1] = v[1]; }
     void tmem_st4(int tid, int col, const float* v) {
         const int row = (((tid >> 5) & 3) << 5) + (tid & 31);
         for (int e = 0; e < 4; ++e) tmem[row * 512 + col + e] = v[e];
