@@ -793,51 +793,48 @@ template <class P> struct Frame {
         }
     }
 
-    // complex M-point Stockham FFT over S streams (radix-4 stages, one radix-2 stage when log2 M is odd);
-    // returns the buffer holding the result.  tw[t] = exp(-2 pi i t / M), t < M/2.
+    // complex M-point Stockham FFT over S streams (radix-4 stages, one radix-2 stage when log2 M is odd).
+    // tw[t] = exp(-2 pi i t / M), t < M/2.  One stage, executed by threads t of nt:
+    static constexpr int NR4 = LOG2M / 2, NSTAGE = NR4 + (LOG2M & 1);
+    FE_DEV static void fft_stage(const float* tw, const float* src, float* dst, int si, bool inverse, int t, int nt) {
+        const float sgn = inverse ? -1.f : 1.f;
+        if (si < NR4) {
+            const int l = 2 * si, st = 1 << l, n1 = M >> (l + 2);       // sub-transform length of this stage: 4 * n1, stride st
+            for (int j = t; j < S * (M / 4); j += nt) {
+                const int s = j / (M / 4), jj = j % (M / 4);
+                const int p = jj >> l, q = jj & (st - 1);
+                const float* sp = src + s * N + 2 * (q + st * p);
+                float* dp = dst + s * N + 2 * (q + st * 4 * p);
+                const f2 a = ld2(sp), b = ld2(sp + 2 * st * n1), c = ld2(sp + 4 * st * n1), d = ld2(sp + 6 * st * n1);
+                f2 w1 = ldg2(tw + 2 * (p * st));
+                w1.y *= sgn;
+                const f2 w2 = mk2(w1.x * w1.x - w1.y * w1.y, 2.f * w1.x * w1.y);
+                const f2 w3 = mk2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
+                const float apcx = a.x + c.x, apcy = a.y + c.y, amcx = a.x - c.x, amcy = a.y - c.y;
+                const float bpdx = b.x + d.x, bpdy = b.y + d.y;
+                const float jx = -sgn * (b.y - d.y), jy = sgn * (b.x - d.x);          // (+-) i (b - d)
+                const float t1x = amcx - jx, t1y = amcy - jy, t2x = apcx - bpdx, t2y = apcy - bpdy, t3x = amcx + jx, t3y = amcy + jy;
+                st2(dp, mk2(apcx + bpdx, apcy + bpdy));
+                st2(dp + 2 * st, mk2(t1x * w1.x - t1y * w1.y, t1x * w1.y + t1y * w1.x));
+                st2(dp + 4 * st, mk2(t2x * w2.x - t2y * w2.y, t2x * w2.y + t2y * w2.x));
+                st2(dp + 6 * st, mk2(t3x * w3.x - t3y * w3.y, t3x * w3.y + t3y * w3.x));
+            }
+        } else {                                 // last stage of an odd log2 M: plain butterflies, twiddle 1
+            const int st = 1 << (2 * NR4);
+            for (int j = t; j < S * (M / 2); j += nt) {
+                const int s = j / (M / 2), q = j % (M / 2);
+                const f2 a = ld2(src + s * N + 2 * q), b = ld2(src + s * N + 2 * (q + st));
+                st2(dst + s * N + 2 * q, mk2(a.x + b.x, a.y + b.y));
+                st2(dst + s * N + 2 * (q + st), mk2(a.x - b.x, a.y - b.y));
+            }
+        }
+    }
+    // the whole transform, one barrier-separated phase per stage; returns the buffer holding the result
     template <class X> FE_DEV static float* fft(X& x, float* src, float* dst, bool inverse) {
         const int ph = inverse ? PH_IFFT : PH_FFT;
         const float* tw = x.blob + P::make_aux().tw;
-        const float sgn = inverse ? -1.f : 1.f;
-        int n = M, lst = 0;                      // n: length of the sub-transforms of this stage, stride = 1 << lst
-        while (n >= 4) {
-            const int n1 = n >> 2, l = lst;
-            x.phase(ph, [&](int tid) {
-                const int st = 1 << l;
-                for (int j = tid; j < S * (M / 4); j += NT) {
-                    const int s = j / (M / 4), jj = j % (M / 4);
-                    const int p = jj >> l, q = jj & (st - 1);
-                    const float* sp = src + s * N + 2 * (q + st * p);
-                    float* dp = dst + s * N + 2 * (q + st * 4 * p);
-                    const f2 a = ld2(sp), b = ld2(sp + 2 * st * n1), c = ld2(sp + 4 * st * n1), d = ld2(sp + 6 * st * n1);
-                    f2 w1 = ldg2(tw + 2 * (p * st));
-                    w1.y *= sgn;
-                    const f2 w2 = mk2(w1.x * w1.x - w1.y * w1.y, 2.f * w1.x * w1.y);
-                    const f2 w3 = mk2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
-                    const float apcx = a.x + c.x, apcy = a.y + c.y, amcx = a.x - c.x, amcy = a.y - c.y;
-                    const float bpdx = b.x + d.x, bpdy = b.y + d.y;
-                    const float jx = -sgn * (b.y - d.y), jy = sgn * (b.x - d.x);          // (+-) i (b - d)
-                    const float t1x = amcx - jx, t1y = amcy - jy, t2x = apcx - bpdx, t2y = apcy - bpdy, t3x = amcx + jx, t3y = amcy + jy;
-                    st2(dp, mk2(apcx + bpdx, apcy + bpdy));
-                    st2(dp + 2 * st, mk2(t1x * w1.x - t1y * w1.y, t1x * w1.y + t1y * w1.x));
-                    st2(dp + 4 * st, mk2(t2x * w2.x - t2y * w2.y, t2x * w2.y + t2y * w2.x));
-                    st2(dp + 6 * st, mk2(t3x * w3.x - t3y * w3.y, t3x * w3.y + t3y * w3.x));
-                }
-            });
-            float* t = src; src = dst; dst = t;
-            n >>= 2; lst += 2;
-        }
-        if (n == 2) {                            // last stage of an odd log2 M: plain butterflies, twiddle 1
-            const int l = lst;
-            x.phase(ph, [&](int tid) {
-                const int st = 1 << l;
-                for (int j = tid; j < S * (M / 2); j += NT) {
-                    const int s = j / (M / 2), q = j % (M / 2);
-                    const f2 a = ld2(src + s * N + 2 * q), b = ld2(src + s * N + 2 * (q + st));
-                    st2(dst + s * N + 2 * q, mk2(a.x + b.x, a.y + b.y));
-                    st2(dst + s * N + 2 * (q + st), mk2(a.x - b.x, a.y - b.y));
-                }
-            });
+        for (int si = 0; si < NSTAGE; ++si) {
+            x.phase(ph, [&](int tid) { fft_stage(tw, src, dst, si, inverse, tid, NT); });
             float* t = src; src = dst; dst = t;
         }
         return src;
@@ -1307,9 +1304,7 @@ template <class P> struct Frame {
         float* W0 = sm + P::SM_W;
         float* W1 = W0 + ACT;
         float* SPEC = sm + P::SM_SPEC;
-        float* OLA = sm + P::SM_OLA;
         const int mode = prm.mode;
-        const int T = prm.n_hops;
         if (!have_z) x.phase(PH_PRETW, [&](int tid) {      // standalone inverse: bins in W0 -> Z in W1
             for (int idx = tid; idx < S * M; idx += NT) {
                 const int s = idx / M, k = idx % M;
@@ -1324,10 +1319,20 @@ template <class P> struct Frame {
             }
         });
         const float* Y = have_z ? fft(x, W0, W1, true) : fft(x, W1, W0, true);
+        x.phase(PH_OLA, [&](int tid) { ola_items(x, Y, hop, tid, NT); });
+    }
+    // synthesis window, overlap-add, emit one hop: items of threads t of nt.  Y = output of the inverse FFT.
+    template <class X> FE_DEV static void ola_items(X& x, const float* Y, int hop, int t, int nt) {
+        const KParams& prm = x.prm;
+        constexpr auto A = P::make_aux();
+        const float* aux = x.blob;
+        float* OLA = x.sm + P::SM_OLA;
+        const int mode = prm.mode;
+        const int T = prm.n_hops;
         const int base = (hop * H) & NMASK;
-        x.phase(PH_OLA, [&](int tid) {
+        {
             const float invM = 1.0f / (float)M;
-            for (int idx = tid; idx < S * N; idx += NT) {
+            for (int idx = t; idx < S * N; idx += nt) {
                 const int s = idx / N, i = idx % N, gs = x.s0 + s;
                 const int slot = s * N + ((base + i) & NMASK);
                 float y = Y[s * N + i] * invM;
@@ -1346,12 +1351,12 @@ template <class P> struct Frame {
                         long t1 = npad / H;
                         if (t1 > T - 1) t1 = T - 1;
                         float env = 0.f;
-                        for (long t = t0; t <= t1; ++t) env += ldg(aux + A.window_sq + (int)(npad - t * H));
+                        for (long tt = t0; tt <= t1; ++tt) env += ldg(aux + A.window_sq + (int)(npad - tt * H));
                         prm.out[(size_t)gs * H * (T - 1) + n] = v / env;
                     }
                 }
             }
-        });
+        }
     }
 
     template <class X> FE_DEV static void frame(X& x, int hop) {
@@ -1371,6 +1376,63 @@ template <class P> struct Frame {
         const float comp_e = prm.compression - 1.0f, decomp_e = 1.0f / prm.compression - 1.0f;
         int ci = 0;    // chunk index within the frame
 
+        // With the overlapped schedule (P::FB_OVL, streaming launches) the front end of hop t + 1 runs beside the back end of hop t,
+        // so only hop 0 runs its front end here.
+        const bool ovl = P::FB_OVL && mode == MODE_STREAM;
+        // analysis window of frame hop_ -> wdst (items of threads t of nt); the new samples are also filed into the input ring
+        auto window_items = [&](int hop_, float* wdst, int t, int nt) {
+            const int wpos = (hop_ * H) & NMASK;
+                for (int idx = t; idx < S * M; idx += nt) {
+                    int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
+                    float a, b;
+                    if (mode != MODE_OFFLINE) {
+                        // frame = [N-H cached samples | the new hop]: the new samples come straight from global memory
+                        // and are filed into the ring on the way (slots disjoint from the cached part)
+                        if (n2 < C::CL) {
+                            a = TIN[s * N + ((wpos + H + n2) & NMASK)];
+                            b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
+                        } else {
+                            const int j = n2 - C::CL;
+                            a = b = 0.f;
+                            if (gs < prm.n_streams) {
+                                const float* src_hop = prm.in + (size_t)gs * prm.ld_in + (size_t)hop_ * H + j;
+                                a = src_hop[0]; b = src_hop[1];
+                            }
+                            TIN[s * N + ((wpos + j) & NMASK)] = a;
+                            TIN[s * N + ((wpos + j + 1) & NMASK)] = b;
+                        }
+                    } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
+                        a = b = 0.f;
+                        if (gs < prm.n_streams) {
+                            const float* w = prm.in + (size_t)gs * prm.L;
+                            long j0 = (long)hop_ * H + n2 - N / 2, j1 = j0 + 1;
+                            if (j0 < 0) j0 = -j0;
+                            if (j0 >= prm.L) j0 = 2L * (prm.L - 1) - j0;
+                            if (j1 < 0) j1 = -j1;
+                            if (j1 >= prm.L) j1 = 2L * (prm.L - 1) - j1;
+                            a = w[j0]; b = w[j1];
+                        }
+                    }
+                    st2(wdst + s * N + n2, mk2(a * ldg(aux + A.window + n2), b * ldg(aux + A.window + n2 + 1)));
+                }
+        };
+        // unpack the packed real FFT Z, drop Nyquist, compress, scatter to the 8 virtual channels of SPEC
+        auto compress_items = [&](const float* Z, int t, int nt) {
+            for (int idx = t; idx < S * M; idx += nt) {
+                int s = idx / M, k = idx % M;
+                f2 zk = ld2(Z + s * N + 2 * k), zm = ld2(Z + s * N + 2 * ((M - k) & (M - 1)));
+                float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+                float dr = 0.5f * (zk.x - zm.x), di = 0.5f * (zk.y + zm.y);
+                float orr = di, oi = -dr;                                // O = -i * D
+                f2 w = ldg2(aux + A.twn + 2 * k);
+                float re = er + (w.x * orr - w.y * oi), im = ei + (w.x * oi + w.y * orr);
+                float mag = sqrtf(re * re + im * im);
+                mag = mag < 1.0e-5f ? 1.0e-5f : mag;
+                float g = powf(mag, comp_e);
+                SPEC[spec_off(0, s, k)] = re * g;
+                SPEC[spec_off(1, s, k)] = im * g;
+            }
+        };
         // ================= front end =================
         if (mode == MODE_ISTFT) {
             // standalone inverse: spectrum [B][NB][T][2] -> W0 (bins 0..M-1) + real part of the Nyquist bin in SPEC[s]
@@ -1385,43 +1447,8 @@ template <class P> struct Frame {
             });
             back_end(x, hop, false);
             return;
-        } else if (mode != MODE_SPEC) {
-            const int wpos = (hop * H) & NMASK;
-            x.phase(PH_WINDOW, [&](int tid) {
-                for (int idx = tid; idx < S * M; idx += NT) {
-                    int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
-                    float a, b;
-                    if (mode != MODE_OFFLINE) {
-                        // frame = [N-H cached samples | the new hop]: the new samples come straight from global memory
-                        // and are filed into the ring on the way (slots disjoint from the cached part)
-                        if (n2 < C::CL) {
-                            a = TIN[s * N + ((wpos + H + n2) & NMASK)];
-                            b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
-                        } else {
-                            const int j = n2 - C::CL;
-                            a = b = 0.f;
-                            if (gs < prm.n_streams) {
-                                const float* src_hop = prm.in + (size_t)gs * prm.ld_in + (size_t)hop * H + j;
-                                a = src_hop[0]; b = src_hop[1];
-                            }
-                            TIN[s * N + ((wpos + j) & NMASK)] = a;
-                            TIN[s * N + ((wpos + j + 1) & NMASK)] = b;
-                        }
-                    } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
-                        a = b = 0.f;
-                        if (gs < prm.n_streams) {
-                            const float* w = prm.in + (size_t)gs * prm.L;
-                            long j0 = (long)hop * H + n2 - N / 2, j1 = j0 + 1;
-                            if (j0 < 0) j0 = -j0;
-                            if (j0 >= prm.L) j0 = 2L * (prm.L - 1) - j0;
-                            if (j1 < 0) j1 = -j1;
-                            if (j1 >= prm.L) j1 = 2L * (prm.L - 1) - j1;
-                            a = w[j0]; b = w[j1];
-                        }
-                    }
-                    st2(W0 + s * N + n2, mk2(a * ldg(aux + A.window + n2), b * ldg(aux + A.window + n2 + 1)));
-                }
-            });
+        } else if (mode != MODE_SPEC && !(ovl && hop > 0)) {
+            x.phase(PH_WINDOW, [&](int tid) { window_items(hop, W0, tid, NT); });
             float* Z = fft(x, W0, W1, false);
             if (mode == MODE_STFT) {      // ONNXSTFT.forward: all n_fft/2 + 1 bins, no compression
                 x.phase(PH_COMPRESS, [&](int tid) {
@@ -1440,24 +1467,8 @@ template <class P> struct Frame {
                 });
                 return;
             }
-            // unpack the packed real FFT, drop Nyquist, compress, scatter to the 8 virtual channels
-            x.phase(PH_COMPRESS, [&](int tid) {
-                for (int idx = tid; idx < S * M; idx += NT) {
-                    int s = idx / M, k = idx % M;
-                    f2 zk = ld2(Z + s * N + 2 * k), zm = ld2(Z + s * N + 2 * ((M - k) & (M - 1)));
-                    float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
-                    float dr = 0.5f * (zk.x - zm.x), di = 0.5f * (zk.y + zm.y);
-                    float orr = di, oi = -dr;                                // O = -i * D
-                    f2 w = ldg2(aux + A.twn + 2 * k);
-                    float re = er + (w.x * orr - w.y * oi), im = ei + (w.x * oi + w.y * orr);
-                    float mag = sqrtf(re * re + im * im);
-                    mag = mag < 1.0e-5f ? 1.0e-5f : mag;
-                    float g = powf(mag, comp_e);
-                    SPEC[spec_off(0, s, k)] = re * g;
-                    SPEC[spec_off(1, s, k)] = im * g;
-                }
-            });
-        } else {
+            x.phase(PH_COMPRESS, [&](int tid) { compress_items(Z, tid, NT); });
+        } else if (mode == MODE_SPEC) {
             x.phase(PH_COMPRESS, [&](int tid) {
                 for (int idx = tid; idx < S * M; idx += NT) {
                     int s = idx / M, k = idx % M, gs = x.s0 + s;
@@ -1903,8 +1914,8 @@ template <class P> struct Frame {
         }
         // One thread per bin pair (k, M - k): both masked / decompressed bins, then Z[k] = E + i O and Z[M-k] = conj(E) + i conj(O)
         // with E = (Y[k] + conj(Y[M-k])) / 2, O = (Y[k] - conj(Y[M-k])) / 2 * exp(+2 pi i k / N); imag of DC ignored, Nyquist = 0.
-        x.phase(PH_MASK, [&](int tid) {
-            for (int idx = tid; idx < S * (M / 2); idx += NT) {          // item 0 takes the two unpaired bins 0 and M/2
+        auto mask_items = [&](int t, int nt) {
+            for (int idx = t; idx < S * (M / 2); idx += nt) {          // item 0 takes the two unpaired bins 0 and M/2
                 const int s = idx / (M / 2), k = idx % (M / 2), gs = x.s0 + s;
                 auto bin = [&](int kk) {
                     const int o0 = spec_off(0, s, kk), o1 = spec_off(1, s, kk);
@@ -1930,7 +1941,34 @@ template <class P> struct Frame {
                     st2(W0 + s * N + 2 * (M - k), mk2(er + oi, orr - ei));
                 }
             }
-        });
+        };
+        if (ovl) {
+            // back end of this hop on threads 0 .. NT/2 - 1, front end of the next hop (if any) on the others, stage by stage
+            constexpr int NH = NT / 2;
+            const bool next = hop + 1 < prm.n_hops;
+            const float* tw = aux + A.tw;
+            float* F0 = sm + P::SM_FF;
+            float* F1 = F0 + S * N;
+            x.phase(PH_MASK, [&](int tid) {
+                if (tid < NH) mask_items(tid, NH);
+                else if (next) window_items(hop + 1, F0, tid - NH, NH);
+            });
+            float *bs = W0, *bd = W1, *fs = F0, *fd = F1;
+            for (int si = 0; si < NSTAGE; ++si) {
+                x.phase(PH_IFFT, [&](int tid) {
+                    if (tid < NH) fft_stage(tw, bs, bd, si, true, tid, NH);
+                    else if (next) fft_stage(tw, fs, fd, si, false, tid - NH, NH);
+                });
+                float* tb = bs; bs = bd; bd = tb;
+                float* tf = fs; fs = fd; fd = tf;
+            }
+            x.phase(PH_OLA, [&](int tid) {
+                if (tid < NH) ola_items(x, bs, hop, tid, NH);
+                else if (next) compress_items(fs, tid - NH, NH);
+            });
+            return;
+        }
+        x.phase(PH_MASK, [&](int tid) { mask_items(tid, NT); });
         back_end(x, hop, true);
     }
 };

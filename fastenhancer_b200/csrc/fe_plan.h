@@ -344,7 +344,15 @@ struct Plan {
     static constexpr int SM_SPEC = SM_W + AB;
     static constexpr int SM_TIN = SM_SPEC + SPECF;             // last N input samples per stream (circular)
     static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
-    static constexpr int SM_RING = SM_OLA + S * C::N_FFT;
+    // Streaming launches overlap the back end of hop t (mask, inverse FFT, overlap-add: half of the threads) with the front end of
+    // hop t + 1 (window, FFT, compression: the other half) when two more FFT buffers fit: half as many barrier-separated phases.
+#ifndef FE_FB_OVL
+#define FE_FB_OVL 1
+#endif
+    static constexpr int SM_FF = SM_OLA + S * C::N_FFT;        // [2][S][N] front-end FFT buffers of the overlapped schedule
+    static constexpr bool FB_OVL = TC && FE_FB_OVL &&
+        (SM_FF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES + 4) * 4 <= 227 * 1024;
+    static constexpr int SM_RING = SM_FF + (FB_OVL ? 2 * S * C::N_FFT : 0);
     static constexpr int SM_BAR = SM_RING + STAGES * CHUNK;    // 2*STAGES mbarriers (8 bytes each)
     static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES + 4;   // + accumulator-ready mbarrier, TMEM base slot
     static_assert(SM_RING % 4 == 0 && SM_BAR % 2 == 0, "alignment");
