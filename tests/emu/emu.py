@@ -15,7 +15,7 @@ MODE_STREAM, MODE_SPEC, MODE_OFFLINE = 0, 1, 2
 
 
 def build(force=False):
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("fe_plan.h", "fe_pack.h", "fe_kernel.cuh", "fe_configs.h")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("fe_plan.h", "fe_pack.h", "fe_kernel.cuh", "fe_configs.h", "fe_half.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
