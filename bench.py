@@ -306,12 +306,14 @@ def main():
         line = {
             "metric": "frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"f16": "f16 (conv section) / tf32 (RNNFormer) tensor-core operands, f32 accumulate, f32 elsewhere",
+            "dtype": {"f16": ("f16 tensor-core operands (conv section and RNNFormer, fp32 master of the GRU state), f32 accumulate, f32 elsewhere"
+                              if size in ("T", "B", "S") else
+                              "f16 (conv section) / tf32 (RNNFormer) tensor-core operands, f32 accumulate, f32 elsewhere"),
                       "tf32": "tf32 contractions (fp32 accumulate), f32 elsewhere", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "rtf": (ms_step * 1e-3) / (n_hops * H / cfg.sample_rate),
             "config": {"workload": f"FastEnhancer_{size} {cfg.sample_rate // 1000} kHz streaming wav2wav, {B} streams/GPU x {args.seconds:g} s "
-                                   f"({n_hops} hops of {H}), fp32, random-init folded weights", "preset": args.preset,
+                                   f"({n_hops} hops of {H}), fp32 audio in/out and weights, random-init folded weights", "preset": args.preset,
                        "streams_per_gpu": B, "hops_per_step": n_hops, "frames_per_step": frames_step,
                        "streams_per_cta": eng.streams_per_cta(B), "precision": args.precision, "parallelism": f"streams sharded x{world}, no collective",
                        "l2": "per-step input+output 2x%.0f MB exceed the 126 MB L2" % (io_bytes / 1e6)},

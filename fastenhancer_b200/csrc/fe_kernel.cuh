@@ -1123,7 +1123,11 @@ template <class P> struct Frame {
                     constexpr int W = decltype(wt)::value;
                     float xo[W], b[W], pv[W], o[W];
                     const int pc = valid ? p : 0;
-                    load_pt<W>(XR + (c >> 2) * RSLABF + pc * 4 + (c & 3), xo);
+                    // lanes past the last position keep zeros: reading position 0 here would race with its owner's store_x
+                    if (valid) load_pt<W>(XR + (c >> 2) * RSLABF + pc * 4 + (c & 3), xo);
+                    else
+#pragma unroll
+                        for (int e = 0; e < W; ++e) xo[e] = 0.f;
                     ldg_pt<W>(aux + ab.fc_b + c, b);
                     ldg_pt<W>(pe + (pc / S) * pfs + c * pcs, pv);
 #pragma unroll
@@ -1255,7 +1259,10 @@ template <class P> struct Frame {
                                                [&](int p, int c, const float* v, bool valid, auto wt) {
                     constexpr int W = decltype(wt)::value;
                     float xo[W], b[W], o[W];
-                    load_pt<W>(XR + (c >> 2) * RSLABF + (valid ? p : 0) * 4 + (c & 3), xo);
+                    if (valid) load_pt<W>(XR + (c >> 2) * RSLABF + p * 4 + (c & 3), xo);
+                    else
+#pragma unroll
+                        for (int e = 0; e < W; ++e) xo[e] = 0.f;
                     ldg_pt<W>(aux + ab.afc_b + c, b);
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
