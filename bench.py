@@ -168,8 +168,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams-per-cta", type=int, default=0)
     ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"],
-                    help="f16 (default): contractions on tcgen05 tensor cores, conv-section operands stored as fp16 and RNNFormer operands "
-                         "as TF32 (both 11-bit significands), fp32 accumulate -- parity 7e-6 RMS vs the 1e-4 bar; tf32: TF32 operands "
+                    help="f16 (default): contractions on tcgen05 tensor cores, conv-section operands stored as fp16, RNNFormer operands "
+                         "as fp16 (T/B/S) or TF32 (M/L) (both 11-bit significands), fp32 accumulate -- parity 7e-6 RMS vs the 1e-4 bar; tf32: TF32 operands "
                          "everywhere (same parity); fp32: every multiply-add on the fp32 FMA pipe (6e-8 RMS)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

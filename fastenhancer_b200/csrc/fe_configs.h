@@ -16,6 +16,13 @@ using C48B = Cfg< 1024, 512,  48, 2, 36, 36, 3>;
 using C48S = Cfg< 1024, 512,  64, 3, 48, 48, 3>;
 using C48M = Cfg< 1024, 320,  96, 3, 72, 72, 4>;
 using C48L = Cfg< 1024, 200, 128, 4, 96, 96, 5>;
+
+// Per-(config, S) tuning overrides (measured on B200, profiles/r01/alt_ring_{tf32,f16}.txt).
+// T, 2 streams per CTA: its layers are short, so the weight producer runs further ahead with a third ring stage
+// (21.9 -> 20.8 us/hop f16, 23.1 -> 21.7 tf32); B loses 3 % with the same change and keeps two.
+#if FE_STAGES == 2
+template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAGES = 3; };
+#endif
 }  // namespace fe
 
 // X(config id, Cfg type, S, PREC)   PREC: false / 0 = everything on the fp32 FMA pipe; true / 1 = contractions on tcgen05 (TF32);

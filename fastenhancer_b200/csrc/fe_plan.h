@@ -187,7 +187,7 @@ struct RowGemmK1 {
 // ----------------------------------------------------------------------------------------------
 // Per-(config, S) tuning.  Primary template = generic heuristics; specialise to override.
 // ----------------------------------------------------------------------------------------------
-template <class C, int S> struct Tune {
+template <class C, int S> struct TuneBase {
     static constexpr int NW = 8;                      // consumer warps (one more warp streams weights)
 #ifndef FE_CHUNK
 #define FE_CHUNK 8192
@@ -206,6 +206,7 @@ template <class C, int S> struct Tune {
     // the Plan lowers it to what fits in 227 KB
     static constexpr int SKIP_SMEM_MAX = C::E + 1;
 };
+template <class C, int S> struct Tune : TuneBase<C, S> {};
 
 // PREC: 0 = everything on the fp32 FMA pipe; 1 = contractions on tcgen05 with TF32 operands; 2 = as 1, with the conv section's
 // activations and weights stored as fp16 (kind::f16: 11-bit significand like TF32, K = 16 per MMA, half the shared memory).

@@ -100,7 +100,9 @@ int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, flo
  *   mode = 1: every multiply-add on the fp32 FMA pipe (~6e-8 RMS);
  *   mode = 2: as 0, with the activations and weights of the conv section (encoder, decoder, 1x1 convs, mask head)
  *             stored as fp16 -- the same 11-bit significand as TF32, twice the contraction length per MMA and half the
- *             shared memory; the RNNFormer stays TF32.  FE_ERR_UNSUPPORTED for models without such a kernel variant.
+ *             shared memory; where the RNNFormer operands live in tensor memory (T/B/S) they are fp16 as well, beside an
+ *             fp32 master of the GRU state; the RNNFormer of M/L stays TF32.  Same waveform error as mode 0.
+ *             FE_ERR_UNSUPPORTED for models without such a kernel variant.
  * Attention, FFTs, (de)compression, the residual stream and all state are fp32 in every mode. */
 int fe_set_precision(fe_engine* e, int mode);
 int fe_get_precision(fe_engine* e);               /* 0 = TF32 tensor-core contractions, 1 = fp32 exact, 2 = fp16 conv section */

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/${1:-alt}
 mkdir -p $OUT
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for lib in default $(ls fastenhancer_b200/_alt/*.so 2>/dev/null); do
   if [ $lib = default ]; then unset FE_LIB; else export FE_LIB=$PWD/$lib; fi
   for a in "16k_b 256 200" "16k_t 256 200" "16k_b 4096 40"; do
