@@ -18,9 +18,11 @@ using C48M = Cfg< 1024, 320,  96, 3, 72, 72, 4>;
 using C48L = Cfg< 1024, 200, 128, 4, 96, 96, 5>;
 
 // Per-(config, S) tuning overrides (measured on B200, profiles/r01/alt_ring_{tf32,f16}.txt).
-// T, 2 streams per CTA: its layers are short, so the weight producer runs further ahead with a third ring stage
-// (21.9 -> 20.8 us/hop f16, 23.1 -> 21.7 tf32); B loses 3 % with the same change and keeps two.
+// T, 1 or 2 streams per CTA: its layers are short, so the weight producer runs further ahead with a third ring stage
+// (2 streams: 21.9 -> 20.8 us/hop f16, 23.1 -> 21.7 tf32; 1 stream: 19.0 -> 18.6 f16; 4 streams: 209.4 -> 210.5, kept at two);
+// B loses 3 % with the same change and keeps two.
 #if FE_STAGES == 2
+template <> struct Tune<C16T, 1> : TuneBase<C16T, 1> { static constexpr int STAGES = 3; };
 template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAGES = 3; };
 #endif
 }  // namespace fe
