@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -51,20 +52,37 @@ size_t weight_count(const fe_config& c) {
     return n;
 }
 
-// h [K][F2][C2] (reference cache layout) <-> h [K][C2][F2] (engine layout); caches copied through.
-__global__ void state_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_streams, int cl2,
-                                       int K, int F2, int C2, int to_native)
+// Per-stream rows [cache_stft | cache_istft | h_0 [F2][C2] | ... | h_{K-1}] (the export layout of the C ABI) <-> the planes the
+// kernels keep: cache_stft [B][CL] | cache_istft [B][CL] | h_k [B][F2][C2], k < K.  Element order inside every piece is the same.
+__global__ void state_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_streams, int cl, int K, int hf,
+                                       int to_planes)
 {
-    const int sf = cl2 + K * F2 * C2;
+    const int sf = 2 * cl + K * hf;
     const long total = (long)n_streams * sf;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int s = (int)(i / sf), r = (int)(i % sf);
-        if (r < cl2) { dst[i] = src[i]; continue; }
-        const int q = r - cl2, k = q / (F2 * C2), e = q % (F2 * C2);
-        int f, c;
-        if (to_native) { c = e / F2; f = e % F2; dst[i] = src[(long)s * sf + cl2 + k * F2 * C2 + f * C2 + c]; }
-        else { f = e / C2; c = e % C2; dst[i] = src[(long)s * sf + cl2 + k * F2 * C2 + c * F2 + f]; }
+        const int s = (int)(i / sf), r = (int)(i % sf);            // i indexes the per-stream-row form
+        long pl;
+        if (r < 2 * cl) pl = ((long)(r / cl) * n_streams + s) * cl + r % cl;
+        else { const int q = r - 2 * cl; pl = 2L * n_streams * cl + ((long)(q / hf) * n_streams + s) * hf + q % hf; }
+        if (to_planes) dst[pl] = src[i];
+        else dst[i] = src[pl];
     }
+}
+
+// fp32 FMA-pipe peak microbenchmark (roofline denominator of the fp32 FMA-pipe kernel family): 16 independent FFMA chains per thread
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b)
+{
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;          // never true: keeps the chains alive
 }
 
 struct Variant {
@@ -81,25 +99,25 @@ struct fe_engine {
     std::vector<float> canonical;
     std::vector<Variant> variants;       // same shape, ascending S
     int forced_s = 0;
-    int tc = 1;                          // 1: conv-type contractions on tcgen05 (TF32 operands, fp32 accumulate); 0: all fp32 FMA
+    int tc = 1;                          // kernel family (Plan::PREC): 0 fp32 FMA pipe, 1 TF32, 2 fp16, 3 bf16 conv section, 4 split fp16 (fp32-accurate)
     long long* prof = nullptr;           // optional per-phase cycle counters (device)
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     std::mutex mu;
-    // offline-mode scratch state (zeroed before every call)
-    float* off_state = nullptr; size_t off_state_floats = 0;
-    float* off_scratch = nullptr; size_t off_scratch_floats = 0;
-    // pipelined host path
-    cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
-    float* h_in[2] = {nullptr, nullptr}; float* h_out[2] = {nullptr, nullptr}; size_t h_floats = 0;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
+// Everything a call mutates lives in the state (or on the call's stream), never in the engine: two states of one engine can be
+// driven from two host threads / CUDA streams concurrently.
 struct fe_state {
     fe_engine* e;
     int n_streams;
-    float* data = nullptr;      // [n_streams][STATE] engine layout
+    float* data = nullptr;      // planes (fe_state_planes): cache_stft | cache_istft | h_0 .. h_{K-1}
+    bool owns_data = true;      // false: the caller's buffer (fe_state_create_on)
     float* scratch = nullptr;   // spill scratch for the largest grid (S = 1)
     size_t scratch_floats = 0;
+    // pipelined host path (fe_stream_host): staging buffers, streams and events of THIS state, created by fe_state_reserve_host
+    cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+    float* h_in[2] = {nullptr, nullptr}; float* h_out[2] = {nullptr, nullptr}; size_t h_floats = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_call = nullptr;
 };
 
 namespace {
@@ -157,7 +175,7 @@ int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st) {
     prm.prof = e->prof;
     const int grid = (prm.n_streams + v.ops.S - 1) / v.ops.S;
     FE_CUDA(v.ops.launch(prm, grid, st));
-    ++e->launches;
+    e->launches.fetch_add(1, std::memory_order_relaxed);
     return FE_OK;
 }
 
@@ -199,11 +217,15 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     e->canonical.assign(canonical, canonical + n_floats);
     e->variants = std::move(vs);
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
+    // Default arithmetic = results identical to the fp32 reference: the fp32-accurate tensor-core family where the model has one
+    // (split-fp16 operands, three MMAs per product), else the fp32 FMA pipe.  The faster reduced-precision families are opt-in.
+    e->tc = 0;
+    for (const Variant& v : e->variants) if (v.ops.tc == 4) e->tc = 4;
     if (const char* env = std::getenv("FE_PRECISION")) {
-        e->tc = std::strcmp(env, "fp32") == 0 ? 0 : 1;
-        if (std::strcmp(env, "f16") == 0) {      // only if this model has fp16 variants
-            for (const Variant& v : e->variants) if (v.ops.tc == 2) e->tc = 2;
-        }
+        const char* names[] = {"fp32", "tf32", "f16", "bf16", "fp32x3"};
+        for (int want = 0; want < 5; ++want)
+            if (std::strcmp(env, names[want]) == 0)
+                for (const Variant& v : e->variants) if (v.ops.tc == want) e->tc = want;     // only if this model has such variants
     }
     *out = e;
     return FE_OK;
@@ -213,42 +235,52 @@ FE_API void fe_destroy(fe_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (Variant& v : e->variants) if (v.blob) cudaFree(v.blob);
-    if (e->off_state) cudaFree(e->off_state);
-    if (e->off_scratch) cudaFree(e->off_scratch);
-    for (int i = 0; i < 2; ++i) {
-        if (e->h_in[i]) cudaFree(e->h_in[i]);
-        if (e->h_out[i]) cudaFree(e->h_out[i]);
-        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
-        if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
-        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
-    }
-    if (e->s_copy_in) cudaStreamDestroy(e->s_copy_in);
-    if (e->s_compute) cudaStreamDestroy(e->s_compute);
-    if (e->s_copy_out) cudaStreamDestroy(e->s_copy_out);
     delete e;
 }
 
-FE_API int fe_state_create(fe_engine* e, int n_streams, fe_state** out) {
+static int state_create(fe_engine* e, int n_streams, float* external, fe_state** out) {
     if (!e || !out || n_streams <= 0) return fail(FE_ERR_ARG, "fe_state_create: bad argument");
     *out = nullptr;
     FE_CUDA(cudaSetDevice(e->device));
     fe_state* s = new fe_state();
     s->e = e; s->n_streams = n_streams;
     const size_t sf = fe_state_floats(&e->cfg);
-    cudaError_t ce = cudaMalloc(&s->data, (size_t)n_streams * sf * sizeof(float));
-    if (ce == cudaSuccess) ce = cudaMemset(s->data, 0, (size_t)n_streams * sf * sizeof(float));
+    cudaError_t ce = cudaSuccess;
+    if (external) { s->data = external; s->owns_data = false; }
+    else {
+        ce = cudaMalloc(&s->data, (size_t)n_streams * sf * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMemset(s->data, 0, (size_t)n_streams * sf * sizeof(float));
+    }
     s->scratch_floats = scratch_need(e, n_streams);
     if (ce == cudaSuccess) ce = cudaMalloc(&s->scratch, s->scratch_floats * sizeof(float));
     if (ce != cudaSuccess) { fe_state_destroy(s); return cuda_fail(ce, "fe_state_create"); }
     *out = s;
     return FE_OK;
 }
+FE_API int fe_state_create(fe_engine* e, int n_streams, fe_state** out) { return state_create(e, n_streams, nullptr, out); }
+FE_API int fe_state_create_on(fe_engine* e, int n_streams, float* planes_device, fe_state** out) {
+    if (!planes_device) return fail(FE_ERR_ARG, "fe_state_create_on: null buffer");
+    if ((reinterpret_cast<size_t>(planes_device) & 15) != 0) return fail(FE_ERR_ARG, "fe_state_create_on: buffer must be 16-byte aligned");
+    return state_create(e, n_streams, planes_device, out);
+}
+FE_API float* fe_state_planes(fe_state* s) { return s ? s->data : nullptr; }
 
 FE_API void fe_state_destroy(fe_state* s) {
     if (!s) return;
     cudaSetDevice(s->e->device);
-    if (s->data) cudaFree(s->data);
+    if (s->data && s->owns_data) cudaFree(s->data);
     if (s->scratch) cudaFree(s->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (s->h_in[i]) cudaFree(s->h_in[i]);
+        if (s->h_out[i]) cudaFree(s->h_out[i]);
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+        if (s->ev_k[i]) cudaEventDestroy(s->ev_k[i]);
+        if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+    }
+    if (s->ev_call) cudaEventDestroy(s->ev_call);
+    if (s->s_copy_in) cudaStreamDestroy(s->s_copy_in);
+    if (s->s_compute) cudaStreamDestroy(s->s_compute);
+    if (s->s_copy_out) cudaStreamDestroy(s->s_copy_out);
     delete s;
 }
 
@@ -258,11 +290,11 @@ FE_API int fe_state_reset(fe_state* s, void* cuda_stream) {
     return FE_OK;
 }
 
-static int state_xpose(fe_state* s, const float* src, float* dst, int to_native, void* cuda_stream) {
+static int state_xpose(fe_state* s, const float* src, float* dst, int to_planes, void* cuda_stream) {
     const fe_config& c = s->e->cfg;
     const long total = (long)s->n_streams * (long)fe_state_floats(&c);
     const int blocks = (int)std::min<long>((total + 255) / 256, 4096);
-    state_transpose_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(src, dst, s->n_streams, 2 * (c.n_fft - c.hop), c.n_blocks, c.f2, c.c2, to_native);
+    state_transpose_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(src, dst, s->n_streams, c.n_fft - c.hop, c.n_blocks, c.f2 * c.c2, to_planes);
     FE_CUDA(cudaGetLastError());
     return FE_OK;
 }
@@ -327,30 +359,66 @@ FE_API int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_o
     if (L <= e->cfg.n_fft / 2) return fail(FE_ERR_ARG, "fe_offline: input shorter than n_fft/2 + 1 samples (reflect padding needs more)");
     FE_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // zero state + spill scratch of THIS call, allocated and freed in stream order: concurrent calls on other streams share nothing
     const size_t sf = fe_state_floats(&e->cfg), need = (size_t)B * sf, sneed = scratch_need(e, B);
-    if (e->off_state_floats < need) {
-        if (e->off_state) FE_CUDA(cudaFree(e->off_state));
-        e->off_state = nullptr; e->off_state_floats = 0;
-        FE_CUDA(cudaMalloc(&e->off_state, need * sizeof(float)));
-        e->off_state_floats = need;
+    float *off_state = nullptr, *off_scratch = nullptr;
+    FE_CUDA(cudaMallocAsync(&off_state, need * sizeof(float), st));
+    cudaError_t ce = cudaMallocAsync(&off_scratch, sneed * sizeof(float), st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(off_state, 0, need * sizeof(float), st);
+    int rc = FE_OK;
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "fe_offline: scratch allocation");
+    else {
+        fe::KParams prm{};
+        prm.state = off_state; prm.in = wav; prm.out = wav_out; prm.spec_out = spec_out;
+        prm.n_streams = B; prm.n_hops = 1 + L / e->cfg.hop; prm.L = L; prm.mode = fe::MODE_OFFLINE; prm.dbg_hop = -1;
+        rc = launch(e, prm, off_scratch, st);
     }
-    if (e->off_scratch_floats < sneed) {
-        if (e->off_scratch) FE_CUDA(cudaFree(e->off_scratch));
-        e->off_scratch = nullptr; e->off_scratch_floats = 0;
-        FE_CUDA(cudaMalloc(&e->off_scratch, sneed * sizeof(float)));
-        e->off_scratch_floats = sneed;
+    cudaFreeAsync(off_state, st);
+    if (off_scratch) cudaFreeAsync(off_scratch, st);
+    return rc;
+}
+
+// Staging buffers / streams / events of the pipelined host path for pieces of up to `hops_per_chunk` hops: call it once up front to
+// keep every allocation out of fe_stream_host (which otherwise reserves on first use / when a larger piece is asked for).
+FE_API int fe_state_reserve_host(fe_state* s, int hops_per_chunk) {
+    if (!s || hops_per_chunk <= 0) return fail(FE_ERR_ARG, "fe_state_reserve_host: bad argument");
+    FE_CUDA(cudaSetDevice(s->e->device));
+    if (!s->s_compute) {
+        FE_CUDA(cudaStreamCreateWithFlags(&s->s_copy_in, cudaStreamNonBlocking));
+        FE_CUDA(cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
+        FE_CUDA(cudaStreamCreateWithFlags(&s->s_copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FE_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+            FE_CUDA(cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming));
+            FE_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        }
+        FE_CUDA(cudaEventCreateWithFlags(&s->ev_call, cudaEventDisableTiming));
     }
-    FE_CUDA(cudaMemsetAsync(e->off_state, 0, need * sizeof(float), st));
-    fe::KParams prm{};
-    prm.state = e->off_state; prm.in = wav; prm.out = wav_out; prm.spec_out = spec_out;
-    prm.n_streams = B; prm.n_hops = 1 + L / e->cfg.hop; prm.L = L; prm.mode = fe::MODE_OFFLINE; prm.dbg_hop = -1;
-    return launch(e, prm, e->off_scratch, st);
+    const size_t need = (size_t)s->n_streams * hops_per_chunk * s->e->cfg.hop;
+    if (s->h_floats < need) {
+        FE_CUDA(cudaStreamSynchronize(s->s_copy_out));
+        FE_CUDA(cudaStreamSynchronize(s->s_compute));
+        for (int i = 0; i < 2; ++i) {
+            if (s->h_in[i]) FE_CUDA(cudaFree(s->h_in[i]));
+            if (s->h_out[i]) FE_CUDA(cudaFree(s->h_out[i]));
+            s->h_in[i] = s->h_out[i] = nullptr;
+        }
+        s->h_floats = 0;
+        for (int i = 0; i < 2; ++i) {
+            FE_CUDA(cudaMalloc(&s->h_in[i], need * sizeof(float)));
+            FE_CUDA(cudaMalloc(&s->h_out[i], need * sizeof(float)));
+        }
+        s->h_floats = need;
+    }
+    return FE_OK;
 }
 
 // Host buffers: [copy-in | kernel | copy-out] pipelined over `hops_per_chunk`-hop pieces on three streams with
 // double-buffered device staging; the GRU / overlap state carries from piece to piece in fe_state.
+// Ordered after the work already queued on `cuda_stream` (a state reset / import issued there); returns when the last copy-out
+// has completed.  On an error every copy already in flight into the caller's buffers is drained before returning.
 FE_API int fe_stream_host(fe_engine* e, fe_state* s, const float* wav_in_host, float* wav_out_host, int n_hops, long long ld_in,
-                   long long ld_out, int hops_per_chunk) {
+                   long long ld_out, int hops_per_chunk, void* cuda_stream) {
     if (!e || !s || s->e != e || !wav_in_host || !wav_out_host) return fail(FE_ERR_ARG, "fe_stream_host: null / mismatched argument");
     const int H = e->cfg.hop, B = s->n_streams;
     if (n_hops < 0 || ld_in < (long long)n_hops * H || ld_out < (long long)n_hops * H)
@@ -359,54 +427,39 @@ FE_API int fe_stream_host(fe_engine* e, fe_state* s, const float* wav_in_host, f
     FE_CUDA(cudaSetDevice(e->device));
     if (hops_per_chunk <= 0) hops_per_chunk = 64;
     hops_per_chunk = std::min(hops_per_chunk, n_hops);
-    if (!e->s_compute) {
-        FE_CUDA(cudaStreamCreateWithFlags(&e->s_copy_in, cudaStreamNonBlocking));
-        FE_CUDA(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
-        FE_CUDA(cudaStreamCreateWithFlags(&e->s_copy_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            FE_CUDA(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
-            FE_CUDA(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
-            FE_CUDA(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
-        }
-    }
-    const size_t need = (size_t)B * hops_per_chunk * H;
-    if (e->h_floats < need) {
-        for (int i = 0; i < 2; ++i) {
-            if (e->h_in[i]) FE_CUDA(cudaFree(e->h_in[i]));
-            if (e->h_out[i]) FE_CUDA(cudaFree(e->h_out[i]));
-            e->h_in[i] = e->h_out[i] = nullptr;
-        }
-        e->h_floats = 0;
-        for (int i = 0; i < 2; ++i) {
-            FE_CUDA(cudaMalloc(&e->h_in[i], need * sizeof(float)));
-            FE_CUDA(cudaMalloc(&e->h_out[i], need * sizeof(float)));
-        }
-        e->h_floats = need;
-    }
-    // order against work already queued on the default stream (state reset / import)
-    FE_CUDA(cudaStreamSynchronize(nullptr));
+    if (int rc = fe_state_reserve_host(s, hops_per_chunk)) return rc;
+    FE_CUDA(cudaEventRecord(s->ev_call, (cudaStream_t)cuda_stream));
+    FE_CUDA(cudaStreamWaitEvent(s->s_compute, s->ev_call, 0));
+    int rc = FE_OK;
+    cudaError_t ce = cudaSuccess;
+#define FE_TRY(call) do { if (rc == FE_OK && ce == cudaSuccess) { ce = (call); if (ce != cudaSuccess) rc = cuda_fail(ce, #call); } } while (0)
     int piece = 0;
-    for (int h0 = 0; h0 < n_hops; h0 += hops_per_chunk, ++piece) {
+    for (int h0 = 0; h0 < n_hops && rc == FE_OK; h0 += hops_per_chunk, ++piece) {
         const int nh = std::min(hops_per_chunk, n_hops - h0), b = piece & 1;
         const size_t w = (size_t)nh * H;
         if (piece >= 2) {   // staging buffers b are free once piece-2 finished its kernel (in) / its copy-out (out)
-            FE_CUDA(cudaStreamWaitEvent(e->s_copy_in, e->ev_k[b], 0));
-            FE_CUDA(cudaStreamWaitEvent(e->s_compute, e->ev_out[b], 0));
+            FE_TRY(cudaStreamWaitEvent(s->s_copy_in, s->ev_k[b], 0));
+            FE_TRY(cudaStreamWaitEvent(s->s_compute, s->ev_out[b], 0));
         }
-        FE_CUDA(cudaMemcpy2DAsync(e->h_in[b], w * sizeof(float), wav_in_host + (size_t)h0 * H, (size_t)ld_in * sizeof(float),
-                                  w * sizeof(float), B, cudaMemcpyHostToDevice, e->s_copy_in));
-        FE_CUDA(cudaEventRecord(e->ev_in[b], e->s_copy_in));
-        FE_CUDA(cudaStreamWaitEvent(e->s_compute, e->ev_in[b], 0));
-        int rc = fe_stream(e, s, e->h_in[b], e->h_out[b], nh, (long long)w, (long long)w, e->s_compute);
-        if (rc) return rc;
-        FE_CUDA(cudaEventRecord(e->ev_k[b], e->s_compute));
-        FE_CUDA(cudaStreamWaitEvent(e->s_copy_out, e->ev_k[b], 0));
-        FE_CUDA(cudaMemcpy2DAsync(wav_out_host + (size_t)h0 * H, (size_t)ld_out * sizeof(float), e->h_out[b], w * sizeof(float),
-                                  w * sizeof(float), B, cudaMemcpyDeviceToHost, e->s_copy_out));
-        FE_CUDA(cudaEventRecord(e->ev_out[b], e->s_copy_out));
+        FE_TRY(cudaMemcpy2DAsync(s->h_in[b], w * sizeof(float), wav_in_host + (size_t)h0 * H, (size_t)ld_in * sizeof(float),
+                                 w * sizeof(float), B, cudaMemcpyHostToDevice, s->s_copy_in));
+        FE_TRY(cudaEventRecord(s->ev_in[b], s->s_copy_in));
+        FE_TRY(cudaStreamWaitEvent(s->s_compute, s->ev_in[b], 0));
+        if (rc == FE_OK) rc = fe_stream(e, s, s->h_in[b], s->h_out[b], nh, (long long)w, (long long)w, s->s_compute);
+        FE_TRY(cudaEventRecord(s->ev_k[b], s->s_compute));
+        FE_TRY(cudaStreamWaitEvent(s->s_copy_out, s->ev_k[b], 0));
+        FE_TRY(cudaMemcpy2DAsync(wav_out_host + (size_t)h0 * H, (size_t)ld_out * sizeof(float), s->h_out[b], w * sizeof(float),
+                                 w * sizeof(float), B, cudaMemcpyDeviceToHost, s->s_copy_out));
+        FE_TRY(cudaEventRecord(s->ev_out[b], s->s_copy_out));
     }
-    FE_CUDA(cudaStreamSynchronize(e->s_copy_out));
-    FE_CUDA(cudaStreamSynchronize(e->s_compute));
+#undef FE_TRY
+    // drain (also on the error path: nothing may still be writing into the caller's buffers once we return)
+    const std::string err_keep = g_err;
+    cudaError_t c1 = cudaStreamSynchronize(s->s_copy_in), c2 = cudaStreamSynchronize(s->s_compute), c3 = cudaStreamSynchronize(s->s_copy_out);
+    if (rc != FE_OK) { g_err = err_keep; return rc; }
+    if (c1 != cudaSuccess) return cuda_fail(c1, "fe_stream_host: copy-in stream");
+    if (c2 != cudaSuccess) return cuda_fail(c2, "fe_stream_host: compute stream");
+    if (c3 != cudaSuccess) return cuda_fail(c3, "fe_stream_host: copy-out stream");
     return FE_OK;
 }
 
@@ -426,8 +479,8 @@ FE_API int fe_set_streams_per_cta(fe_engine* e, int s) {
 }
 FE_API int fe_set_precision(fe_engine* e, int mode) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_precision: null engine");
-    if (mode < 0 || mode > 2) return fail(FE_ERR_ARG, "fe_set_precision: mode must be 0 (tf32), 1 (fp32) or 2 (f16)");
-    const int tc = mode == 1 ? 0 : (mode == 2 ? 2 : 1);
+    if (mode < 0 || mode > 4) return fail(FE_ERR_ARG, "fe_set_precision: mode must be 0 (tf32), 1 (fp32), 2 (f16), 3 (bf16) or 4 (fp32x3)");
+    const int tc = mode == 1 ? 0 : (mode == 0 ? 1 : mode);
     bool ok = false;
     for (const Variant& v : e->variants) ok = ok || (v.ops.tc == tc && (e->forced_s == 0 || v.ops.S == e->forced_s));
     if (!ok) return fail(FE_ERR_UNSUPPORTED, "fe_set_precision: this model has no kernel variant for the requested mode");
@@ -435,7 +488,34 @@ FE_API int fe_set_precision(fe_engine* e, int mode) {
     return FE_OK;
 }
 FE_API int fe_get_precision(fe_engine* e) {
-    return e ? (e->tc == 0 ? 1 : (e->tc == 2 ? 2 : 0)) : fail(FE_ERR_ARG, "fe_get_precision: null engine");
+    return e ? (e->tc == 0 ? 1 : (e->tc == 1 ? 0 : e->tc)) : fail(FE_ERR_ARG, "fe_get_precision: null engine");
+}
+// Measured fp32 FMA throughput of `device` in TFLOP/s (2 FLOP per FFMA): the roofline denominator bench.py uses for the fp32 FMA-pipe
+// kernel family instead of the nominal 148 SM x 128 lanes x 2 x clock.
+FE_API int fe_microbench_fma(int device, double* tflops) {
+    if (!tflops) return fail(FE_ERR_ARG, "fe_microbench_fma: null argument");
+    FE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FE_CUDA(cudaGetDeviceProperties(&prop, device));
+    float* out = nullptr;
+    FE_CUDA(cudaMalloc(&out, 4));
+    cudaEvent_t e0, e1;
+    FE_CUDA(cudaEventCreate(&e0)); FE_CUDA(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        FE_CUDA(cudaEventRecord(e0));
+        fma_peak_kernel<<<grid, 256>>>(out, iters, 1.0000001f, 1e-7f);
+        FE_CUDA(cudaEventRecord(e1));
+        FE_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return FE_OK;
 }
 FE_API int fe_profile_slots(void) { return (int)(fe::PH_COUNT + fe::PH_COUNT * fe::PH_NSUB); }
 FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
@@ -443,7 +523,7 @@ FE_API int fe_set_profile(fe_engine* e, long long* counters_device) {
     e->prof = counters_device;
     return FE_OK;
 }
-FE_API long long fe_kernel_launches(fe_engine* e) { return e ? e->launches : 0; }
+FE_API long long fe_kernel_launches(fe_engine* e) { return e ? e->launches.load(std::memory_order_relaxed) : 0; }
 FE_API int fe_tap_floats(fe_engine* e) { return e ? e->variants[0].ops.tap_floats : 0; }
 
 }  // extern "C"

@@ -28,18 +28,20 @@ template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAG
 }  // namespace fe
 
 // X(config id, Cfg type, S, PREC)   PREC: false / 0 = everything on the fp32 FMA pipe; true / 1 = contractions on tcgen05 (TF32);
-// 2 = as 1 with the conv section's operands in fp16 (K = 16 per MMA, half the shared memory)
+// 2 = as 1 with the conv section's operands in fp16 (K = 16 per MMA, half the shared memory); 3 = bfloat16 conv section, TF32 RNNFormer
+// (BASELINE config 3: "bf16 conv / fp32 GRU"); 4 = fp32-accurate split-fp16 operands, three MMAs per product (fe_plan.h)
 #define FE_VARIANTS_16T(X) X(0, C16T, 1, false) X(0, C16T, 2, false) X(0, C16T, 4, false) X(0, C16T, 1, true) X(0, C16T, 2, true) X(0, C16T, 4, true) \
-    X(0, C16T, 1, 2) X(0, C16T, 2, 2) X(0, C16T, 4, 2)
-#define FE_VARIANTS_16B(X) X(1, C16B, 1, false) X(1, C16B, 2, false) X(1, C16B, 1, true) X(1, C16B, 2, true) X(1, C16B, 1, 2) X(1, C16B, 2, 2)
-#define FE_VARIANTS_16S(X) X(2, C16S, 1, false) X(2, C16S, 1, true) X(2, C16S, 1, 2) X(2, C16S, 2, 2)
-#define FE_VARIANTS_16M(X) X(3, C16M, 1, false) X(3, C16M, 1, true) X(3, C16M, 1, 2)
-#define FE_VARIANTS_16L(X) X(4, C16L, 1, false) X(4, C16L, 1, true) X(4, C16L, 1, 2)
-#define FE_VARIANTS_48T(X) X(5, C48T, 1, false) X(5, C48T, 2, false) X(5, C48T, 1, true) X(5, C48T, 2, true) X(5, C48T, 1, 2) X(5, C48T, 2, 2)
-#define FE_VARIANTS_48B(X) X(6, C48B, 1, false) X(6, C48B, 1, true) X(6, C48B, 1, 2) X(6, C48B, 2, 2)
+    X(0, C16T, 1, 2) X(0, C16T, 2, 2) X(0, C16T, 4, 2) X(0, C16T, 2, 3) X(0, C16T, 1, 4) X(0, C16T, 2, 4)
+#define FE_VARIANTS_16B(X) X(1, C16B, 1, false) X(1, C16B, 2, false) X(1, C16B, 1, true) X(1, C16B, 2, true) X(1, C16B, 1, 2) X(1, C16B, 2, 2) \
+    X(1, C16B, 2, 3) X(1, C16B, 1, 4) X(1, C16B, 2, 4)
+#define FE_VARIANTS_16S(X) X(2, C16S, 1, false) X(2, C16S, 1, true) X(2, C16S, 1, 2) X(2, C16S, 2, 2) X(2, C16S, 1, 3)
+#define FE_VARIANTS_16M(X) X(3, C16M, 1, false) X(3, C16M, 1, true) X(3, C16M, 1, 2) X(3, C16M, 1, 3)
+#define FE_VARIANTS_16L(X) X(4, C16L, 1, false) X(4, C16L, 1, true) X(4, C16L, 1, 2) X(4, C16L, 1, 3)
+#define FE_VARIANTS_48T(X) X(5, C48T, 1, false) X(5, C48T, 2, false) X(5, C48T, 1, true) X(5, C48T, 2, true) X(5, C48T, 1, 2) X(5, C48T, 2, 2) X(5, C48T, 1, 4)
+#define FE_VARIANTS_48B(X) X(6, C48B, 1, false) X(6, C48B, 1, true) X(6, C48B, 1, 2) X(6, C48B, 2, 2) X(6, C48B, 1, 4)
 #define FE_VARIANTS_48S(X) X(7, C48S, 1, false) X(7, C48S, 1, true) X(7, C48S, 1, 2)
-#define FE_VARIANTS_48M(X) X(8, C48M, 1, false) X(8, C48M, 1, true) X(8, C48M, 1, 2)
-#define FE_VARIANTS_48L(X) X(9, C48L, 1, false) X(9, C48L, 1, true) X(9, C48L, 1, 2)
+#define FE_VARIANTS_48M(X) X(8, C48M, 1, false) X(8, C48M, 1, true) X(8, C48M, 1, 2) X(8, C48M, 1, 3)
+#define FE_VARIANTS_48L(X) X(9, C48L, 1, false) X(9, C48L, 1, true) X(9, C48L, 1, 2) X(9, C48L, 1, 3)
 #define FE_ALL_VARIANTS(X) FE_VARIANTS_16T(X) FE_VARIANTS_16B(X) FE_VARIANTS_16S(X) FE_VARIANTS_16M(X) FE_VARIANTS_16L(X) \
     FE_VARIANTS_48T(X) FE_VARIANTS_48B(X) FE_VARIANTS_48S(X) FE_VARIANTS_48M(X) FE_VARIANTS_48L(X)
 

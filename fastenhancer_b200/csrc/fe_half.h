@@ -1,4 +1,4 @@
-// fe_half.h -- host-side IEEE binary16 conversion (round to nearest even), shared by the weight packer and the CPU emulation.
+// fe_half.h -- host-side IEEE binary16 / bfloat16 conversion (round to nearest even), shared by the weight packer and the CPU emulation.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -45,5 +45,23 @@ inline float f16_bits_to_f32(uint16_t h) {
     std::memcpy(&f, &x, 4);
     return f;
 }
+
+// bfloat16: the top 16 bits of an fp32, round to nearest even (what cvt.rn.bf16x2.f32 does); finite inputs only
+inline uint16_t f32_to_bf16_bits(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    if ((x & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((x >> 16) | 0x40u);                     // nan stays nan
+    x += 0x7fffu + ((x >> 16) & 1u);
+    return (uint16_t)(x >> 16);
+}
+inline float bf16_bits_to_f32(uint16_t h) {
+    const uint32_t x = (uint32_t)h << 16;
+    float f;
+    std::memcpy(&f, &x, 4);
+    return f;
+}
+// 16-bit operand format of a tensor-core variant: fp16 (FMT 1) or bfloat16 (FMT 2)
+template <bool BF> inline uint16_t f32_to_h16_bits(float f) { return BF ? f32_to_bf16_bits(f) : f32_to_f16_bits(f); }
+template <bool BF> inline float h16_bits_to_f32(uint16_t h) { return BF ? bf16_bits_to_f32(h) : f16_bits_to_f32(h); }
 
 }  // namespace fe

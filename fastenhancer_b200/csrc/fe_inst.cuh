@@ -52,8 +52,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16: A / B format 0 = fp16, 1 = bfloat16
+__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int bf = 0) {
+    return (1u << 4) | ((uint32_t)bf << 7) | ((uint32_t)bf << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -123,15 +124,16 @@ template <class P> struct GpuCtx {
 #endif
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     // M64: a 64-row MMA, whose accumulator row r lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
-    // F16: kind::f16 -- operands are halves (8 per 16-byte row: K = 16 per MMA), same descriptors.
-    template <bool M64 = false, bool F16 = false>
+    // FMT: 0 = kind::tf32; 1 / 2 = kind::f16 with fp16 / bfloat16 operands (8 per 16-byte row: K = 16 per MMA), same descriptors.
+    static constexpr int FMT16 = P::BF16 ? 2 : 1;      // the 16-bit operand format of this variant's conv section
+    template <bool M64 = false, int FMT = 0>
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
-        if constexpr (F16)
+        if constexpr (FMT != 0)
             asm volatile(
                 "{\n\t" FE_MMA_ELECT
                 FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_f16(M64 ? 64 : 128, np)), "r"(acc ? 1u : 0u) : "memory");
+                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_f16(M64 ? 64 : 128, np, FMT == 2)), "r"(acc ? 1u : 0u) : "memory");
         else
             asm volatile(
                 "{\n\t" FE_MMA_ELECT

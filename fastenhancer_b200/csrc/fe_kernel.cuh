@@ -48,9 +48,10 @@ inline float fe_div(float a, float b) { return a / b; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
 inline void sth(float* base, int idx, float v) { reinterpret_cast<uint16_t*>(base)[idx] = f32_to_f16_bits(v); }      // store one half
-// two floats -> two fp16 in one 32-bit word (a in the low half), and back
-inline float pack_h2(float a, float b) { uint32_t u = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(b) << 16); float r; std::memcpy(&r, &u, 4); return r; }
-inline f2 unpack_h2(float p) { uint32_t u; std::memcpy(&u, &p, 4); f2 r; r.x = f16_bits_to_f32((uint16_t)(u & 0xffffu)); r.y = f16_bits_to_f32((uint16_t)(u >> 16)); return r; }
+inline float rnd_h(float v) { return f16_bits_to_f32(f32_to_f16_bits(v)); }       // v rounded to fp16, as a float
+// two floats -> two fp16 (BF: bfloat16) in one 32-bit word (a in the low half), and back
+template <bool BF = false> inline float pack_h2(float a, float b) { uint32_t u = (uint32_t)f32_to_h16_bits<BF>(a) | ((uint32_t)f32_to_h16_bits<BF>(b) << 16); float r; std::memcpy(&r, &u, 4); return r; }
+template <bool BF = false> inline f2 unpack_h2(float p) { uint32_t u; std::memcpy(&u, &p, 4); f2 r; r.x = h16_bits_to_f32<BF>((uint16_t)(u & 0xffffu)); r.y = h16_bits_to_f32<BF>((uint16_t)(u >> 16)); return r; }
 inline float tf32_clean(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 }  // namespace fe
 #else
@@ -82,16 +83,31 @@ FE_DEV float tf32_pre(float x) { return __uint_as_float(__float_as_uint(x) + 0x1
 FE_DEV float tf32_pre(float x) { return tf32_rna(x); }
 #endif
 FE_DEV float tf32_clean(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-// two floats -> two fp16 in one 32-bit word (a in the low half, round to nearest even: one cvt.rn.f16x2.f32), and back
-FE_DEV float pack_h2(float a, float b) { uint32_t u; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a)); return __uint_as_float(u); }
+// two floats -> two fp16 (BF: bfloat16) in one 32-bit word (a in the low half, round to nearest even: one cvt.rn.{f16x2,bf16x2}.f32), and back
+template <bool BF = false> FE_DEV float pack_h2(float a, float b) {
+    uint32_t u;
+    if constexpr (BF) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+    return __uint_as_float(u);
+}
 FE_DEV void sth(float* base, int idx, float v) {       // store one half (round to nearest even)
     unsigned short h;
     asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
     reinterpret_cast<unsigned short*>(base)[idx] = h;
 }
-FE_DEV f2 unpack_h2(float p) {
+FE_DEV float rnd_h(float v) {          // v rounded to fp16, as a float
+    float r;
+    asm("{\n\t.reg .b16 t;\n\tcvt.rn.f16.f32 t, %1;\n\tcvt.f32.f16 %0, t;\n\t}" : "=f"(r) : "f"(v));
+    return r;
+}
+template <bool BF = false> FE_DEV f2 unpack_h2(float p) {
     f2 r;
-    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(__float_as_uint(p)));
+    if constexpr (BF) {      // a bfloat16 is the top half of an fp32
+        const uint32_t u = __float_as_uint(p);
+        r.x = __uint_as_float(u << 16); r.y = __uint_as_float(u & 0xffff0000u);
+    } else {
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(__float_as_uint(p)));
+    }
     return r;
 }
 }  // namespace fe
@@ -146,6 +162,12 @@ constexpr int PH_NSUB = PH_COUNT - PH_TC_WAITW;      // the profile buffer is [P
 
 FE_DEV f4 mk4(float a, float b, float c, float d) { f4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
 FE_DEV f2 mk2(float a, float b) { f2 v; v.x = a; v.y = b; return v; }
+// split variants: (a, b) -> hi = the fp16 pair, lo = the fp16 pair of the remainders a - hi.a, b - hi.b (exact in fp32)
+FE_DEV void split_h2(float a, float b, float& hi, float& lo) {
+    hi = pack_h2(a, b);
+    const f2 r = unpack_h2(hi);
+    lo = pack_h2(a - r.x, b - r.y);
+}
 FE_DEV float silu(float x) { return fe_div(x, 1.0f + fe_exp(-x)); }
 // GRU gates: ex2.approx / rcp.approx based (absolute error ~1e-7, far inside the fp32 noise of the recurrence)
 FE_DEV float sigmoid_acc(float x) { return fe_div(1.0f, 1.0f + fe_exp(-x)); }
@@ -340,10 +362,10 @@ FE_DEV void row_gemm(X& x, int tid, int ci0, const float* xbase, int row_pitch, 
 // Row GEMM, one k per step (frequency-axis linear over a tensor-core-layout activation, where consecutive frequencies are not
 // contiguous), vectorised over channels: a lane owns 4 consecutive channels of one stream (one float4 per k in the tensor-core
 // layouts, where channels are the innermost index).  xrow(l) -> float4 of k = 0 for lane l (< NLANE); epi(l, o0, acc[4][NO]).
-// CLEAN: the input holds pre-rounded TF32 MMA operands (tf32_pre): mask the low bits.  XH16: the input holds halves (8 bytes = the
-// lane's 4 channels).
-template <class L, int NLANE, bool CLEAN = false, bool XH16 = false, class X, class XRow, class Epi>
-FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi) {
+// CLEAN: the input holds pre-rounded TF32 MMA operands (tf32_pre): mask the low bits.  XFMT: 0 = the input holds floats; 1 / 2 = fp16 /
+// bfloat16 (8 bytes = the lane's 4 channels); 3 = split fp16: hi parts as for 1, the lo parts `xlo` floats further.
+template <class L, int NLANE, bool CLEAN = false, int XFMT = 0, class X, class XRow, class Epi>
+FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi, int xlo = 0) {
     constexpr int NO = L::NO;
     static_assert(NLANE <= 32 && L::RT <= 4, "row gemm (vector form): at most 32 lanes of 4 channels");
     const int og = tid >> 5, lane = tid & 31;
@@ -365,10 +387,15 @@ FE_DEV void row_gemm_k1v(X& x, int tid, int ci0, XRow xrow, int kstride, Epi epi
 #pragma unroll 4
             for (int kk = 0; kk < rows; ++kk) {
                 f4 xv;
-                if constexpr (XH16) {
+                if constexpr (XFMT != 0) {
                     const f2 raw = ld2(xr + (c * L::KC + kk) * kstride);
-                    const f2 lo = unpack_h2(raw.x), hi = unpack_h2(raw.y);
+                    const f2 lo = unpack_h2<XFMT == 2>(raw.x), hi = unpack_h2<XFMT == 2>(raw.y);
                     xv = mk4(lo.x, lo.y, hi.x, hi.y);
+                    if constexpr (XFMT == 3) {
+                        const f2 raw2 = ld2(xr + xlo + (c * L::KC + kk) * kstride);
+                        const f2 lo2 = unpack_h2(raw2.x), hi2 = unpack_h2(raw2.y);
+                        xv.x += lo2.x; xv.y += lo2.y; xv.z += hi2.x; xv.w += hi2.y;
+                    }
                 } else {
                     xv = ld4(xr + (c * L::KC + kk) * kstride);
                 }
@@ -509,9 +536,12 @@ FE_DEV void tc_epilogue64(X& x, int tid, Epi epi) {
 
 // a_desc(j) -> descriptor of the A operand of k-step j (two 4-channel slabs, LBO apart), positioned at the first data
 // slot; tap t of a 3-tap layer reads slots shifted by (t - 1) * tapstride (one slot = 16 bytes = 4 floats).
+// alo (split layers, L::PARTS == 2): float offset from the hi parts of the A operand to its lo parts; the lo tile of the weights follows
+// the hi tile.  Three MMAs per product: hi * hi, lo * hi, hi * lo.
 template <class L, bool M64, class X, class ADesc>
-FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride) {
+FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride, int alo = 0) {
     static_assert(!M64 || (L::NMT == 1 && L::NPOS <= 64), "M = 64 layers have one M tile");
+    constexpr int FMT = L::KE == 16 ? X::FMT16 : 0;
     tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
         const int t = tile / L::NKS, j = tile % L::NKS;
         const int shift = (L::TAPS == 3 ? (t - 1) * tapstride : 0);
@@ -519,36 +549,48 @@ FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride) {
         for (int mt = 0; mt < L::NMT; ++mt) {
             const int rows = (L::NPOS - mt * 128) < 128 ? (L::NPOS - mt * 128) : 128;
 #pragma unroll
-            for (int ns = 0; ns < L::NSPLIT; ++ns)
-                x.template mma<M64, L::KE == 16>(tid, x.desc_add(a_desc(j), (shift + mt * 128) * 4), x.desc_add(wd, ns * L::NPS * 4), L::NPS,
-                                                 mt * L::NP + ns * L::NPS, tile > 0, rows);
+            for (int ns = 0; ns < L::NSPLIT; ++ns) {
+                const auto a = x.desc_add(a_desc(j), (shift + mt * 128) * 4), b = x.desc_add(wd, ns * L::NPS * 4);
+                x.template mma<M64, FMT>(tid, a, b, L::NPS, mt * L::NP + ns * L::NPS, tile > 0, rows);
+                if constexpr (L::PARTS == 2) {
+                    x.template mma<M64, FMT>(tid, x.desc_add(a, alo), b, L::NPS, mt * L::NP + ns * L::NPS, true, rows);
+                    x.template mma<M64, FMT>(tid, a, x.desc_add(b, L::TILE1), L::NPS, mt * L::NP + ns * L::NPS, true, rows);
+                }
+            }
         }
     });
 }
 template <class L, class X, class ADesc, class Epi>
-FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi) {
-    tc_mmas<L, false>(x, tid, ci, a_desc, tapstride);
+FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi, int alo = 0) {
+    tc_mmas<L, false>(x, tid, ci, a_desc, tapstride, alo);
     tc_epilogue<L>(x, tid, epi);
 }
 template <int W> struct WTag { static constexpr int value = W; };
 // RNNFormer layer (1x1, positions = S * F2): epi(position, first channel, values[W], WTag<W>) with W = 2 (M = 64 path) or 4
 // ALLROWS: see tc_epilogue (rows past the last position reach epi with valid = false).
 template <class L, bool M64, bool ALLROWS = false, class X, class ADesc, class Epi>
-FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi) {
-    tc_mmas<L, M64>(x, tid, ci, a_desc, 0);
+FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi, int alo = 0) {
+    tc_mmas<L, M64>(x, tid, ci, a_desc, 0, alo);
     if constexpr (M64) tc_epilogue64<L>(x, tid, [&](int p, int c, const float* v) { epi(p, c, v, true, WTag<2>{}); });
     else if constexpr (ALLROWS) tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
     else tc_epilogue<L>(x, tid, [&](int p, int g, const float* v) { epi(p, 4 * g, v, true, WTag<4>{}); });
 }
 
 // Same with the A operand in tensor memory: k-step j reads columns a_col0 + 8j .. + 7 (TMEM lane = position, M = 128).
+// (split layers: the lo parts of the operand sit `alo` columns after the hi parts)
 template <class L, class X, class Epi>
-FE_DEV void rf_layer_ts(X& x, int tid, int ci, int a_col0, Epi epi) {
+FE_DEV void rf_layer_ts(X& x, int tid, int ci, int a_col0, Epi epi, int alo = 0) {
     static_assert(L::NMT == 1 && L::TAPS == 1, "TMEM A operands: one M tile, no taps");
     tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
 #pragma unroll
-        for (int ns = 0; ns < L::NSPLIT; ++ns)
-            x.template mma_ts<L::KE == 16>(tid, a_col0 + 8 * tile, x.desc_add(wd, ns * L::NPS * 4), L::NPS, ns * L::NPS, tile > 0, L::NPOS);
+        for (int ns = 0; ns < L::NSPLIT; ++ns) {
+            const auto b = x.desc_add(wd, ns * L::NPS * 4);
+            x.template mma_ts<L::KE == 16>(tid, a_col0 + 8 * tile, b, L::NPS, ns * L::NPS, tile > 0, L::NPOS);
+            if constexpr (L::PARTS == 2) {
+                x.template mma_ts<true>(tid, a_col0 + alo + 8 * tile, b, L::NPS, ns * L::NPS, true, L::NPOS);
+                x.template mma_ts<true>(tid, a_col0 + 8 * tile, x.desc_add(b, L::TILE1), L::NPS, ns * L::NPS, true, L::NPOS);
+            }
+        }
     });
     // every lane runs the epilogue (it may store operands to tensor memory); rows past the end come with valid = false
     tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
@@ -577,6 +619,14 @@ template <class P> struct Frame {
     static constexpr int TAP_SPECHAT = TAP_MASK + 2 * FIN;
     static constexpr int TAP_TOTAL = TAP_SPECHAT + 2 * FIN;
 
+    // State in global memory: planes in the reference's own cache shapes, so that host wrappers can hand them out as zero-copy
+    // tensors: cache_stft [B][N-H] | cache_istft [B][N-H] | h_0 [B][F2][C2] | ... | h_{K-1}  (functional/audio_modules.py:238-241,
+    // models/fastenhancer/default/model.py:263-264, 614-618; B = n_streams of the state).
+    FE_DEV static size_t st_cache(const KParams& prm, int which, int gs) { return ((size_t)which * prm.n_streams + gs) * C::CL; }
+    FE_DEV static size_t st_h(const KParams& prm, int k, int gs) {
+        return 2 * (size_t)prm.n_streams * C::CL + ((size_t)k * prm.n_streams + gs) * (size_t)(F2 * C2);
+    }
+
     struct PwAcc { float v[P::PwCat::CT][P::PwCat::PT]; };
     static constexpr int SLABF = P::SLABF;
 
@@ -597,9 +647,23 @@ template <class P> struct Frame {
     FE_DEV static int rf_off16(int c, int s, int f) { return (c >> 3) * P::RSLABF + (f * S + s) * 4 + ((c >> 2) & 1) * 2; }
     // one activation element as fp32, whatever the storage format (taps / debug only)
     FE_DEV static float act_get(const float* buf, int c, int s, int f) {
-        if constexpr (P::H16) { const f2 v = unpack_h2(buf[act_off16(c & ~3, s, f) + ((c >> 1) & 1)]); return (c & 1) ? v.y : v.x; }
+        if constexpr (P::H16) {
+            const int o = act_off16(c & ~3, s, f) + ((c >> 1) & 1);
+            f2 v = unpack_h2<P::BF16>(buf[o]);
+            if constexpr (P::SPLIT) { const f2 l = unpack_h2(buf[o + P::ACT1]); v.x += l.x; v.y += l.y; }
+            return (c & 1) ? v.y : v.x;
+        }
         else if constexpr (P::TC) return tf32_clean(buf[act_off(c, s, f)]);       // pre-rounded MMA operands
         else return buf[act_off(c, s, f)];
+    }
+
+    // split variants: fp16 hi / lo copy of compressed-spectrum bin k of stream s for the enc_pre MMAs -- slab of 8 virtual channels
+    // (c * 4 + k % 4) per slot, [hi slab | zero slab | lo slab | zero slab] at SPEC + O_SPECH
+    FE_DEV static void spec_h16(float* SPEC, int s, int k, float re, float im) {
+        float* b = SPEC + P::O_SPECH;
+        const int slot = ((k >> 2) + 1) * S + s, q = k & 3;
+        sth(b, slot * 8 + q, re); sth(b, slot * 8 + 4 + q, im);
+        sth(b + 2 * SLABF, slot * 8 + q, re - rnd_h(re)); sth(b + 2 * SLABF, slot * 8 + 4 + q, im - rnd_h(im));
     }
 
     // Tensor-core layer epilogue: bias (+SiLU), TF32 rounding for the next MMA, one float4 per 4-channel group;
@@ -615,10 +679,19 @@ template <class P> struct Frame {
             if constexpr (P::H16) {
                 if (round) {         // operand of a later MMA: four halves (8 bytes) of the 8-channel row
                     const int off = (g >> 1) * SLABF + (S + gp) * 4 + (g & 1) * 2;
-                    const f2 h = mk2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
-                    st2(dst + off, h);
-                    if constexpr (P::SKIP_SMEM < P::NSK) {
-                        if (gdst) st2(gdst + off, h);
+                    if constexpr (P::SPLIT) {
+                        f2 h, l;
+                        split_h2(o[0], o[1], h.x, l.x); split_h2(o[2], o[3], h.y, l.y);
+                        st2(dst + off, h); st2(dst + P::ACT1 + off, l);
+                        if constexpr (P::SKIP_SMEM < P::NSK) {
+                            if (gdst) { st2(gdst + off, h); st2(gdst + P::ACT1 + off, l); }
+                        }
+                    } else {
+                        const f2 h = mk2(pack_h2<P::BF16>(o[0], o[1]), pack_h2<P::BF16>(o[2], o[3]));
+                        st2(dst + off, h);
+                        if constexpr (P::SKIP_SMEM < P::NSK) {
+                            if (gdst) st2(gdst + off, h);
+                        }
                     }
                 } else {             // the mask: fp32, the spectrum's layout
                     st4(dst + g * SLABF + (S + gp) * 4, mk4(o[0], o[1], o[2], o[3]));
@@ -642,13 +715,14 @@ template <class P> struct Frame {
     // It also clears the slab that pads the channels to a whole k-step (fp16 variants of configs with C1 % 16 != 0).
     static constexpr int NSLAB = P::C1P / P::CG;         // slabs of a conv-section operand buffer
     FE_DEV static void zero_halo(float* dst, int tid) {
-        for (int idx = tid; idx < NSLAB * 2 * S; idx += NT) {
+        for (int idx = tid; idx < P::NPART * NSLAB * 2 * S; idx += NT) {         // (split variants: the slabs of the lo parts follow the hi parts)
             const int g = idx / (2 * S), r = idx % (2 * S);
             st4(dst + g * SLABF + (r < S ? r : S * F1 + r) * 4, mk4(0.f, 0.f, 0.f, 0.f));
         }
         if constexpr (P::C1P > C1) {
             static_assert(P::C1P - C1 == P::CG, "channel padding is one whole slab");
-            for (int idx = tid; idx < P::SLOTS; idx += NT) st4(dst + (NSLAB - 1) * SLABF + idx * 4, mk4(0.f, 0.f, 0.f, 0.f));
+            for (int idx = tid; idx < P::NPART * P::SLOTS; idx += NT)
+                st4(dst + ((idx / P::SLOTS + 1) * NSLAB - 1) * SLABF + (idx % P::SLOTS) * 4, mk4(0.f, 0.f, 0.f, 0.f));
         }
     }
 
@@ -685,8 +759,7 @@ template <class P> struct Frame {
                     int gs = x.s0 + s;
                     float a = 0.f, b = 0.f;
                     if (gs < prm.n_streams) {
-                        const float* st = prm.state + (size_t)gs * C::STATE;
-                        a = st[i]; b = st[C::CL + i];
+                        a = prm.state[st_cache(prm, 0, gs) + i]; b = prm.state[st_cache(prm, 1, gs) + i];
                     }
                     sm[P::SM_TIN + s * N + ((H + i) & NMASK)] = a;
                     sm[P::SM_OLA + s * N + i] = b;
@@ -704,16 +777,20 @@ template <class P> struct Frame {
                         const float z[4] = {0.f, 0.f, 0.f, 0.f};
                         if constexpr (!P::RF16) x.tmem_st4(tid, P::TM_XT + 4 * g, z);      // K-padding columns of x stay zero; the others are rewritten every hop
                         for (int k = 0; k < C::K; ++k) {
-                            float v[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = 4 * g + e;
-                                v[e] = (live && c < C2) ? prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f] : 0.f;
+                            float v[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (live && 4 * g < C2) {
+                                const f4 t = ldg4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * g);
+                                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                             }
                             x.tmem_st4(tid, P::TM_H + k * P::C2P + 4 * g, v);
-                            if constexpr (P::RF16) {         // the MMA operand copy: packed halves, two channels per column
+                            if constexpr (P::SPLIT) {        // the MMA operand copy: hi and lo parts as packed halves
+                                float h2[2], l2[2];
+                                split_h2(v[0], v[1], h2[0], l2[0]); split_h2(v[2], v[3], h2[1], l2[1]);
+                                x.tmem_st2(tid, P::TM_H16 + k * P::XH + 2 * g, h2);
+                                x.tmem_st2(tid, P::TM_H16 + k * P::XH + P::C2H / 2 + 2 * g, l2);
+                            } else if constexpr (P::RF16) {  // the MMA operand copy: packed halves, two channels per column
                                 const float h2[2] = {pack_h2(v[0], v[1]), pack_h2(v[2], v[3])};
-                                x.tmem_st2(tid, P::TM_H16 + k * (P::C2H / 2) + 2 * g, h2);
+                                x.tmem_st2(tid, P::TM_H16 + k * P::XH + 2 * g, h2);
                             }
                         }
                     }
@@ -724,9 +801,12 @@ template <class P> struct Frame {
                         const int g = half * GH16 + i;
                         if (g < NG16) {
                             const float z2[2] = {0.f, 0.f};
-                            x.tmem_st2(tid, P::TM_XT + 2 * g, z2);
-                            if (g >= NGP)
-                                for (int k = 0; k < C::K; ++k) x.tmem_st2(tid, P::TM_H16 + k * (P::C2H / 2) + 2 * g, z2);
+#pragma unroll
+                            for (int part = 0; part < P::NPART; ++part) {
+                                x.tmem_st2(tid, P::TM_XT + part * (P::C2H / 2) + 2 * g, z2);
+                                if (g >= NGP)
+                                    for (int k = 0; k < C::K; ++k) x.tmem_st2(tid, P::TM_H16 + k * P::XH + part * (P::C2H / 2) + 2 * g, z2);
+                            }
                         }
                     }
                 }
@@ -738,7 +818,7 @@ template <class P> struct Frame {
                     const int s = idx / (C::K * P::C2P * F2), r = idx % (C::K * P::C2P * F2);
                     const int k = r / (P::C2P * F2), c = (r / F2) % P::C2P, f = r % F2, gs = x.s0 + s;
                     float v = 0.f;
-                    if (c < C2 && gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f];
+                    if (c < C2 && gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
                     sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)] = v;
                 }
             });
@@ -759,10 +839,7 @@ template <class P> struct Frame {
                             float v[4];
                             x.tmem_ld4(tid, P::TM_H + k * P::C2P + 4 * g, v);
                             x.tmem_ld_wait();
-                            if (live) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + 4 * g + e) * F2 + f] = v[e];
-                            }
+                            if (live) st4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * g, mk4(v[0], v[1], v[2], v[3]));
                         }
                     }
                 }
@@ -773,7 +850,7 @@ template <class P> struct Frame {
                     const int s = idx / (C::K * C2 * F2), r = idx % (C::K * C2 * F2);
                     const int k = r / (C2 * F2), c = (r / F2) % C2, f = r % F2, gs = x.s0 + s;
                     if (gs < prm.n_streams)
-                        prm.state[(size_t)gs * C::STATE + 2 * C::CL + ((size_t)k * C2 + c) * F2 + f] = sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)];
+                        prm.state[st_h(prm, k, gs) + f * C2 + c] = sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)];
                 }
             });
         }
@@ -784,9 +861,8 @@ template <class P> struct Frame {
                     int s = idx / C::CL, i = idx % C::CL;
                     int gs = x.s0 + s;
                     if (gs < prm.n_streams) {
-                        float* st = prm.state + (size_t)gs * C::STATE;
-                        if (prm.mode != MODE_ISTFT) st[i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
-                        if (prm.mode != MODE_STFT) st[C::CL + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
+                        if (prm.mode != MODE_ISTFT) prm.state[st_cache(prm, 0, gs) + i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
+                        if (prm.mode != MODE_STFT) prm.state[st_cache(prm, 1, gs) + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
                     }
                 }
             });
@@ -884,7 +960,12 @@ template <class P> struct Frame {
             if constexpr (P::H_TMEM) {           // the MMAs read x from tensor memory: this thread's lane, columns TM_XT + c ..
                 // (warp-collective: also executed, with garbage, by the lanes past the last position)
                 static_assert(W == 4, "TMEM operand stores cover 4 channels");
-                if constexpr (P::RF16) {
+                if constexpr (P::SPLIT) {
+                    float r[2], l[2];
+                    split_h2(o[0], o[1], r[0], l[0]); split_h2(o[2], o[3], r[1], l[1]);
+                    x.tmem_st2_row(p, P::TM_XT + c / 2, r);
+                    x.tmem_st2_row(p, P::TM_XT + P::C2H / 2 + c / 2, l);
+                } else if constexpr (P::RF16) {
                     const float r[2] = {pack_h2(o[0], o[1]), pack_h2(o[2], o[3])};
                     x.tmem_st2_row(p, P::TM_XT + c / 2, r);       // p is the calling thread's own lane
                 } else {
@@ -905,19 +986,25 @@ template <class P> struct Frame {
         // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
         x.phase(PH_LIN_PRE, [&](int tid) {
             // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
-            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, !P::H16, P::H16>(x, tid, ci,
+            constexpr int XFMT = P::SPLIT ? 3 : (P::BF16 ? 2 : (P::H16 ? 1 : 0));
+            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, !P::H16, XFMT>(x, tid, ci,
                 [&](int l) { return enc_last + (P::H16 ? act_off16(4 * (l / S), l % S, 0) : act_off(4 * (l / S), l % S, 0)); }, S * 4,
                 [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
                 float* yr = Y1 + (P::H16 ? rf_off16(4 * (l / S), l % S, 0) : rf_off(4 * (l / S), l % S, 0));
 #pragma unroll
                 for (int j = 0; j < P::LinPreT::NO; ++j)
                     if (o0 + j < F2) {
-                        if constexpr (P::H16) st2(yr + (o0 + j) * S * 4, mk2(pack_h2(a[0][j], a[1][j]), pack_h2(a[2][j], a[3][j])));
+                        if constexpr (P::SPLIT) {
+                            f2 h, lo;
+                            split_h2(a[0][j], a[1][j], h.x, lo.x); split_h2(a[2][j], a[3][j], h.y, lo.y);
+                            st2(yr + (o0 + j) * S * 4, h); st2(yr + P::Y1T1 + (o0 + j) * S * 4, lo);
+                        } else if constexpr (P::H16) st2(yr + (o0 + j) * S * 4, mk2(pack_h2<P::BF16>(a[0][j], a[1][j]), pack_h2<P::BF16>(a[2][j], a[3][j])));
                         else st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
                     }
-            });
+            }, P::ACT1);
             if constexpr (P::H16 && P::C1P > C1) {      // the slab that pads the channels to a whole k-step (scratch: re-zeroed every hop)
-                for (int idx = tid; idx < P::RSLOTS; idx += NT) st4(Y1 + (P::C1P / 8 - 1) * RSLABF + idx * 4, mk4(0.f, 0.f, 0.f, 0.f));
+                for (int idx = tid; idx < P::NPART * P::RSLOTS; idx += NT)
+                    st4(Y1 + (idx / P::RSLOTS) * P::Y1T1 + (P::C1P / 8 - 1) * RSLABF + (idx % P::RSLOTS) * 4, mk4(0.f, 0.f, 0.f, 0.f));
             }
         });
         ci += P::LinPreT::NCHUNK;
@@ -932,7 +1019,7 @@ template <class P> struct Frame {
 #pragma unroll
                 for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
                 store_x(p, c, o, valid, wt, WTag<1>{});
-            });
+            }, P::Y1T1);
             if constexpr (P::H_TMEM) x.tmem_st_wait();
         });
         ci += P::TRfPre::NCHUNK;
@@ -941,14 +1028,18 @@ template <class P> struct Frame {
         for (int k = 0; k < C::K; ++k) {
             const auto ab = A.blk(k);
             float* H = P::H_RES ? x.sm + P::SM_HST + k * XTS : AB + P::O_HB_T;
-            const size_t hoff = 2 * C::CL + (size_t)k * C2 * F2;
             if constexpr (!P::H_RES) {
                 x.phase(PH_HLOAD, [&](int tid) {
-                    for (int idx = tid; idx < S * C2P * F2; idx += NT) {
-                        const int s = idx / (C2P * F2), r = idx % (C2P * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
-                        float v = 0.f;
-                        if (c < C2 && gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + hoff + c * F2 + f];
-                        H[rf_off(c, s, f)] = v;
+                    // one float4 = 4 channels of one (stream, frequency): 8 consecutive threads take 8 frequencies of the same channel
+                    // group (conflict-free 16-byte shared-memory stores), the next 8 the next group (64 contiguous bytes per row of h)
+                    constexpr int NC4 = C2P / 4;
+                    static_assert(F2 % 8 == 0, "per-hop state staging assumes F2 % 8 == 0");
+                    for (int idx = tid; idx < S * NC4 * F2; idx += NT) {
+                        const int s = idx / (NC4 * F2), r = idx % (NC4 * F2);
+                        const int f = (r % 8) + 8 * (r / (8 * NC4)), c4 = (r / 8) % NC4, gs = x.s0 + s;
+                        f4 v = mk4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * c4 < C2 && gs < prm.n_streams) v = ldg4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * c4);
+                        st4(H + rf_off(4 * c4, s, f), v);
                     }
                 });
             }
@@ -961,7 +1052,8 @@ template <class P> struct Frame {
                 const auto dx = x.make_desc(XT, RSLABF), dh = x.make_desc(H, RSLABF);
                 constexpr int TM_HK0 = P::TM_H;
                 const int tm_h = TM_HK0 + k * P::C2P;                  // this block's fp32 state columns (H_TMEM)
-                const int tm_ha = P::RF16 ? P::TM_H16 + k * (P::C2H / 2) : tm_h;      // ... and the columns the MMAs read
+                const int tm_ha = P::RF16 ? P::TM_H16 + k * P::XH : tm_h;             // ... and the columns the MMAs read
+                static_assert(!P::SPLIT || L::MERGED, "split variants use the merged GRU tile");
                 tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
                     if constexpr (L::MERGED) {
                         // one MMA per (input, k-step): h tiles first (k-step 0 overwrites all four accumulator blocks, zeroing NX), then x
@@ -971,7 +1063,12 @@ template <class P> struct Frame {
                         const int n = first ? 4 * NPG : 3 * NPG;
                         const auto wsub = x.desc_add(wd, row0 * 4);
                         if constexpr (P::H_TMEM) {
-                            x.template mma_ts<P::RF16>(tid, (inp == 0 ? P::TM_XT : tm_ha) + 8 * j, wsub, n, row0, !first, P::RSLOTS);
+                            const int a_col = (inp == 0 ? P::TM_XT : tm_ha) + 8 * j;
+                            x.template mma_ts<P::RF16>(tid, a_col, wsub, n, row0, !first, P::RSLOTS);
+                            if constexpr (P::SPLIT) {      // lo * hi, hi * lo
+                                x.template mma_ts<true>(tid, a_col + P::C2H / 2, wsub, n, row0, true, P::RSLOTS);
+                                x.template mma_ts<true>(tid, a_col, x.desc_add(wsub, L::TILE1), n, row0, true, P::RSLOTS);
+                            }
                         } else {
                             const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
                             x.template mma<M64>(tid, a, wsub, n, row0, !first, P::RSLOTS);
@@ -1017,11 +1114,7 @@ template <class P> struct Frame {
                     if (valid) store_pt<W>(hp, hn);        // rows past the last position compute on garbage and store nothing
                     if constexpr (!P::H_RES) {
                         const int gs = x.s0 + p % S;
-                        if (valid && gs < prm.n_streams) {
-                            float* gp = prm.state + (size_t)gs * C::STATE + hoff + (size_t)c * F2 + p / S;
-#pragma unroll
-                            for (int e = 0; e < W; ++e) gp[e * F2] = hn[e];
-                        }
+                        if (valid && gs < prm.n_streams) store_pt<W>(prm.state + st_h(prm, k, gs) + (p / S) * C2 + c, hn);
                     }
                 };
                 if constexpr (P::H_TMEM) {
@@ -1050,7 +1143,12 @@ template <class P> struct Frame {
                                 float hn[4];
                                 gru_gates(4 * g, vr[b], vz[b], vx[b], vh[b], vo[b], hn, WTag<4>{});
                                 x.tmem_st4(tid, tm_h + 4 * g, hn);
-                                if constexpr (P::RF16) {
+                                if constexpr (P::SPLIT) {
+                                    float h2[2], l2[2];
+                                    split_h2(hn[0], hn[1], h2[0], l2[0]); split_h2(hn[2], hn[3], h2[1], l2[1]);
+                                    x.tmem_st2(tid, tm_ha + 2 * g, h2);
+                                    x.tmem_st2(tid, tm_ha + P::C2H / 2 + 2 * g, l2);
+                                } else if constexpr (P::RF16) {
                                     const float h2[2] = {pack_h2(hn[0], hn[1]), pack_h2(hn[2], hn[3])};
                                     x.tmem_st2(tid, tm_ha + 2 * g, h2);
                                 }
@@ -1135,7 +1233,7 @@ template <class P> struct Frame {
                     store_x(p, c, o, valid, wt, WTag<0>{});
                 };
                 if constexpr (P::H_TMEM) {
-                    rf_layer_ts<typename P::TFc>(x, tid, ci, P::RF16 ? P::TM_H16 + k * (P::C2H / 2) : P::TM_H + k * P::C2P, epi);
+                    rf_layer_ts<typename P::TFc>(x, tid, ci, P::RF16 ? P::TM_H16 + k * P::XH : P::TM_H + k * P::C2P, epi, P::C2H / 2);
                     x.tmem_st_wait();
                 } else {
                     rf_layer<typename P::TFc, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
@@ -1151,7 +1249,7 @@ template <class P> struct Frame {
                     // the bias is all zeros in every shipped config (attn_bias: False): the packer says so and the epilogue then
                     // is a plain store (uniform branch, taken outside the unrolled group loop)
                     auto run = [&](auto epi) {
-                        if constexpr (P::H_TMEM) rf_layer_ts<typename P::TQkv>(x, tid, ci, P::TM_XT, epi);
+                        if constexpr (P::H_TMEM) rf_layer_ts<typename P::TQkv>(x, tid, ci, P::TM_XT, epi, P::C2H / 2);
                         else rf_layer<typename P::TQkv, M64>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * RSLABF); }, epi);
                     };
                     if (ldg(aux + A.flags) != 0.f) {
@@ -1178,8 +1276,11 @@ template <class P> struct Frame {
                     auto att_off16 = [&](int c, int s, int f) { return (c >> 3) * (RSLABF * 2) + (f * S + s) * 8 + (c & 7); };
                     if (hg == 0) {
                         if constexpr (P::RF16) {
-                            for (int idx = tid; idx < (P::C2H - C2) * P::RSLOTS; idx += NT)
-                                sth(ATT, att_off16(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S), 0.f);
+                            for (int idx = tid; idx < (P::C2H - C2) * P::RSLOTS; idx += NT) {
+                                const int o = att_off16(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S);
+                                sth(ATT, o, 0.f);
+                                if constexpr (P::SPLIT) sth(ATT + XTS, o, 0.f);
+                            }
                         } else {
                             for (int idx = tid; idx < (C2P - C2) * P::RSLOTS; idx += NT)
                                 ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
@@ -1247,7 +1348,11 @@ template <class P> struct Frame {
 #pragma unroll
                         for (int d = 0; d < HD; ++d) {
                             const float ov = ((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv;
-                            if constexpr (P::RF16) sth(ATT, att_off16((hg * P::HG + hh) * HD + d, s, i), ov);
+                            if constexpr (P::SPLIT) {       // hi part, and the remainder in the XT region (unused: x lives in tensor memory)
+                                const int o = att_off16((hg * P::HG + hh) * HD + d, s, i);
+                                sth(ATT, o, ov);
+                                sth(ATT + XTS, o, ov - rnd_h(ov));
+                            } else if constexpr (P::RF16) sth(ATT, att_off16((hg * P::HG + hh) * HD + d, s, i), ov);
                             else ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_pre(ov);
                         }
                     }
@@ -1267,7 +1372,7 @@ template <class P> struct Frame {
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
                     store_x(p, c, o, valid, wt, WTag<0>{});
-                });
+                }, XTS);
                 if constexpr (P::H_TMEM) x.tmem_st_wait();
             });
             ci += P::TFc::NCHUNK;
@@ -1292,7 +1397,7 @@ template <class P> struct Frame {
                         for (int idx = tid; idx < F2 * C2; idx += NT) {
                             const int c = idx % C2, f = idx / C2;
                             prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
-                                P::H_RES ? H[rf_off(c, 0, f)] : prm.state[(size_t)x.s0 * C::STATE + hoff + c * F2 + f];
+                                P::H_RES ? H[rf_off(c, 0, f)] : prm.state[st_h(prm, k, x.s0) + f * C2 + c];
                         }
                     }
                 });
@@ -1438,6 +1543,7 @@ template <class P> struct Frame {
                 float g = powf(mag, comp_e);
                 SPEC[spec_off(0, s, k)] = re * g;
                 SPEC[spec_off(1, s, k)] = im * g;
+                if constexpr (P::SPLIT) spec_h16(SPEC, s, k, re * g, im * g);
             }
         };
         // ================= front end =================
@@ -1489,6 +1595,7 @@ template <class P> struct Frame {
                     float g = powf(mag, comp_e);
                     SPEC[spec_off(0, s, k)] = re * g;
                     SPEC[spec_off(1, s, k)] = im * g;
+                    if constexpr (P::SPLIT) spec_h16(SPEC, s, k, re * g, im * g);
                 }
             });
         }
@@ -1523,15 +1630,21 @@ template <class P> struct Frame {
                 if (i == 0) {
                     x.phase(PH_ENC_PRE, [&](int tid) {
                         if (halo) zero_halo(dst, tid);
-                        const auto a0 = x.make_desc(src + S * 4, SLABF);
-                        tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi);
+                        if constexpr (P::SPLIT) {
+                            // fp16 copy of the spectrum: [hi slab | zero slab | lo slab | zero slab] (K = 8 virtual channels padded to 16)
+                            const auto a0 = x.make_desc(SPEC + P::O_SPECH + S * 4, SLABF);
+                            tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi, 2 * SLABF);
+                        } else {
+                            const auto a0 = x.make_desc(src + S * 4, SLABF);
+                            tc_layer<typename P::TEncPre>(x, tid, ci, [&](int) { return a0; }, S, epi);
+                        }
                     });
                     ci += P::TEncPre::NCHUNK;
                 } else {
                     x.phase(PH_ENC, [&](int tid) {
                         if (halo) zero_halo(dst, tid);
                         const auto a0 = x.make_desc(src + S * 4, SLABF);
-                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ACT1);
                     });
                     ci += P::TConv3::NCHUNK;
                 }
@@ -1590,7 +1703,7 @@ template <class P> struct Frame {
                     for (int idx = tid; idx < S * C2 * F2; idx += NT) {
                         int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
                         float v = 0.f;
-                        if (gs < prm.n_streams) v = prm.state[(size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + r];
+                        if (gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
                         HB[c * PR + s * F2P + f] = v;
                     }
                 });
@@ -1651,8 +1764,10 @@ template <class P> struct Frame {
                                         hn[j] = (1.0f - z) * nn + z * ho[j];
                                     }
                                     store_pt<PT>(G + c * PR + g.xoff, hn);
-                                    if (gs < prm.n_streams)
-                                        store_pt<PT>(prm.state + (size_t)gs * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + c * F2 + g.f, hn);
+                                    if (gs < prm.n_streams) {
+#pragma unroll
+                                        for (int j = 0; j < PT; ++j) prm.state[st_h(prm, k, gs) + (g.f + j) * C2 + c] = hn[j];
+                                    }
                                 }
                             }
                         }
@@ -1752,7 +1867,7 @@ template <class P> struct Frame {
                     x.phase(PH_DBG, [&](int tid) {       // h_new of stream 0, oracle layout [F2][C2]
                         for (int idx = tid; idx < F2 * C2; idx += NT)
                             prm.dbg[TAP_BLK + (k * 3 + 2) * F2 * C2 + idx] =
-                                prm.state[(size_t)x.s0 * C::STATE + 2 * C::CL + (size_t)k * C2 * F2 + (idx % C2) * F2 + idx / C2];
+                                prm.state[st_h(prm, k, x.s0) + idx];
                     });
                 }
             }
@@ -1768,15 +1883,21 @@ template <class P> struct Frame {
 #pragma unroll
                     for (int j = 0; j < P::LinPostT::NO; ++j)
                         if (o0 + j < F1) {
-                            if constexpr (P::H16) st2(zr + (o0 + j) * S * 4, mk2(pack_h2(a[0][j], a[1][j]), pack_h2(a[2][j], a[3][j])));
+                            if constexpr (P::SPLIT) {
+                                f2 h, lo;
+                                split_h2(a[0][j], a[1][j], h.x, lo.x); split_h2(a[2][j], a[3][j], h.y, lo.y);
+                                st2(zr + (o0 + j) * S * 4, h); st2(zr + P::ZB1 + (o0 + j) * S * 4, lo);
+                            } else if constexpr (P::H16) st2(zr + (o0 + j) * S * 4, mk2(pack_h2<P::BF16>(a[0][j], a[1][j]), pack_h2<P::BF16>(a[2][j], a[3][j])));
                             else st4(zr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
                         }
                 });
                 // zero the channels that pad C2 to a whole k-step (the scratch region is reused every frame)
-                if constexpr (P::H16) {
-                    for (int idx = tid; idx < ((P::C2Z - C2) / 4) * S * F1; idx += NT) {        // one 8-byte unit = 4 channels
-                        const int c = C2 + 4 * (idx / (S * F1)), r = idx % (S * F1);
-                        st2(Zb + act_off16(c, r % S, r / S), mk2(0.f, 0.f));
+                if constexpr (P::H16 && P::C2Z == C2) {
+                } else if constexpr (P::H16) {
+                    for (int idx = tid; idx < P::NPART * ((P::C2Z - C2) / 4) * S * F1; idx += NT) {        // one 8-byte unit = 4 channels
+                        const int part = idx / (((P::C2Z - C2) / 4) * S * F1), i2 = idx % (((P::C2Z - C2) / 4) * S * F1);
+                        const int c = C2 + 4 * (i2 / (S * F1)), r = i2 % (S * F1);
+                        st2(Zb + part * P::ZB1 + act_off16(c, r % S, r / S), mk2(0.f, 0.f));
                     }
                 } else {
                     for (int idx = tid; idx < (P::C2P - C2) * S * F1; idx += NT) {
@@ -1790,7 +1911,7 @@ template <class P> struct Frame {
             x.phase(PH_RF_POST, [&](int tid) {
                 zero_halo(W1, tid);          // W1 was FFT / RNNFormer scratch
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
-                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1);
             });
             ci += P::TRfPost::NCHUNK;
         } else {
@@ -1833,14 +1954,14 @@ template <class P> struct Frame {
                     if (i == 0 || sk >= P::SKIP_SMEM) zero_halo(W0, tid);
                     const auto ax = x.make_desc(W1 + S * 4, SLABF), as = x.make_desc(skip + S * 4, SLABF);
                     tc_layer<typename P::TPwCat>(x, tid, ci, [&](int j) {
-                        return j < P::C1P / P::KEC ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - P::C1P / P::KEC) * SLABF); }, S, epi);
+                        return j < P::C1P / P::KEC ? x.desc_add(ax, 2 * j * SLABF) : x.desc_add(as, 2 * (j - P::C1P / P::KEC) * SLABF); }, S, epi, P::ACT1);
                 });
                 ci += P::TPwCat::NCHUNK;
                 if (i < E) {
                     TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};      // rf_post zeroed W1's halos this frame
                     x.phase(PH_DEC, [&](int tid) {
                         const auto a0 = x.make_desc(W0 + S * 4, SLABF);
-                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2, P::ACT1);
                     });
                     ci += P::TConv3::NCHUNK;
                     if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);
@@ -1885,7 +2006,7 @@ template <class P> struct Frame {
             TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};     // the mask is not a conv input: no halo
             x.phase(PH_CONVT, [&](int tid) {
                 const auto a0 = x.make_desc(W0 + S * 4, SLABF);
-                tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi);
+                tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ACT1);
             });
             ci += P::TConvT::NCHUNK;
         } else {

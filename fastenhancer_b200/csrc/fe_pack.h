@@ -110,14 +110,20 @@ template <class P> class Packer {
         for (int tile = 0; tile < L::NTILE; ++tile) {
             const int t = tile / L::NKS, j = tile % L::NKS;
             if constexpr (L::KE == 16) {
+                // hi parts, then (split layers) the tile of the remainders w - fp16(w)
                 uint16_t* h = reinterpret_cast<uint16_t*>(&blob_[off_ + (long)tile * L::TILE]);
+                uint16_t* lo = reinterpret_cast<uint16_t*>(&blob_[off_ + (long)tile * L::TILE + L::TILE1]);
                 for (int kc2 = 0; kc2 < 2; ++kc2)
                     for (int n = 0; n < L::NP; ++n)
                         for (int e = 0; e < 8; ++e) {
                             const int k = 16 * j + 8 * kc2 + e;
-                            h[(kc2 * L::NP + n) * 8 + e] = f32_to_f16_bits((n < L::N && k < L::K) ? scale * w(n, k, t) : 0.f);
+                            const float v = (n < L::N && k < L::K) ? scale * w(n, k, t) : 0.f;
+                            const uint16_t hb = f32_to_h16_bits<P::BF16>(v);
+                            h[(kc2 * L::NP + n) * 8 + e] = hb;
+                            if constexpr (L::PARTS == 2) lo[(kc2 * L::NP + n) * 8 + e] = f32_to_f16_bits(v - f16_bits_to_f32(hb));
                         }
             } else {
+                static_assert(L::PARTS == 1, "split layers have 16-bit operands");
                 for (int kc2 = 0; kc2 < 2; ++kc2)
                     for (int n = 0; n < L::NP; ++n)
                         for (int e = 0; e < 4; ++e) {
@@ -140,8 +146,12 @@ template <class P> class Packer {
             float* t = &blob_[off_ + (long)tile * L::TILE];
             // element (k-chunk kc2, row n of a part with `rows` rows starting `base` floats into the tile, e) <- value
             auto put = [&](int base, int rows, int kc2, int n, int e, float v) {
-                if constexpr (L::KE == 16) reinterpret_cast<uint16_t*>(t + base)[(kc2 * rows + n) * 8 + e] = f32_to_f16_bits(v);
-                else t[base + (kc2 * rows + n) * 4 + e] = tf32_rna(v);
+                if constexpr (L::KE == 16) {
+                    const uint16_t hb = f32_to_f16_bits(v);
+                    reinterpret_cast<uint16_t*>(t + base)[(kc2 * rows + n) * 8 + e] = hb;
+                    if constexpr (L::PARTS == 2)
+                        reinterpret_cast<uint16_t*>(t + L::TILE1 + base)[(kc2 * rows + n) * 8 + e] = f32_to_f16_bits(v - f16_bits_to_f32(hb));
+                } else t[base + (kc2 * rows + n) * 4 + e] = tf32_rna(v);
             };
             if constexpr (L::MERGED) {
                 // h tiles first; rows [ W_in | W_r | W_z | W_hn ], the set that does not belong to this input is zero
@@ -285,7 +295,7 @@ public:
             }
         };
         if constexpr (P::TC) {
-            tc<typename P::TEncPre>(w_enc_pre, HS);
+            tc<typename P::TEncPre>([&](int co, int v, int t) { return v < 8 ? w_enc_pre(co, v, t) : 0.f; }, HS);
             for (int i = 0; i < C::E; ++i)
                 tc<typename P::TConv3>([&](int co, int ci, int t) { return ci < C1 ? cw.enc_w[i][(co * C1 + ci) * 3 + t] : 0.f; }, HS);
             rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });

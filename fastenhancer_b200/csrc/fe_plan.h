@@ -120,14 +120,18 @@ struct RowGemm {
 // NP = N rounded up to 16, zero rows / zero k beyond the real sizes, values pre-rounded to TF32.
 // ----------------------------------------------------------------------------------------------
 // KE = 16: kind::f16 -- the operands are halves, 8 per 16-byte row, so a tile [2][NP][8 halves] has the same bytes and covers K = 16.
-template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_, int TMEMC_ = 256, int KE_ = 8>
+// PARTS = 2 (split variants): every tile is followed by the tile of the weights' low parts (w - fp16(w) as fp16), and the layer
+// issues three MMAs per tile -- (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) -- for an fp32-accurate product.
+template <int NPOS_, int N_, int K_, int TAPS_, int CHUNK_, int TMEMC_ = 256, int KE_ = 8, int PARTS_ = 1>
 struct TcGemm {
+    static constexpr int PARTS = PARTS_;
     static constexpr int NPOS = NPOS_, N = N_, K = K_, TAPS = TAPS_;   // TAPS doubles as "weight sets" for the GRU (6)
     static constexpr int KE = KE_;                     // contraction length of one MMA
     static constexpr int NP = round_up(N, 16), KP = round_up(K, KE);
     static constexpr int NKS = KP / KE;                // k-steps per tap
     static constexpr int NTILE = TAPS * NKS;
-    static constexpr int TILE = NP * 8;                // floats per tile (32 bytes per output row)
+    static constexpr int TILE1 = NP * 8;               // floats per tile part (32 bytes per output row)
+    static constexpr int TILE = TILE1 * PARTS;
     static_assert(TILE <= CHUNK_, "one weight tile must fit a ring chunk");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
     static constexpr int NCHUNK = cdiv(NTILE, TPC);
@@ -148,9 +152,9 @@ struct TcGemm {
 // Split form (M, L): per (input x | h, k-step) one tile [ R|Z part: [2][2 NPG][4] | N part: [2][NPG][4] ], i.e. two MMAs: N = 2 NPG into
 // the R|Z accumulator columns (x and h accumulate together) and N = NPG into NX or NH; x tiles first; columns [ R | Z | NX | NH ].
 // KE = 16: fp16 operands (x and h as packed halves), tiles [2][rows][8 halves].
-template <int NPOS_, int C2_, int CHUNK_, int KE_ = 8>
+template <int NPOS_, int C2_, int CHUNK_, int KE_ = 8, int PARTS_ = 1>
 struct TcGru {
-    static constexpr int NPOS = NPOS_, N = C2_, K = C2_, KE = KE_;
+    static constexpr int NPOS = NPOS_, N = C2_, K = C2_, KE = KE_, PARTS = PARTS_;
     static constexpr int NPG = round_up(C2_, 16), KP = round_up(C2_, KE_), NKS = KP / KE_;
 #ifndef FE_GRU_MERGE
 #define FE_GRU_MERGE 1
@@ -158,7 +162,8 @@ struct TcGru {
     static constexpr bool MERGED = FE_GRU_MERGE && 4 * NPG <= 256;
     static constexpr int NP = MERGED ? 4 * NPG : 2 * NPG;              // rows (LBO) of the tile / of its R|Z part
     static constexpr int NTILE = 2 * NKS;              // MERGED: h tiles, then x tiles; split: x tiles, then h tiles
-    static constexpr int TILE = (MERGED ? 4 : 3) * NPG * 8;
+    static constexpr int TILE1 = (MERGED ? 4 : 3) * NPG * 8;
+    static constexpr int TILE = TILE1 * PARTS;
     static constexpr int COL_NX = MERGED ? 0 : 2 * NPG, COL_R = MERGED ? NPG : 0, COL_Z = MERGED ? 2 * NPG : NPG, COL_NH = 3 * NPG;
     static_assert(TILE <= CHUNK_ && NP <= 256, "GRU tile");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
@@ -209,14 +214,21 @@ template <class C, int S> struct TuneBase {
 template <class C, int S> struct Tune : TuneBase<C, S> {};
 
 // PREC: 0 = everything on the fp32 FMA pipe; 1 = contractions on tcgen05 with TF32 operands; 2 = as 1, with the conv section's
-// activations and weights stored as fp16 (kind::f16: 11-bit significand like TF32, K = 16 per MMA, half the shared memory).
+// activations and weights stored as fp16 (kind::f16: 11-bit significand like TF32, K = 16 per MMA, half the shared memory);
+// 3 = as 2 with bfloat16 instead of fp16 in the conv section and a TF32 RNNFormer ("bf16 conv / fp32 GRU", BASELINE config 3);
+// 4 = fp32-accurate tensor-core mode: every MMA operand is stored as two fp16 parts, hi = fp16(v) and lo = fp16(v - hi)
+//     (22 significand bits together), and every product is three kind::f16 MMAs into the same fp32 accumulator:
+//     hi*hi + lo*hi + hi*lo (the dropped lo*lo term is ~2^-22 relative).  Same shared-memory footprint as the TF32 variant.
 template <class C, int S_, int PREC_ = 0>
 struct Plan {
     using Cf = C;
     static constexpr int S = S_;
     static constexpr int PREC = PREC_;
     static constexpr bool TC = PREC_ != 0;             // conv-type contractions on tcgen05 instead of the FMA pipe
-    static constexpr bool H16 = PREC_ == 2;            // conv-section operands in fp16
+    static constexpr bool H16 = PREC_ >= 2;            // conv-section operands are 16-bit
+    static constexpr bool BF16 = PREC_ == 3;           // ... bfloat16 instead of fp16
+    static constexpr bool SPLIT = PREC_ == 4;          // ... stored as hi + lo fp16 parts
+    static constexpr int NPART = SPLIT ? 2 : 1;
     static constexpr int CG = H16 ? 8 : 4;             // channels per 16-byte row of a conv-section operand buffer
     static constexpr int KEC = H16 ? 16 : 8;           // contraction length of one conv-section MMA
     static constexpr int C1P = H16 ? round_up(C::C1, 16) : C::C1;                 // conv channels padded to a k-step
@@ -232,9 +244,14 @@ struct Plan {
     static constexpr int SLOTS = (C::F1 + 2) * S;
     static constexpr int SLABF = SLOTS * 4;            // floats per 4-channel slab
     static constexpr int C2P = round_up(C::C2, 8);     // rf_post conv input channels padded to a k-step
-    static constexpr int ACT = TC ? (C1P / CG) * SLABF : C::C1 * CP1 + 4;
-    static constexpr int SPECF = TC ? 2 * SLABF : 8 * CP1 + 4;   // compressed spectrum: 8 virtual channels (c*4+q), fp32 in every variant
-    static constexpr int ZBF = TC ? (C2Z / CG) * SLABF : C::C2 * CP1;   // rf_post linear output
+    static constexpr int ACT1 = (C1P / CG) * SLABF;    // one part of a conv-section operand buffer (TC variants); the low parts follow at + ACT1
+    static constexpr int ACT = TC ? NPART * ACT1 : C::C1 * CP1 + 4;
+    // compressed spectrum: 8 virtual channels (c*4+q), fp32 in every variant; split variants add an fp16 operand copy for enc_pre:
+    // [hi slab | zero slab | lo slab | zero slab] of 8 halves per slot (a zero slab is the second k-chunk of a part: K = 8 padded to 16)
+    static constexpr int SPECF = TC ? 2 * SLABF + (SPLIT ? 4 * SLABF : 0) : 8 * CP1 + 4;
+    static constexpr int O_SPECH = 2 * SLABF;
+    static constexpr int ZB1 = (C2Z / CG) * SLABF;
+    static constexpr int ZBF = TC ? NPART * ZB1 : C::C2 * CP1;   // rf_post linear output
     static_assert(C::C1 % 8 == 0, "C1 must be a multiple of 8");
     static_assert(2 * SLABF <= ACT, "the fp32 mask (two 4-channel slabs) must fit an activation buffer");
     // ---- RNNFormer geometry: [C2][S][F2P] channel-major, F2P = 4*odd ----
@@ -246,10 +263,10 @@ struct Plan {
     static constexpr int hg_tc() {
         for (int hg = C::NH; hg > 1; hg /= 2) {
             if (C::NH % hg) continue;
-            const int act = (C1P / CG) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
+            const int act = NPART * (C1P / CG) * (C::F1 + 2) * S * 4, xts = (round_up(C::C2, 8) / 4) * S * C::F2 * 4;
             const int f2p = ((C::F2 / 4) % 2 == 1) ? C::F2 : C::F2 + 4;
             const int qn = hg * 3 * round_up(C::HD, 4), qrow = ((qn / 4) % 2 == 1) ? qn : qn + 4;
-            const int need1 = cmax(S * C::F2 * qrow + xts, (C1P / CG) * S * C::F2 * 4) + xts;
+            const int need1 = cmax(S * C::F2 * qrow + xts, NPART * (C1P / CG) * S * C::F2 * 4) + xts;
             if (f2p < 0) return 0;
             const int rest = 2 * (C::F1 + 2) * S * 4 + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
             if (cmax(2, cdiv(need1, act)) * act + rest <= 227 * 256) return hg;
@@ -266,17 +283,18 @@ struct Plan {
     static constexpr int QROW_PAD = ((QN / 4) % 2 == 1) ? QN : QN + 4;
     // ... unless that padding alone would cost another work buffer (16 kHz B: 192 floats over)
     static constexpr int rf_need2(int qrow) {      // [QKV | ATT] or Y1T, then XT (padded channels), then XR (real channels only)
-        return cmax(S * C::F2 * qrow + (round_up(C::C2, 8) / 4) * S * C::F2 * 4, (C1P / CG) * S * C::F2 * 4) +
+        return cmax(S * C::F2 * qrow + (round_up(C::C2, 8) / 4) * S * C::F2 * 4, NPART * (C1P / CG) * S * C::F2 * 4) +
                (round_up(C::C2, 8) / 4) * S * C::F2 * 4 + (C::C2 / 4) * S * C::F2 * 4;
     }
-    static constexpr int act_tc() { return (C1P / CG) * (C::F1 + 2) * S * 4; }
+    static constexpr int act_tc() { return NPART * (C1P / CG) * (C::F1 + 2) * S * 4; }
     static constexpr int QROW = (cdiv(rf_need2(QROW_PAD), act_tc()) > cdiv(rf_need2(QN), act_tc())) ? QN : QROW_PAD;
     static constexpr int QKVS = TC ? S * C::F2 * QROW : 3 * C::HD * HG * PR;
     // ---- RNNFormer tensor-core geometry ("GeoR", TC variants): [C2P/4][RSLOTS][4], slot = f2*S + s ----
     static constexpr int RSLOTS = S * C::F2;
     static constexpr int RSLABF = RSLOTS * 4;
     static constexpr int XTS = (C2P / 4) * RSLABF;     // one RNNFormer activation in GeoR (x, h, attention output)
-    static constexpr int Y1TS = (C1P / CG) * RSLABF;   // rf_pre linear output in GeoR (fp16 in the H16 variants)
+    static constexpr int Y1T1 = (C1P / CG) * RSLABF;
+    static constexpr int Y1TS = NPART * Y1T1;          // rf_pre linear output in GeoR (16-bit in the H16 variants; low parts at + Y1T1)
     static constexpr int NPG = round_up(C::C2, 16);    // accumulator columns per GRU gate
     static_assert(RSLOTS <= 128, "RNNFormer positions exceed one M tile: lower S");
     // RNNFormer MMAs with M = 64 when the positions fit: a 64-row accumulator occupies 16 lanes in each of the four TMEM lane
@@ -306,6 +324,7 @@ struct Plan {
     static constexpr int O_Y1 = 0;                     // rf_pre linear output
     static constexpr int O_Z = 0;                      // rf_post linear output
     static_assert(TC || XRS + cmax(XRS, QKVS) <= O_XR, "RNNFormer scratch does not fit: lower Tune::HG");
+    static_assert(!SPLIT || XT_COPY, "split variants keep the lo parts of the attention output in the (otherwise unused) XT region");
     static_assert(!TC || (QKVS <= O_ATT_T && Y1TS <= O_XT && Y1TS <= (NWORK - 1) * ACT), "RNNFormer tensor-core scratch does not fit");
     static_assert(TC || (C::C1 * PR <= O_XR && C::C1 * PR <= (NWORK - 1) * ACT), "rf_pre scratch does not fit");
     static_assert(ZBF <= O_XR, "rf_post scratch does not fit");
@@ -329,13 +348,16 @@ struct Plan {
     // fp16 variants with TMEM operands run the RNNFormer MMAs on fp16 too (RF16): x and h as packed halves (two channels per column,
     // K = 16 per MMA), beside an fp32 master of h for the state update.
     static constexpr int C2H = round_up(C::C2, 16);
+    static constexpr bool WANT_RF16 = H16 && !BF16 && FE_RF16;     // the bf16 variants keep a TF32 RNNFormer ("fp32 GRU")
+    static constexpr int XH = NPART * (C2H / 2);       // columns of one packed-halves operand (x, or the state of one block): hi part, then (split) lo part
     static constexpr int TM_COLS_TF32 = ACCW + C2P * (C::K + 1);
-    static constexpr int TM_COLS_F16 = ACCW + C2H / 2 + C::K * (C2P + C2H / 2);
-    static constexpr bool H_TMEM = TC && FE_HTMEM && !RM64 && ((H16 && FE_RF16) ? TM_COLS_F16 : TM_COLS_TF32) <= 512;
-    static constexpr bool RF16 = H16 && FE_RF16 && H_TMEM;
-    static constexpr int TM_XT = ACCW;                 // x as MMA operand: C2P columns (TF32) or C2H / 2 columns (packed halves)
-    static constexpr int TM_H = ACCW + (RF16 ? C2H / 2 : C2P);     // K x C2P columns: fp32 GRU state, resident for the whole launch
-    static constexpr int TM_H16 = TM_H + C::K * C2P;   // RF16: K x C2H / 2 columns: the state as packed halves (MMA operand)
+    static constexpr int TM_COLS_F16 = ACCW + XH + C::K * (C2P + XH);
+    static constexpr bool H_TMEM = TC && FE_HTMEM && !RM64 && (WANT_RF16 ? TM_COLS_F16 : TM_COLS_TF32) <= 512;
+    static constexpr bool RF16 = WANT_RF16 && H_TMEM;
+    static_assert(!SPLIT || RF16, "split variants exist only where the RNNFormer operands fit tensor memory");
+    static constexpr int TM_XT = ACCW;                 // x as MMA operand: C2P columns (TF32) or XH columns (packed halves)
+    static constexpr int TM_H = ACCW + (RF16 ? XH : C2P);          // K x C2P columns: fp32 GRU state, resident for the whole launch
+    static constexpr int TM_H16 = TM_H + C::K * C2P;   // RF16: K x XH columns: the state as packed halves (MMA operand)
     static constexpr int TM_COLS = RF16 ? TM_COLS_F16 : TM_COLS_TF32;
     // TC variants keep the GRU state of all K blocks on chip across hops: in TMEM, else in shared memory when it fits
     static constexpr bool H_RES = TC && (H_TMEM || SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
@@ -379,19 +401,20 @@ struct Plan {
 
     // tensor-core versions of the conv-type layers (TC variants only)
     // (K = padded input channels: the packer fills the padding with zero weights)
-    using TEncPre = TcGemm<S * C::F1, C::C1, 8, 3, CHUNK>;                            // reads the fp32 spectrum: TF32 in every variant
-    using TConv3 = TcGemm<S * C::F1, C::C1, C1P, 3, CHUNK, 256, KEC>;
-    using TPwCat = TcGemm<S * C::F1, C::C1, 2 * C1P, 1, CHUNK, 256, KEC>;
-    using TConvT = TcGemm<S * C::F1, 8, C1P, 3, CHUNK, 256, KEC>;
-    using TRfPost = TcGemm<S * C::F1, C::C1, C2Z, 1, CHUNK, 256, KEC>;
+    // enc_pre reads the fp32 spectrum as TF32 operands; the split variants read its fp16 hi / lo copy (K = 8 padded to one k-step of 16)
+    using TEncPre = TcGemm<S * C::F1, C::C1, SPLIT ? 16 : 8, 3, CHUNK, 256, SPLIT ? 16 : 8, NPART>;
+    using TConv3 = TcGemm<S * C::F1, C::C1, C1P, 3, CHUNK, 256, KEC, NPART>;
+    using TPwCat = TcGemm<S * C::F1, C::C1, 2 * C1P, 1, CHUNK, 256, KEC, NPART>;
+    using TConvT = TcGemm<S * C::F1, 8, C1P, 3, CHUNK, 256, KEC, NPART>;
+    using TRfPost = TcGemm<S * C::F1, C::C1, C2Z, 1, CHUNK, 256, KEC, NPART>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
     static constexpr int TMEMC = pow2ceil(H_TMEM ? TM_COLS : ACCW);
     static_assert(TMEMC <= 512, "TMEM columns");
-    using TRfPre = TcGemm<S * C::F2, C::C2, C1P, 1, CHUNK, 512, KEC>;
+    using TRfPre = TcGemm<S * C::F2, C::C2, C1P, 1, CHUNK, 512, KEC, NPART>;
     static constexpr int KER = RF16 ? 16 : 8;          // contraction length of one RNNFormer MMA
-    using TGru = TcGru<S * C::F2, C::C2, CHUNK, KER>;
-    using TFc = TcGemm<S * C::F2, C::C2, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER>;
-    using TQkv = TcGemm<S * C::F2, QN, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER>;
+    using TGru = TcGru<S * C::F2, C::C2, CHUNK, KER, NPART>;
+    using TFc = TcGemm<S * C::F2, C::C2, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER, NPART>;
+    using TQkv = TcGemm<S * C::F2, QN, RF16 ? C2H : C::C2, 1, CHUNK, 512, KER, NPART>;
     using LinPostT = RowGemmK1<C::C2 * S, C::F2, C::F1, NW, CHUNK>;
     // (An experimental variant of these two layers that stored every weight twice gave intermittently wrong rf_pre outputs on the GPU
     // for 48 kHz L while the CPU emulation was exact.  It was slower anyway and is gone; the ring itself is not the cause -- capping
@@ -469,7 +492,7 @@ struct Plan {
 // kernel parameters (plain data, passed by value)
 struct KParams {
     const float* blob;        // packed weights + tables (device)
-    float* state;             // [n_streams][STATE] native layout: cache_stft | cache_istft | h[K][C2][F2]
+    float* state;             // planes: cache_stft [n_streams][N-H] | cache_istft [n_streams][N-H] | h_k [n_streams][F2][C2], k < K
     const float* in;          // mode 0/3: wav [n_streams][ld_in]; mode 1/4: spec [B][NB][T][2]; mode 2: wav [B][L]
     float* out;               // mode 0/4: wav [n_streams][ld_out]; mode 1/3: spec [B][NB][T][2]; mode 2: wav [B][H*(T-1)]
     float* spec_out;          // mode 2 (optional): compressed masked spectrum [B][FIN][T][2]

@@ -23,8 +23,12 @@ ABI_SYMBOLS = (
     "fe_last_error", "fe_weight_count", "fe_state_floats", "fe_create", "fe_destroy", "fe_state_create",
     "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
-    "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision",
+    "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
+    "fe_state_create_on", "fe_state_planes", "fe_microbench_fma",
 )
+
+#: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
+PRECISION_MODES = {"tf32": 0, "fp32": 1, "f16": 2, "bf16": 3, "fp32x3": 4}
 
 
 class CConfig(ctypes.Structure):
@@ -63,13 +67,17 @@ def load_library(build_if_missing: bool = True):
     lib.fe_destroy.argtypes = [vp]
     lib.fe_destroy.restype = None
     lib.fe_state_create.argtypes = [vp, ip, ctypes.POINTER(vp)]
+    lib.fe_state_create_on.argtypes = [vp, ip, fp, ctypes.POINTER(vp)]
+    lib.fe_state_planes.argtypes = [vp]
+    lib.fe_state_planes.restype = ctypes.c_void_p
     lib.fe_state_destroy.argtypes = [vp]
     lib.fe_state_destroy.restype = None
     lib.fe_state_reset.argtypes = [vp, vp]
     lib.fe_state_export.argtypes = [vp, fp, vp]
     lib.fe_state_import.argtypes = [vp, fp, vp]
     lib.fe_stream.argtypes = [vp, vp, fp, fp, ip, ll, ll, vp]
-    lib.fe_stream_host.argtypes = [vp, vp, fp, fp, ip, ll, ll, ip]
+    lib.fe_stream_host.argtypes = [vp, vp, fp, fp, ip, ll, ll, ip, vp]
+    lib.fe_state_reserve_host.argtypes = [vp, ip]
     lib.fe_spec.argtypes = [vp, vp, fp, fp, ip, vp]
     lib.fe_offline.argtypes = [vp, fp, ip, ip, fp, fp, vp]
     lib.fe_stft.argtypes = [vp, vp, fp, fp, ip, ll, vp]
@@ -82,6 +90,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_stream_taps.argtypes = [vp, vp, fp, fp, ip, ll, ll, fp, ip, vp]
     lib.fe_profile_slots.argtypes = []
     lib.fe_set_profile.argtypes = [vp, vp]
+    lib.fe_microbench_fma.argtypes = [ip, ctypes.POINTER(ctypes.c_double)]
     lib.fe_set_precision.argtypes = [vp, ip]
     lib.fe_get_precision.argtypes = [vp]
     _lib = lib
@@ -94,39 +103,86 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else 'unknown error'}")
 
 
-def _stream_ptr() -> int:
+def measured_fma_tflops(device_index: int = 0) -> float:
+    """fp32 FMA-pipe throughput of the device, measured (fe_microbench_fma)."""
+    v = ctypes.c_double()
+    _check(load_library().fe_microbench_fma(int(device_index), ctypes.byref(v)), "fe_microbench_fma")
+    return float(v.value)
+
+
+def _stream_ptr(device=None) -> int:
+    """raw cudaStream_t of torch's current stream ON THE ENGINE'S DEVICE (not of whatever device is current)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 class State:
     """Recurrent (GRU h per block) + overlap (STFT / iSTFT caches) state of ``n_streams`` streams, on device."""
 
     def __init__(self, engine: "Engine", n_streams: int):
+        """The state lives in a torch allocation handed to the engine (fe_state_create_on): the kernels keep it as planes in
+        the reference's own cache shapes, so :meth:`caches` returns zero-copy views the reference-shaped wrappers hand out."""
+        import torch
         self.engine, self.n_streams = engine, int(n_streams)
+        self.buf = torch.zeros(self.n_streams * engine.state_floats, dtype=torch.float32, device=engine.device)
         h = ctypes.c_void_p()
-        _check(engine._lib.fe_state_create(engine._h, self.n_streams, ctypes.byref(h)), "fe_state_create")
+        _check(engine._lib.fe_state_create_on(engine._h, self.n_streams, self.buf.data_ptr(), ctypes.byref(h)), "fe_state_create_on")
         self._h = h
+        cfg, B = engine.cfg, self.n_streams
+        cl, hf = cfg.cache_len, cfg.rf_freq * cfg.rf_channels
+        self._caches = [self.buf[:B * cl].view(B, cl), self.buf[B * cl:2 * B * cl].view(B, cl)] + \
+            [self.buf[2 * B * cl + k * B * hf: 2 * B * cl + (k + 1) * B * hf].view(1, B * cfg.rf_freq, cfg.rf_channels)
+             for k in range(cfg.rf_blocks)]
+
+        self._live = [None] * len(self._caches)
+
+    # Reference-shaped cache tensors without copies.  Plane i (0 = cache_stft [B, N-H], 1 = cache_istft [B, N-H], 2 + k = h_k
+    # [1, B*F2, C2]: the shapes of ONNXSTFT.initialize_cache + ONNXModel.initialize_cache, functional/audio_modules.py:238-241,
+    # model.py:614-618) is handed out by emit(i) as a fresh view object of the device state and taken back by adopt(i, t):
+    #   * t is the object emit(i) returned last  -> the state already holds it: nothing to do (the per-hop fast path);
+    #   * t is some other tensor                 -> its contents are copied in (explicit caches of another session, zeros, ...);
+    #   * t is an OLDER view of the same memory  -> its contents are gone (the state has moved on): a loud error, never silence.
+    def emit(self, i: int):
+        v = self._caches[i].view(self._caches[i].shape)
+        self._live[i] = v
+        return v
+
+    def adopt(self, i: int, t) -> None:
+        c = self._caches[i]
+        if t is None:
+            c.zero_()
+        elif t is self._live[i]:
+            return
+        elif t.device == c.device and t.data_ptr() == c.data_ptr():
+            raise RuntimeError("stale cache tensor: the caches this engine returns are views of its device state and are overwritten "
+                               "by the next step; clone() one if you need to keep an older generation")
+        else:
+            c.copy_(t.reshape(c.shape))
+        self._live[i] = None
 
     def __del__(self):
         if getattr(self, "_h", None):
             self.engine._lib.fe_state_destroy(self._h)
             self._h = None
 
+    def reserve_host(self, hops_per_chunk: int = 64) -> None:
+        """pre-allocate the staging buffers / streams of :meth:`Engine.stream_host` (keeps allocations out of the hot call)."""
+        _check(self.engine._lib.fe_state_reserve_host(self._h, int(hops_per_chunk)), "fe_state_reserve_host")
+
     def reset(self) -> None:
-        _check(self.engine._lib.fe_state_reset(self._h, _stream_ptr()), "fe_state_reset")
+        _check(self.engine._lib.fe_state_reset(self._h, _stream_ptr(self.engine.device)), "fe_state_reset")
 
     def export(self):
         """-> float32 cuda tensor [n_streams, state_floats] in the reference cache layout
         [cache_stft | cache_istft | h_0 [F2][C2] | ...]."""
         import torch
         out = torch.empty(self.n_streams, self.engine.state_floats, dtype=torch.float32, device=self.engine.device)
-        _check(self.engine._lib.fe_state_export(self._h, out.data_ptr(), _stream_ptr()), "fe_state_export")
+        _check(self.engine._lib.fe_state_export(self._h, out.data_ptr(), _stream_ptr(self.engine.device)), "fe_state_export")
         return out
 
     def load(self, t) -> None:
         t = self.engine._dev(t, (self.n_streams, self.engine.state_floats))
-        _check(self.engine._lib.fe_state_import(self._h, t.data_ptr(), _stream_ptr()), "fe_state_import")
+        _check(self.engine._lib.fe_state_import(self._h, t.data_ptr(), _stream_ptr(self.engine.device)), "fe_state_import")
 
 
 class Engine:
@@ -134,9 +190,11 @@ class Engine:
 
     def __init__(self, cfg: FEConfig, canonical: np.ndarray, device: tp.Union[int, str, None] = None,
                  precision: tp.Optional[str] = None):
-        """``precision``: "tf32" (default; contractions on tcgen05 tensor cores with TF32 operands, fp32 accumulate), "fp32"
-        (everything on the fp32 FMA pipe) or "f16" (as tf32 with the conv section's operands stored as fp16; only for models
-        that have such a kernel variant).  ``FE_PRECISION`` in the environment sets the default."""
+        """``precision``: None (default) = results identical to the fp32 reference -- "fp32x3" (fp32-accurate tensor-core
+        contractions: split-fp16 operands, three MMAs per product) where the model has such kernels, else "fp32" (everything on
+        the fp32 FMA pipe).  Faster, reduced-precision opt-ins: "tf32" (TF32 operands, fp32 accumulate), "f16" (as tf32 with the
+        conv section's operands stored as fp16), "bf16" (bfloat16 conv section, TF32 RNNFormer: BASELINE config 3's arithmetic).
+        ``FE_PRECISION`` in the environment overrides the default."""
         import torch
         cfg.validate()
         if not torch.cuda.is_available():
@@ -175,15 +233,25 @@ class Engine:
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
 
+    def _out(self, out, like):
+        """validate a caller-provided output tensor: same device / dtype / shape as ``like``, contiguous rows."""
+        import torch
+        if out is None:
+            return torch.empty_like(like)
+        if not isinstance(out, torch.Tensor) or out.device != like.device or out.dtype != torch.float32 or \
+                tuple(out.shape) != tuple(like.shape) or (out.dim() > 1 and out.stride(-1) != 1) or \
+                (out.dim() > 2 and not out.is_contiguous()):
+            raise ValueError(f"out must be a float32 tensor of shape {tuple(like.shape)} on {like.device} with contiguous rows")
+        return out
+
     def set_precision(self, precision: str) -> None:
-        modes = {"tf32": 0, "fp32": 1, "f16": 2}
-        if precision not in modes:
-            raise ValueError("precision must be 'tf32', 'fp32' or 'f16'")
-        _check(self._lib.fe_set_precision(self._h, modes[precision]), "fe_set_precision")
+        if precision not in PRECISION_MODES:
+            raise ValueError(f"precision must be one of {sorted(PRECISION_MODES)}")
+        _check(self._lib.fe_set_precision(self._h, PRECISION_MODES[precision]), "fe_set_precision")
 
     @property
     def precision(self) -> str:
-        return {0: "tf32", 1: "fp32", 2: "f16"}[int(self._lib.fe_get_precision(self._h))]
+        return {v: k for k, v in PRECISION_MODES.items()}[int(self._lib.fe_get_precision(self._h))]
 
     def new_state(self, n_streams: int) -> State:
         return State(self, n_streams)
@@ -226,10 +294,9 @@ class Engine:
         H = self.cfg.hop_size
         if B != state.n_streams or L % H:
             raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(x.shape)}")
-        if out is None:
-            out = torch.empty_like(x)
+        out = self._out(out, x)
         _check(self._lib.fe_stream(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), out.stride(0),
-                                   _stream_ptr()), "fe_stream")
+                                   _stream_ptr(self.device)), "fe_stream")
         return out
 
     def stream_taps(self, state: State, wav_in, tap_hop: int):
@@ -240,7 +307,7 @@ class Engine:
         out = torch.empty_like(x)
         taps = torch.zeros(int(self._lib.fe_tap_floats(self._h)), dtype=torch.float32, device=self.device)
         _check(self._lib.fe_stream_taps(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), out.stride(0),
-                                        taps.data_ptr(), int(tap_hop), _stream_ptr()), "fe_stream_taps")
+                                        taps.data_ptr(), int(tap_hop), _stream_ptr(self.device)), "fe_stream_taps")
         return out, taps
 
     def stream_host(self, state: State, wav_in, out=None, hops_per_chunk: int = 0):
@@ -254,8 +321,10 @@ class Engine:
             raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(wav_in.shape)}")
         if out is None:
             out = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        elif out.device.type != "cpu" or out.dtype != torch.float32 or tuple(out.shape) != (B, L) or out.stride(1) != 1:
+            raise ValueError(f"out must be a float32 CPU tensor of shape {(B, L)} with contiguous rows")
         _check(self._lib.fe_stream_host(self._h, state._h, wav_in.data_ptr(), out.data_ptr(), L // H, wav_in.stride(0),
-                                        out.stride(0), int(hops_per_chunk)), "fe_stream_host")
+                                        out.stride(0), int(hops_per_chunk), _stream_ptr(self.device)), "fe_stream_host")
         return out
 
     def spec(self, state: State, spec_in, out=None):
@@ -265,9 +334,8 @@ class Engine:
         B, NB, T, two = x.shape
         if B != state.n_streams or NB != self.cfg.n_fft // 2 + 1 or two != 2:
             raise ValueError(f"bad spectrum shape {tuple(x.shape)}")
-        if out is None:
-            out = torch.empty_like(x)
-        _check(self._lib.fe_spec(self._h, state._h, x.data_ptr(), out.data_ptr(), T, _stream_ptr()), "fe_spec")
+        out = self._out(out, x)
+        _check(self._lib.fe_spec(self._h, state._h, x.data_ptr(), out.data_ptr(), T, _stream_ptr(self.device)), "fe_spec")
         return out
 
     def stft(self, state: State, wav_in):
@@ -280,7 +348,7 @@ class Engine:
         if B != state.n_streams or L % H:
             raise ValueError(f"wav_in must be [{state.n_streams}, k*{H}], got {tuple(x.shape)}")
         out = torch.empty((B, self.cfg.n_fft // 2 + 1, L // H, 2), dtype=torch.float32, device=self.device)
-        _check(self._lib.fe_stft(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), _stream_ptr()), "fe_stft")
+        _check(self._lib.fe_stft(self._h, state._h, x.data_ptr(), out.data_ptr(), L // H, x.stride(0), _stream_ptr(self.device)), "fe_stft")
         return out
 
     def istft(self, state: State, spec_in):
@@ -291,7 +359,7 @@ class Engine:
         if B != state.n_streams or NB != self.cfg.n_fft // 2 + 1 or two != 2:
             raise ValueError(f"bad spectrum shape {tuple(x.shape)}")
         out = torch.empty((B, T * self.cfg.hop_size), dtype=torch.float32, device=self.device)
-        _check(self._lib.fe_istft(self._h, state._h, x.data_ptr(), out.data_ptr(), T, out.stride(0), _stream_ptr()), "fe_istft")
+        _check(self._lib.fe_istft(self._h, state._h, x.data_ptr(), out.data_ptr(), T, out.stride(0), _stream_ptr(self.device)), "fe_istft")
         return out
 
     def offline(self, wav, want_spec: bool = True):
@@ -304,5 +372,5 @@ class Engine:
         out = torch.empty((B, H * (T - 1)), dtype=torch.float32, device=self.device)
         spec = torch.empty((B, self.cfg.f_in, T, 2), dtype=torch.float32, device=self.device) if want_spec else None
         _check(self._lib.fe_offline(self._h, x.data_ptr(), B, L, out.data_ptr(), spec.data_ptr() if want_spec else None,
-                                    _stream_ptr()), "fe_offline")
+                                    _stream_ptr(self.device)), "fe_offline")
         return out, spec

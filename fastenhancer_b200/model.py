@@ -14,8 +14,11 @@ This is the host-side mirror of the reference's operator interface for the hot p
 
 The modules hold the reference's *pre-fold* parameters under the reference's own names, so
 ``load_state_dict(ckpt['model'], strict=True)`` works on a reference checkpoint
-(wrappers/ns.py:308-321).  Parameters are folded (fastenhancer_b200.fold) and packed on first use;
+(wrappers/ns.py:308-321).  Parameters are folded (fastenhancer_b200.fold) and packed on first use -- a snapshot: ``load_state_dict`` / ``.to()`` re-pack,
+in-place edits of a parameter afterwards need ``remove_weight_reparameterizations()`` to be picked up;
 every forward then is a launch of the fused kernel through the C ABI.  There is no PyTorch compute path.
+Arithmetic: by default results identical to the fp32 reference (fp32-accurate tensor-core kernels where the model has them,
+else the fp32 FMA pipe); ``model.precision = "f16" | "tf32" | "bf16"`` opts into the faster reduced-precision kernels.
 ``ONNXModel.stft(x, cache)`` / ``.stft.inverse(spec, cache)`` run the front / back end of the same kernel on their own.
 """
 from __future__ import annotations
@@ -96,6 +99,7 @@ class ONNXModel(nn.Module):
         self.stft = _StftShim(self, self._streaming_stft)
         self._engine: tp.Optional[Engine] = None
         self._states: tp.Dict[int, State] = {}
+        self.precision: tp.Optional[str] = None      # None = identical-to-reference default (Engine picks fp32x3 or fp32)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # ---- engine lifetime ----
@@ -120,13 +124,21 @@ class ONNXModel(nn.Module):
                 if not torch.cuda.is_available():
                     raise RuntimeError("fastenhancer_b200: no CUDA device visible; the engine has no CPU fallback")
                 dev = torch.device("cuda", torch.cuda.current_device())
-            self._engine = Engine(self.cfg, self.canonical_weights(), dev)
+            self._engine = Engine(self.cfg, self.canonical_weights(), dev, precision=self.precision)
+        elif self.precision is not None and self._engine.precision != self.precision:
+            self._engine.set_precision(self.precision)
         return self._engine
 
+    _MAX_STATES = 4      # batch sizes kept alive (least recently used goes first)
+
     def _state(self, n_streams: int) -> State:
-        st = self._states.get(n_streams)
+        """the device state of this module's streaming session for ``n_streams`` streams (one per batch size)."""
+        st = self._states.pop(n_streams, None)
         if st is None:
-            st = self._states[n_streams] = self.engine.new_state(n_streams)
+            st = self.engine.new_state(n_streams)
+            while len(self._states) >= self._MAX_STATES:
+                self._states.pop(next(iter(self._states)))
+        self._states[n_streams] = st
         return st
 
     # ---- reference API ----
@@ -143,57 +155,36 @@ class ONNXModel(nn.Module):
         """GRU caches, one per RNNFormer block: [1, B*F2, C2] zeros (model.py:263-264, 614-618; B = x.size(0))."""
         return [x.new_zeros(1, x.size(0) * self.cfg.rf_freq, self.cfg.rf_channels) for _ in range(self.cfg.rf_blocks)]
 
-    def _pack_state(self, B: int, cache_stft, cache_istft, hs) -> Tensor:
-        """reference cache tensors -> [B, state_floats] in the C ABI's export layout."""
-        cfg, dev = self.cfg, self.engine.device
-        z = torch.zeros(B, cfg.cache_len, device=dev)
-        parts = [z if cache_stft is None else cache_stft.to(dev, torch.float32).reshape(B, cfg.cache_len),
-                 z if cache_istft is None else cache_istft.to(dev, torch.float32).reshape(B, cfg.cache_len)]
-        for k in range(cfg.rf_blocks):
-            if hs is None or len(hs) == 0:
-                parts.append(torch.zeros(B, cfg.rf_freq * cfg.rf_channels, device=dev))
-            else:
-                parts.append(hs[k].to(dev, torch.float32).reshape(B, cfg.rf_freq * cfg.rf_channels))
-        return torch.cat(parts, dim=1)
-
-    def _unpack_h(self, B: int, flat: Tensor, like: Tensor) -> tp.List[Tensor]:
-        cfg = self.cfg
-        n = cfg.rf_freq * cfg.rf_channels
-        off = 2 * cfg.cache_len
-        return [flat[:, off + k * n: off + (k + 1) * n].reshape(1, B * cfg.rf_freq, cfg.rf_channels).to(like.device)
-                for k in range(cfg.rf_blocks)]
-
     @torch.no_grad()
     def forward(self, spec_noisy: Tensor, *args):
-        """[B, n_fft/2+1, T, 2] (+ GRU caches) -> (spec_hat, *caches_out); no caches = zero state (model.py:623-626)."""
-        B = spec_noisy.size(0)
-        if len(args) not in (0, self.cfg.rf_blocks):
-            raise ValueError(f"expected 0 or {self.cfg.rf_blocks} cache tensors, got {len(args)}")
+        """[B, n_fft/2+1, T, 2] (+ GRU caches) -> (spec_hat, *caches_out); no caches = zero state (model.py:623-626).
+        The returned caches are views of the engine's device state (see fastenhancer_b200.engine.State.emit): feeding them back
+        into the next call -- what scripts/test_onnx_spec.py:55-62 does -- costs nothing; foreign tensors are copied in."""
+        B, K = spec_noisy.size(0), self.cfg.rf_blocks
+        if len(args) not in (0, K):
+            raise ValueError(f"expected 0 or {K} cache tensors, got {len(args)}")
         st = self._state(B)
-        st.load(self._pack_state(B, None, None, args))
+        for k in range(K):
+            st.adopt(2 + k, args[k] if args else None)
         out = self.engine.spec(st, spec_noisy)
-        hs = self._unpack_h(B, st.export(), spec_noisy)
-        return (out.to(spec_noisy.device), *hs)
+        return (out.to(spec_noisy.device), *[st.emit(2 + k) for k in range(K)])
 
     # per-hop STFT / iSTFT shims (functional/audio_modules.py:243-303); one fused-kernel launch each
     @torch.no_grad()
     def _stft_forward(self, x: Tensor, cache: tp.Optional[Tensor]):
         """ONNXSTFT.forward: x [B, k*hop], cache [B, N-H] -> (spec [B, N/2+1, k, 2], cache)."""
-        B = x.size(0)
-        st = self._state(B)
-        st.load(self._pack_state(B, cache, None, None))
+        st = self._state(x.size(0))
+        st.adopt(0, cache)
         spec = self.engine.stft(st, x)
-        return spec.to(x.device), st.export()[:, :self.cfg.cache_len].to(x.device)
+        return spec.to(x.device), st.emit(0)
 
     @torch.no_grad()
     def _stft_inverse(self, spec: Tensor, cache: tp.Optional[Tensor]):
         """ONNXSTFT.inverse: spec [B, N/2+1, T, 2], cache [B, N-H] -> (wav [B, T*hop], cache)."""
-        B = spec.size(0)
-        st = self._state(B)
-        st.load(self._pack_state(B, None, cache, None))
+        st = self._state(spec.size(0))
+        st.adopt(1, cache)
         wav = self.engine.istft(st, spec)
-        cl = self.cfg.cache_len
-        return wav.to(spec.device), st.export()[:, cl:2 * cl].to(spec.device)
+        return wav.to(spec.device), st.emit(1)
 
 
 class Model(ONNXModel):
@@ -211,12 +202,15 @@ class StreamingModel(nn.Module):
     """The wav2wav streaming graph of scripts/export_onnx.py:37-58, one fused launch per call:
     ``(wav_in [B, hop], cache_stft [B, N-H], cache_istft [B, N-H], *h [1, B*F2, C2]) -> (wav_out, caches...)``.
 
-    ``run(wav [B, n_hops*hop])`` keeps the state on the device between hops (no cache round trip), which is
-    what the engine is built for; ``forward`` keeps the reference's explicit-cache calling convention."""
+    ``forward`` keeps the reference's explicit-cache calling convention (the loop of scripts/test_onnx.py:44-49): the caches it
+    returns are views of the engine's device state, so feeding them back costs nothing and a hop is ONE kernel launch; any other
+    cache tensors are copied in first.  ``run(wav [B, n_hops*hop])`` processes many hops in one launch on a state the module
+    keeps between calls (``reset()`` zeroes it)."""
 
     def __init__(self, model: ONNXModel):
         super().__init__()
         self.model = model
+        self._run_states: tp.Dict[int, State] = {}
 
     def initialize_cache(self, x: Tensor) -> tp.List[Tensor]:
         return self.model.stft.initialize_cache(x) + self.model.initialize_cache(x)
@@ -224,18 +218,28 @@ class StreamingModel(nn.Module):
     @torch.no_grad()
     def forward(self, wav_in: Tensor, cache_stft: Tensor, cache_istft: Tensor, *cache_model):
         m = self.model
-        B = wav_in.size(0)
-        st = m._state(B)
-        st.load(m._pack_state(B, cache_stft, cache_istft, cache_model))
+        n = 2 + m.cfg.rf_blocks
+        if len(cache_model) != m.cfg.rf_blocks:
+            raise ValueError(f"expected {m.cfg.rf_blocks} GRU cache tensors, got {len(cache_model)}")
+        st = m._state(wav_in.size(0))
+        for i, t in enumerate((cache_stft, cache_istft, *cache_model)):
+            st.adopt(i, t)
         out = m.engine.stream(st, wav_in)
-        flat = st.export()
-        cl = m.cfg.cache_len
-        return (out.to(wav_in.device), flat[:, :cl].to(wav_in.device), flat[:, cl:2 * cl].to(wav_in.device),
-                *m._unpack_h(B, flat, wav_in))
+        return (out.to(wav_in.device), *[st.emit(i) for i in range(n)])
+
+    def reset(self) -> None:
+        """zero the state(s) ``run`` keeps between calls."""
+        for st in self._run_states.values():
+            st.reset()
 
     @torch.no_grad()
     def run(self, wav: Tensor, state: tp.Optional[State] = None) -> Tensor:
+        """many hops in one launch.  Without ``state`` the module's own persistent state for this batch size is used and
+        carries over from call to call (chunked callers keep their GRU / overlap state); call ``reset()`` to start over."""
         m = self.model
         if state is None:
-            state = m.engine.new_state(wav.size(0))
+            B = wav.size(0)
+            if B not in self._run_states or self._run_states[B].engine is not m.engine:
+                self._run_states[B] = m.engine.new_state(B)
+            state = self._run_states[B]
         return m.engine.stream(state, wav).to(wav.device)

@@ -9,8 +9,10 @@
  * cudaStream_t passed as void* (NULL = default stream).
  *
  * Every function returns 0 on success and a negative code on failure; fe_last_error() returns a
- * thread-local description.  One engine per device; calls on one engine are serialised per CUDA
- * stream by the caller; distinct engines are independent (no global state).
+ * thread-local description.  One engine per device.  An engine is immutable after fe_create apart from
+ * its settings (fe_set_*); everything a call mutates lives in the fe_state it is given or on the call's
+ * CUDA stream, so distinct states of one engine may be driven concurrently from different host threads
+ * and streams.  Calls on ONE state are serialised by the caller.  No global state.
  */
 #ifndef FASTENHANCER_B200_H
 #define FASTENHANCER_B200_H
@@ -58,6 +60,13 @@ void fe_destroy(fe_engine* e);
 /* Replaces: ONNXSTFT.initialize_cache + ONNXModel.initialize_cache (audio_modules.py:238-241,
  * model.py:614-618): zeroed cache_stft [n, n_fft-hop], cache_istft [n, n_fft-hop], h_k [n*f2, c2] x K. */
 int fe_state_create(fe_engine* e, int n_streams, fe_state** out);
+/* Same on a caller-owned device buffer of n_streams * fe_state_floats floats (16-byte aligned, zeroed by the caller or by
+ * fe_state_reset).  The kernels keep the state there as PLANES in the reference's own cache shapes,
+ *   cache_stft [n][n_fft-hop] | cache_istft [n][n_fft-hop] | h_0 [n][f2][c2] | ... | h_{K-1} [n][f2][c2],
+ * so a host wrapper can hand the pieces out as zero-copy tensors (`cache_in_* / cache_out_*` of scripts/test_onnx.py:34-49)
+ * and a streaming step needs no cache import / export.  fe_state_planes returns that buffer (owned or not). */
+int fe_state_create_on(fe_engine* e, int n_streams, float* planes_device, fe_state** out);
+float* fe_state_planes(fe_state* s);
 void fe_state_destroy(fe_state* s);
 int fe_state_reset(fe_state* s, void* cuda_stream);
 /* Reference cache layout per stream: [cache_stft | cache_istft | h_0 [f2][c2] | ... | h_{K-1}], so ORT-style
@@ -74,9 +83,13 @@ int fe_stream(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, in
               long long ld_in, long long ld_out, void* cuda_stream);
 
 /* Same, HOST buffers (pinned or pageable): host->device copy, kernel and device->host copy are pipelined in
- * `hops_per_chunk`-hop pieces (0 = default).  This is the end-to-end path bench.py times as `e2e`. */
+ * `hops_per_chunk`-hop pieces (0 = default) on streams owned by `s`.  Ordered after the work already queued on
+ * `cuda_stream`; returns once the last device->host copy has completed (also drains on error).
+ * fe_state_reserve_host pre-allocates the staging buffers / streams / events so that no allocation happens inside
+ * fe_stream_host (otherwise they are created on first use).  This is the end-to-end path bench.py times as `e2e`. */
+int fe_state_reserve_host(fe_state* s, int hops_per_chunk);
 int fe_stream_host(fe_engine* e, fe_state* s, const float* wav_in_host, float* wav_out_host, int n_hops,
-                   long long ld_in, long long ld_out, int hops_per_chunk);
+                   long long ld_in, long long ld_out, int hops_per_chunk, void* cuda_stream);
 
 /* Replaces: ONNXModel.forward(spec_noisy, *h) (model.py:677-710; the spec2spec graph of
  * scripts/export_onnx_spec.py:135-142).  spec_in / spec_out: device, [n_streams][n_fft/2+1][T][2]. */
@@ -93,19 +106,28 @@ int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, in
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
 
-/* Arithmetic of the channel contractions (conv-type layers, RNNFormer linears, GRU matrix products):
- *   mode = 0 (default): tcgen05 tensor cores, TF32 operands (round-to-nearest), fp32 accumulation in TMEM --
- *             what PyTorch itself does for cuDNN convolutions by default (allow_tf32); waveform error vs the
- *             fp32 reference ~7e-6 RMS, against the 1e-4 RMS bar;
+/* Arithmetic of the channel contractions (conv-type layers, RNNFormer linears, GRU matrix products).
+ * The DEFAULT of a new engine reproduces the fp32 reference: mode 4 where the model has such kernels (T / B), else mode 1.
+ *   mode = 4: "fp32x3" -- fp32-accurate on the tcgen05 tensor cores: every operand is held as two fp16 parts
+ *             (hi = fp16(v), lo = fp16(v - hi): 22 significand bits) and every product is three kind::f16 MMAs
+ *             (hi*hi + lo*hi + hi*lo) into one fp32 TMEM accumulator; waveform error vs the fp32 reference ~7e-8 RMS,
+ *             the same as mode 1.  FE_ERR_UNSUPPORTED for models without such a kernel variant.
  *   mode = 1: every multiply-add on the fp32 FMA pipe (~6e-8 RMS);
+ *   mode = 0: tcgen05 tensor cores, TF32 operands (round-to-nearest), fp32 accumulation in TMEM --
+ *             what PyTorch itself does for cuDNN convolutions by default (allow_tf32); waveform error vs the
+ *             fp32 reference ~7e-6 RMS on the synthetic checkpoint whose mask is near identity and up to ~1e-3
+ *             relative when the mask is network-dominated (tests/test_gpu_parity.py), against the 1e-4 RMS bar;
  *   mode = 2: as 0, with the activations and weights of the conv section (encoder, decoder, 1x1 convs, mask head)
  *             stored as fp16 -- the same 11-bit significand as TF32, twice the contraction length per MMA and half the
  *             shared memory; where the RNNFormer operands live in tensor memory (T/B/S) they are fp16 as well, beside an
  *             fp32 master of the GRU state; the RNNFormer of M/L stays TF32.  Same waveform error as mode 0.
  *             FE_ERR_UNSUPPORTED for models without such a kernel variant.
+ *   mode = 3: "bf16 conv / fp32 GRU" (BASELINE.json configs[2]): as 2 with bfloat16 (8-bit significand) activations and
+ *             weights in the conv section; the RNNFormer (GRU, linears, qkv) keeps TF32 operands, the GRU state is fp32.
+ *             Waveform error ~3e-5 RMS on the near-identity-mask checkpoint.  FE_ERR_UNSUPPORTED without such a variant.
  * Attention, FFTs, (de)compression, the residual stream and all state are fp32 in every mode. */
 int fe_set_precision(fe_engine* e, int mode);
-int fe_get_precision(fe_engine* e);               /* 0 = TF32 tensor-core contractions, 1 = fp32 exact, 2 = fp16 conv section */
+int fe_get_precision(fe_engine* e);               /* 0 TF32, 1 fp32 FMA pipe, 2 fp16, 3 bf16 conv section, 4 fp32x3 */
 
 /* Introspection used by the host wrapper, tests and bench. */
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
@@ -116,6 +138,10 @@ int fe_tap_floats(fe_engine* e);
  * (layout of oracle/fe_oracle.c::core) into taps_device [fe_tap_floats]. */
 int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops,
                    long long ld_in, long long ld_out, float* taps_device, int tap_hop, void* cuda_stream);
+
+/* Measured fp32 FMA-pipe throughput of `device` in TFLOP/s (a short FFMA microbenchmark): the roofline denominator of the fp32
+ * FMA-pipe kernel family (mode 1) in bench.py. */
+int fe_microbench_fma(int device, double* tflops);
 
 /* Profiling hook: when set, CTA 0 of every fused-kernel launch accumulates the SM cycles it spends in each
  * phase of the frame (ids: enum PhaseId in fastenhancer_b200/csrc/fe_kernel.cuh) into counters_device

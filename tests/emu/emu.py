@@ -15,11 +15,22 @@ MODE_STREAM, MODE_SPEC, MODE_OFFLINE = 0, 1, 2
 
 
 def build(force=False):
+    """g++ the emulation: ten translation units (one per model configuration) in parallel + the dispatcher, linked into one .so."""
+    import concurrent.futures as cf
     deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("fe_plan.h", "fe_pack.h", "fe_kernel.cuh", "fe_configs.h", "fe_half.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
-    os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", _SO, _SRC], check=True)
+    bdir = os.path.dirname(_SO)
+    os.makedirs(bdir, exist_ok=True)
+    jobs = [(f"-DFE_EMU_GROUP={g}", os.path.join(bdir, f"fe_emu_g{g}.o")) for g in range(10)] + [("-DFE_EMU_MAIN", os.path.join(bdir, "fe_emu_main.o"))]
+
+    def cc(job):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", job[0], "-c", _SRC, "-o", job[1]], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"emu build failed ({job[0]}):\n{r.stderr[-4000:]}")
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(cc, jobs))
+    subprocess.run(["g++", "-shared", "-o", _SO] + [j[1] for j in jobs], check=True)
     return _SO
 
 
@@ -46,18 +57,20 @@ def _shape(cfg):
 
 
 def to_native(cfg, state):
-    """canonical state [B, 2*CL + K*F2*C2] (h as [K][F2][C2]) -> native (h as [K][C2][F2])."""
-    B = state.shape[0]
-    cl2 = 2 * cfg.cache_len
-    h = state[:, cl2:].reshape(B, cfg.rf_blocks, cfg.rf_freq, cfg.rf_channels).transpose(0, 1, 3, 2)
-    return np.ascontiguousarray(np.concatenate([state[:, :cl2], h.reshape(B, -1)], axis=1), np.float32)
+    """per-stream rows [B, 2*CL + K*F2*C2] -> the kernels' planes (flat): cache_stft [B][CL] | cache_istft [B][CL] | h_k [B][F2*C2]."""
+    B, cl, hf = state.shape[0], cfg.cache_len, cfg.rf_freq * cfg.rf_channels
+    parts = [state[:, :cl], state[:, cl:2 * cl]] + [state[:, 2 * cl + k * hf: 2 * cl + (k + 1) * hf] for k in range(cfg.rf_blocks)]
+    return np.ascontiguousarray(np.concatenate([p.reshape(-1) for p in parts]), np.float32)
 
 
-def to_canonical(cfg, state):
-    B = state.shape[0]
-    cl2 = 2 * cfg.cache_len
-    h = state[:, cl2:].reshape(B, cfg.rf_blocks, cfg.rf_channels, cfg.rf_freq).transpose(0, 1, 3, 2)
-    return np.ascontiguousarray(np.concatenate([state[:, :cl2], h.reshape(B, -1)], axis=1), np.float32)
+def to_canonical(cfg, planes):
+    cl, hf, K = cfg.cache_len, cfg.rf_freq * cfg.rf_channels, cfg.rf_blocks
+    B = planes.size // (2 * cl + K * hf)
+    off, parts = 0, []
+    for n in [cl, cl] + [hf] * K:
+        parts.append(planes[off:off + B * n].reshape(B, n))
+        off += B * n
+    return np.ascontiguousarray(np.concatenate(parts, axis=1), np.float32)
 
 
 def run(cfg, S, canonical, mode, state_native, inp, out, spec_out=None, n_streams=1, n_hops=1, L=0, ld_in=0, ld_out=0,

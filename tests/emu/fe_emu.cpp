@@ -46,12 +46,14 @@ template <class P> struct EmuCtx {
     Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
     Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats}; }
     // element (row r, k) of a K-major / no-swizzle fp16 operand: 8 halves per 16-byte row, k-chunks of 8 LBO apart
-    static float h16(const float* p, int lbo, int r, int k) {
+    template <bool BF = false> static float h16(const float* p, int lbo, int r, int k) {
         const uint16_t* h = reinterpret_cast<const uint16_t*>(p + (k / 8) * lbo + r * 4);
-        return f16_bits_to_f32(h[k % 8]);
+        return h16_bits_to_f32<BF>(h[k % 8]);
     }
-    template <bool M64 = false, bool F16 = false>
+    static constexpr int FMT16 = P::BF16 ? 2 : 1;
+    template <bool M64 = false, int FMT = 0>
     void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
+        constexpr bool F16 = FMT != 0, BF = FMT == 2;
         if (tid != 0) return;                       // one elected lane of warp 0 issues
         if (M64 && rows > 64) throw std::runtime_error("emu: M = 64 MMA with more than 64 rows");
         for (int m = 0; m < rows; ++m) {
@@ -59,7 +61,7 @@ template <class P> struct EmuCtx {
             for (int n = 0; n < NP; ++n) {
                 float sum = acc ? tmem[lane * 512 + col + n] : 0.f;
                 if (F16) {
-                    for (int k = 0; k < 16; ++k) sum += h16(a.p, a.lbo, m, k) * h16(b.p, b.lbo, n, k);
+                    for (int k = 0; k < 16; ++k) sum += h16<BF>(a.p, a.lbo, m, k) * h16<BF>(b.p, b.lbo, n, k);
                 } else {
                     for (int k = 0; k < 8; ++k)
                         sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);
@@ -131,6 +133,54 @@ template <class P> int run_variant(const float* canonical, KParams prm) {
 
 }  // namespace fe
 
+// The variants are instantiated in ten groups (one per model configuration) so that emu.py can compile them in parallel:
+//   -DFE_EMU_GROUP=g   : fee_run_g<g> and fee_tap_g<g> for the variants of configuration g
+//   -DFE_EMU_MAIN      : fee_run / fee_tap_total dispatching over the groups
+#define FE_CAT2(a, b) a##b
+#define FE_CAT(a, b) FE_CAT2(a, b)
+#ifdef FE_EMU_GROUP
+#if FE_EMU_GROUP == 0
+#define FE_GROUP_VARIANTS FE_VARIANTS_16T
+#elif FE_EMU_GROUP == 1
+#define FE_GROUP_VARIANTS FE_VARIANTS_16B
+#elif FE_EMU_GROUP == 2
+#define FE_GROUP_VARIANTS FE_VARIANTS_16S
+#elif FE_EMU_GROUP == 3
+#define FE_GROUP_VARIANTS FE_VARIANTS_16M
+#elif FE_EMU_GROUP == 4
+#define FE_GROUP_VARIANTS FE_VARIANTS_16L
+#elif FE_EMU_GROUP == 5
+#define FE_GROUP_VARIANTS FE_VARIANTS_48T
+#elif FE_EMU_GROUP == 6
+#define FE_GROUP_VARIANTS FE_VARIANTS_48B
+#elif FE_EMU_GROUP == 7
+#define FE_GROUP_VARIANTS FE_VARIANTS_48S
+#elif FE_EMU_GROUP == 8
+#define FE_GROUP_VARIANTS FE_VARIANTS_48M
+#else
+#define FE_GROUP_VARIANTS FE_VARIANTS_48L
+#endif
+extern "C" int FE_CAT(fee_run_g, FE_EMU_GROUP)(const fe::ShapeKey* key, int S, int tc, const float* canonical, const fe::KParams* prm)
+{
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(*key) && S == SV && tc == (int)(TCV)) return fe::run_variant<fe::Plan<fe::CFG, SV, TCV>>(canonical, *prm);
+    FE_GROUP_VARIANTS(X)
+#undef X
+    return -1;
+}
+extern "C" int FE_CAT(fee_tap_g, FE_EMU_GROUP)(const fe::ShapeKey* key)
+{
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(*key)) return fe::Frame<fe::Plan<fe::CFG, SV, TCV>>::TAP_TOTAL;
+    FE_GROUP_VARIANTS(X)
+#undef X
+    return -1;
+}
+#endif
+
+#ifdef FE_EMU_MAIN
+#define FE_GROUPS(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+#define X(g) extern "C" int fee_run_g##g(const fe::ShapeKey*, int, int, const float*, const fe::KParams*); extern "C" int fee_tap_g##g(const fe::ShapeKey*);
+FE_GROUPS(X)
+#undef X
 extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S, int tc,
                        const float* canonical, int mode, float* state, const float* in, float* out, float* spec_out,
                        int n_streams, int n_hops, int L, long long ld_in, long long ld_out, float* dbg, int dbg_hop,
@@ -142,8 +192,8 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
     prm.ld_in = ld_in; prm.ld_out = ld_out; prm.n_streams = n_streams; prm.n_hops = n_hops; prm.mode = mode; prm.L = L;
     prm.dbg_hop = dbg_hop; prm.compression = compression;
     try {
-#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key) && S == SV && tc == (int)(TCV)) return fe::run_variant<fe::Plan<fe::CFG, SV, TCV>>(canonical, prm);
-        FE_ALL_VARIANTS(X)
+#define X(g) { const int rc = fee_run_g##g(&key, S, tc, canonical, &prm); if (rc != -1) return rc; }
+        FE_GROUPS(X)
 #undef X
     } catch (const std::exception& e) {
         std::fprintf(stderr, "fee_run: %s\n", e.what());
@@ -155,8 +205,9 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
 extern "C" int fee_tap_total(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads)
 {
     fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
-#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(key)) return fe::Frame<fe::Plan<fe::CFG, SV, TCV>>::TAP_TOTAL;
-    FE_ALL_VARIANTS(X)
+#define X(g) { const int rc = fee_tap_g##g(&key); if (rc != -1) return rc; }
+    FE_GROUPS(X)
 #undef X
     return -1;
 }
+#endif

@@ -16,12 +16,19 @@ from emu import emu
 VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 1), ("16k_m", 1), ("48k_t", 2), ("48k_s", 1)]
 # fp32 variants: FMA-pipe arithmetic; tensor-core variants: TF32 operands (rounded to nearest), fp32 accumulation
 # precision 2: as True, with the conv section's operands stored as fp16 (same 11-bit significand as TF32)
+# precision 3: bfloat16 conv section (8-bit significand), TF32 RNNFormer -- BASELINE config 3's "bf16 conv / fp32 GRU"
+# precision 4: split-fp16 operands (hi + lo, three MMAs per product): held to the fp32 tolerances
 TOL = {False: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4), True: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
-       2: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
+       2: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
+       3: dict(wav=1e-4, state=5e-3, tap=2e-2, spec=1e-2, spec_abs=2e-2),
+       4: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4)}
 F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_s", 2), ("16k_m", 1), ("48k_t", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
+BF16_VARIANTS = [("16k_b", 2), ("16k_m", 1), ("48k_l", 1)]
+SPLIT_VARIANTS = [("16k_t", 2), ("16k_b", 2), ("16k_b", 1), ("48k_b", 1)]
 
 
-@pytest.mark.parametrize("name,S,tc", [(n, s, t) for n, s in VARIANTS for t in (False, True)] + [(n, s, 2) for n, s in F16_VARIANTS])
+@pytest.mark.parametrize("name,S,tc", [(n, s, t) for n, s in VARIANTS for t in (False, True)] + [(n, s, 2) for n, s in F16_VARIANTS] +
+                         [(n, s, 3) for n, s in BF16_VARIANTS] + [(n, s, 4) for n, s in SPLIT_VARIANTS])
 def test_streaming_and_state_round_trip(name, S, tc, canonical):
     cfg = PRESETS[name]
     canon = canonical(name)
@@ -51,7 +58,8 @@ def test_streaming_and_state_round_trip(name, S, tc, canonical):
         off += n
 
 
-@pytest.mark.parametrize("name,S,tc", [("16k_t", 2, False), ("16k_t", 2, True), ("16k_m", 1, False), ("16k_m", 1, True), ("16k_t", 2, 2), ("16k_b", 2, 2)])
+@pytest.mark.parametrize("name,S,tc", [("16k_t", 2, False), ("16k_t", 2, True), ("16k_m", 1, False), ("16k_m", 1, True), ("16k_t", 2, 2), ("16k_b", 2, 2),
+                                       ("16k_m", 1, 3), ("16k_b", 2, 4)])
 def test_spec_and_offline_modes(name, S, tc, canonical):
     cfg = PRESETS[name]
     canon = canonical(name)

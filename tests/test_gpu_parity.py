@@ -1,11 +1,19 @@
 """Parity of the fused CUDA kernel (through the C ABI, fastenhancer_b200.engine) against the CPU oracle and
 against the committed golden vectors produced by the reference itself (tools/gen_golden.py).
 
-Tolerance (north-star): <= 1e-4 RMS on the enhanced waveform against the fp32 reference.  All three arithmetic modes of
-the engine are tested: "fp32" (every multiply-add on the FMA pipe) is held to 1e-5 RMS, "tf32" (the default: contractions
-on tcgen05 tensor cores with TF32 operands and fp32 accumulation) and "f16" (as tf32, with the conv section's activations and
-weights stored as fp16 -- the same 11-bit significand) to 5e-5 RMS.  Frame indexing (hop alignment, n_fft - hop delay, output
-lengths, zero Nyquist bin) is checked exactly in all of them."""
+Tolerance (north-star): <= 1e-4 RMS on the enhanced waveform against the fp32 reference.  All five arithmetic modes of
+the engine are tested.  The two fp32-accurate ones -- "fp32x3" (the default where it exists: tensor-core contractions on
+split-fp16 operands, three MMAs per product) and "fp32" (every multiply-add on the FMA pipe) -- are held to 1e-5 RMS on the
+waveform and 2e-5 on the GRU state; "tf32" (TF32 operands, fp32 accumulation) and "f16" (as tf32, with the conv section's
+activations and weights stored as fp16 -- the same 11-bit significand) to 5e-5 RMS; "bf16" (BASELINE config 3's "bf16 conv /
+fp32 GRU": bfloat16 conv section, 8-bit significand, TF32 RNNFormer, fp32 state) to 1e-4 RMS.  Frame indexing (hop
+alignment, n_fft - hop delay, output lengths, zero Nyquist bin) is checked exactly in all of them.
+
+Those numbers are for the seed-0 synthetic checkpoint, whose mask head has bias [1, 0] (mask ~ identity + a small network
+term), which attenuates network error in the waveform.  `test_network_dominated_mask` repeats the comparison on a checkpoint
+whose mask is driven by the network alone (zero head bias, final transposed-conv weights x 15) and reports RELATIVE error:
+the fp32-accurate modes must stay below 2e-5 relative there, the reduced-precision ones below 5e-3 (tf32 / f16) and
+2e-2 (bf16) -- which is why they are opt-in and not the default."""
 import numpy as np
 import pytest
 import torch
@@ -21,11 +29,18 @@ N_HOPS = 24
 
 #                 waveform RMS, state max, tap relative, spectrum relative
 TOL = {"fp32": dict(wav=1e-5, state=2e-5, tap=2e-5, spec=1e-5, spec_abs=1e-4),
+       "fp32x3": dict(wav=1e-5, state=2e-5, tap=2e-5, spec=1e-5, spec_abs=1e-4),
        "tf32": dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
-       "f16": dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3)}
+       "f16": dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
+       "bf16": dict(wav=1e-4, state=5e-3, tap=2e-2, spec=1e-2, spec_abs=2e-2)}
+#: relative waveform RMS error on the network-dominated-mask checkpoint
+TOL_NET = {"fp32": 2e-5, "fp32x3": 2e-5, "tf32": 5e-3, "f16": 5e-3, "bf16": 2e-2}
+#: presets that have kernels of the optional families (fe_configs.h)
+HAS = {"fp32x3": {"16k_t", "16k_b", "48k_t", "48k_b"},
+       "bf16": {"16k_t", "16k_b", "16k_s", "16k_m", "16k_l", "48k_m", "48k_l"}}
 
 
-@pytest.fixture(scope="module", params=["tf32", "fp32", "f16"])
+@pytest.fixture(scope="module", params=["fp32x3", "tf32", "fp32", "f16", "bf16"])
 def precision(request):
     return request.param
 
@@ -36,6 +51,8 @@ def engines(canonical, precision):
     cache = {}
 
     def get(name):
+        if name not in HAS.get(precision, PRESETS):
+            pytest.skip(f"{name} has no {precision} kernels")
         if name not in cache:
             cache[name] = Engine(PRESETS[name], canonical(name), "cuda:0", precision=precision)
             assert cache[name].precision == precision
@@ -245,3 +262,98 @@ def test_reference_style_composition_with_stft_shims(golden):
         ref = torch.fft.rfft(torch.cat([torch.zeros(2, cfg.n_fft - H, device="cuda"), x[:, :H]], dim=1) * m.stft.window.cuda(), dim=1)
         got, _ = m.stft(x[:, :H], None)
         assert (torch.view_as_complex(got[:, :, 0].contiguous()) - ref).abs().max() < 1e-5 * ref.abs().max()
+
+
+def _net_mask_canonical(name, canonical):
+    """canonical weights of the seed-0 checkpoint with a NETWORK-DOMINATED mask: zero bias of the final transposed conv
+    (instead of [1, 0]) and its weights x 15, so the mask is the network output alone and precision loss in the network
+    is not attenuated in the waveform."""
+    from fastenhancer_b200.schema import canonical_schema
+    cfg = PRESETS[name]
+    w = canonical(name).copy()
+    off = 0
+    for nm, shp in canonical_schema(cfg):
+        n = int(np.prod(shp))
+        if nm == "dec_post.wt":
+            w[off:off + n] *= 15.0
+        if nm == "dec_post.bt":
+            w[off:off + n] = 0.0
+        off += n
+    return w
+
+
+@pytest.mark.parametrize("name", ["16k_b", "16k_m"])
+def test_network_dominated_mask(name, canonical, precision):
+    from fastenhancer_b200.engine import Engine
+    from oracle.oracle import Oracle
+    if name not in HAS.get(precision, PRESETS):
+        pytest.skip(f"{name} has no {precision} kernels")
+    cfg = PRESETS[name]
+    w = _net_mask_canonical(name, canonical)
+    x = synthetic_noisy(4, 40 * cfg.hop_size, cfg.sample_rate)
+    want = Oracle(cfg, w).stream(np.zeros((4, cfg.state_floats), np.float32), x)
+    eng = Engine(cfg, w, "cuda:0", precision=precision)
+    got = eng.stream(eng.new_state(4), torch.from_numpy(x).cuda()).cpu().numpy()
+    rel = rms(got - want) / rms(want)
+    print(f"network-dominated mask, {name} {precision}: output rms {rms(want):.3f}, relative rms error {rel:.2e}")
+    assert rms(want) > 0.02                      # the mask really is the network
+    assert rel < TOL_NET[precision]
+
+
+#: BASELINE configs at their real horizon (SURVEY 8(d)): B 626 hops, M 1 003, L 1 605, 48 kHz L 2 405
+LONG = [("16k_b", 626), ("16k_m", 1003), ("16k_l", 1605), ("48k_l", 2405)]
+_LONG_CACHE = {}
+
+
+@pytest.mark.parametrize("name,n_hops", LONG)
+def test_long_horizon_against_oracle(name, n_hops, canonical, engines, precision):
+    """the GRU recurrence over the whole utterance: waveform and final state against the oracle, no drift in any mode."""
+    cfg, eng = PRESETS[name], engines(name)
+    B = 2 if cfg.channels < 128 else 1                          # the L configs cost the CPU oracle ~1 min per stream
+    x = synthetic_noisy(B, n_hops * cfg.hop_size, cfg.sample_rate, first_stream=11)
+    if name not in _LONG_CACHE:                                 # one oracle run serves every precision
+        o = _oracle(name, canonical)
+        ost = o.new_state(B)
+        _LONG_CACHE[name] = (o.stream(ost, x, n_threads=B), ost)
+    want, ost = _LONG_CACHE[name]
+    st = eng.new_state(B)
+    got = eng.stream(st, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rms(got - want) < TOL[precision]["wav"]
+    tail = slice((n_hops - 50) * cfg.hop_size, None)          # the error is not growing: the last 50 hops on their own
+    assert rms(got[:, tail] - want[:, tail]) < TOL[precision]["wav"]
+    assert np.abs(st.export().cpu().numpy() - ost).max() < TOL[precision]["state"]
+
+
+@pytest.mark.parametrize("name", ["16k_b", "16k_m"])
+def test_long_horizon_against_reference_golden(name, golden, engines, precision):
+    """>= 600 hops of the REFERENCE's own streaming graph (tools/gen_golden.py --long): the tail of the waveform and the
+    final state, so that the oracle itself is pinned over a long recurrence."""
+    g = golden(name + "_long")
+    cfg, eng = PRESETS[name], engines(name)
+    n_hops, keep = int(g["n_hops"]), int(g["keep_hops"])
+    x = synthetic_noisy(1, n_hops * cfg.hop_size, cfg.sample_rate, first_stream=5)
+    st = eng.new_state(1)
+    y = eng.stream(st, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rms(y[:, -keep * cfg.hop_size:] - g["stream_tail"]) < TOL[precision]["wav"]
+    assert np.abs(st.export().cpu().numpy() - g["stream_state"]).max() < TOL[precision]["state"]
+
+
+def test_two_states_stream_host_concurrently(engines):
+    """fe_stream_host keeps its staging buffers / streams in the state: two states of one engine driven from two host
+    threads give the same bits as one after the other."""
+    import threading
+    cfg, eng = PRESETS["16k_b"], engines("16k_b")
+    H = cfg.hop_size
+    xs = [torch.from_numpy(synthetic_noisy(8, 64 * H, cfg.sample_rate, first_stream=8 * i)).pin_memory() for i in range(2)]
+    want = [eng.stream(eng.new_state(8), x.cuda()).cpu() for x in xs]
+    states = [eng.new_state(8) for _ in range(2)]
+    outs = [None, None]
+
+    def work(i):
+        outs[i] = eng.stream_host(states[i], xs[i], hops_per_chunk=4)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert torch.equal(outs[0], want[0]) and torch.equal(outs[1], want[1])

@@ -120,3 +120,17 @@ def test_streaming_equals_offline_interior(canonical):
     ys = ys[:, N - H:N - H + L]
     # the GRU state differs at t=0 (offline sees a reflected first frame), so compare late frames
     assert rms(ys[:, 20 * H:28 * H] - off[:, 20 * H:28 * H]) < 5e-3 * rms(off)
+
+
+@pytest.mark.parametrize("name", ["16k_b", "16k_m"])
+def test_long_horizon_streaming(name, golden, canonical):
+    """the oracle over the WHOLE 10 s utterance (626 / 1 003 hops) against the reference's own streaming graph
+    (tools/gen_golden.py --long): the recurrence does not drift away from the reference."""
+    cfg, g = PRESETS[name], golden(name + "_long")
+    n_hops, keep = int(g["n_hops"]), int(g["keep_hops"])
+    o = Oracle(cfg, canonical(name))
+    x = synthetic_noisy(1, n_hops * cfg.hop_size, cfg.sample_rate, first_stream=5)
+    state = o.new_state(1)
+    y = o.stream(state, x)
+    assert rms(y[:, -keep * cfg.hop_size:] - g["stream_tail"]) < 1e-6
+    assert np.abs(state - g["stream_state"]).max() < 1e-5

@@ -72,9 +72,45 @@ def reference_canonical(cfg, m) -> np.ndarray:
     return np.concatenate([np.asarray(t[n], np.float32).reshape(-1) for n, _ in canonical_schema(cfg)])
 
 
+LONG_HOPS = {"16k_b": 626, "16k_m": 1003}      # BASELINE configs 2 / 3 at their real horizon (10 s utterances)
+LONG_KEEP = 50                                  # hops of the tail kept in the fixture
+
+
+def gen_long(ONNXModel, name):
+    """tests/golden/<name>_long.npz: the reference's streaming graph over the whole 10 s utterance, one stream; keeps the last
+    LONG_KEEP hops of the waveform and the final caches (a long-recurrence pin for the oracle and the kernels)."""
+    cfg = PRESETS[name]
+    n_hops = LONG_HOPS[name]
+    H, N, K, F2, C2 = cfg.hop_size, cfg.n_fft, cfg.rf_blocks, cfg.rf_freq, cfg.rf_channels
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in synthetic_state_dict(cfg, seed=0).items()}
+    with torch.no_grad():
+        m = ONNXModel(**cfg.to_model_kwargs()).eval()
+        m.load_state_dict(sd, strict=True)
+        m.remove_weight_reparameterizations()
+        x = torch.from_numpy(synthetic_noisy(1, n_hops * H, cfg.sample_rate, first_stream=5))
+        c_stft, c_istft = torch.zeros(1, N - H), torch.zeros(1, N - H)
+        hs = [torch.zeros(1, F2, C2) for _ in range(K)]
+        hops = []
+        for i in range(n_hops):
+            spec_in, c_stft = m.stft(x[:, i * H:(i + 1) * H], c_stft)
+            spec_out, *hs = m(spec_in, *hs)
+            y, c_istft = m.stft.inverse(spec_out, c_istft)
+            hops.append(y.clone())
+    out = {"n_hops": np.int64(n_hops), "keep_hops": np.int64(LONG_KEEP),
+           "stream_tail": torch.cat(hops[-LONG_KEEP:], dim=1).numpy(),
+           "stream_state": torch.cat([c_stft, c_istft] + [h.view(1, F2 * C2) for h in hs], dim=1).numpy()}
+    path = os.path.join(ROOT, "tests", "golden", f"{name}_long.npz")
+    np.savez_compressed(path, torch_version=np.array(torch.__version__), **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), {n_hops} hops, tail rms {np.sqrt((out['stream_tail'] ** 2).mean()):.4f}")
+
+
 def main():
     Model, ONNXModel = import_reference()
     torch.set_num_threads(1)
+    if "--long" in sys.argv:
+        for name in [a for a in sys.argv[1:] if a != "--long"] or sorted(LONG_HOPS):
+            gen_long(ONNXModel, name)
+        return
     names = sys.argv[1:] or sorted(PRESETS)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for name in names:
