@@ -205,6 +205,10 @@ FE_DEV f2 silu2_half(f2 h) {
     f2 y; y.x = silu(2.f * h.x); y.y = silu(2.f * h.y); return y;
 #endif
 }
+// accurate forms (ex2.approx + rcp.approx, ~1e-7): the fp32-accurate split variants use these in place of the tanh.approx ones
+FE_DEV f2 silu2_acc(f2 x) { f2 y; y.x = silu(x.x); y.y = silu(x.y); return y; }
+FE_DEV f2 sigmoid2_acc(f2 x) { f2 y; y.x = sigmoid_acc(x.x); y.y = sigmoid_acc(x.y); return y; }
+FE_DEV f2 tanh2_acc(f2 x) { f2 y; y.x = tanh_acc(x.x); y.y = tanh_acc(x.y); return y; }
 FE_DEV f2 sigmoid2(f2 x) {
 #if FE_FAST_ACT >= 2
     f2 hh; hh.x = hh.y = 0.5f;
@@ -674,7 +678,10 @@ template <class P> struct Frame {
             float o[4];
             const f4 b4 = ldg4(bias + 4 * g);
             f2 t01 = add2(mk2(v[0], v[1]), mk2(b4.x, b4.y)), t23 = add2(mk2(v[2], v[3]), mk2(b4.z, b4.w));
-            if (act) { t01 = silu2_half(t01); t23 = silu2_half(t23); }
+            if (act) {
+                if constexpr (P::FAST_ACT) { t01 = silu2_half(t01); t23 = silu2_half(t23); }     // weights / bias pre-halved: t = x / 2
+                else { t01 = silu2_acc(t01); t23 = silu2_acc(t23); }
+            }
             o[0] = t01.x; o[1] = t01.y; o[2] = t23.x; o[3] = t23.y;
             if constexpr (P::H16) {
                 if (round) {         // operand of a later MMA: four halves (8 bytes) of the 8-channel row
@@ -1095,10 +1102,11 @@ template <class P> struct Frame {
                     ldg_pt<W>(aux + ab.b_in + c, bi); ldg_pt<W>(aux + ab.b_hn + c, bh);
 #pragma unroll
                     for (int e = 0; e < W; e += 2) {
-                        const f2 r = sigmoid2(add2(mk2(vr[e], vr[e + 1]), mk2(br[e], br[e + 1])));
-                        const f2 z = sigmoid2(add2(mk2(vz[e], vz[e + 1]), mk2(bz[e], bz[e + 1])));
-                        const f2 nn = tanh2(fma2(r, add2(mk2(vh[e], vh[e + 1]), mk2(bh[e], bh[e + 1])),
-                                                 add2(mk2(vx[e], vx[e + 1]), mk2(bi[e], bi[e + 1]))));
+                        const f2 ar = add2(mk2(vr[e], vr[e + 1]), mk2(br[e], br[e + 1])), az = add2(mk2(vz[e], vz[e + 1]), mk2(bz[e], bz[e + 1]));
+                        const f2 r = P::FAST_ACT ? sigmoid2(ar) : sigmoid2_acc(ar);
+                        const f2 z = P::FAST_ACT ? sigmoid2(az) : sigmoid2_acc(az);
+                        const f2 an = fma2(r, add2(mk2(vh[e], vh[e + 1]), mk2(bh[e], bh[e + 1])), add2(mk2(vx[e], vx[e + 1]), mk2(bi[e], bi[e + 1])));
+                        const f2 nn = P::FAST_ACT ? tanh2(an) : tanh2_acc(an);
                         // (1 - z) n + z h = n + z (h - n)
                         const f2 hv = fma2(z, add2(mk2(hov[e], hov[e + 1]), mk2(-nn.x, -nn.y)), nn);
                         hn[e] = hv.x; hn[e + 1] = hv.y;

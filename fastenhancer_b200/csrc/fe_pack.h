@@ -258,8 +258,8 @@ public:
         cp(A.dp_b, cw.dp_b, C1);
         // Tensor-core variants: layers followed by SiLU carry weights and bias pre-multiplied by 1/2 (exact), so the accumulator is
         // h = x / 2 and the epilogue computes silu(x) = h + h tanh(h) without the extra multiply.
-        constexpr float HS = P::TC ? 0.5f : 1.f;
-        if constexpr (P::TC) {
+        constexpr float HS = P::FAST_ACT ? 0.5f : 1.f;
+        if constexpr (P::FAST_ACT) {
             auto half = [&](int dst, int n) { for (int i = 0; i < n; ++i) blob_[dst + i] *= 0.5f; };
             half(A.enc_pre_b, C1);
             for (int i = 0; i < C::E; ++i) { half(A.enc_b(i), C1); half(A.dec1_b(i), C1); half(A.dec2_b(i), C1); }

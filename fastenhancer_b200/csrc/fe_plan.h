@@ -229,6 +229,9 @@ struct Plan {
     static constexpr bool BF16 = PREC_ == 3;           // ... bfloat16 instead of fp16
     static constexpr bool SPLIT = PREC_ == 4;          // ... stored as hi + lo fp16 parts
     static constexpr int NPART = SPLIT ? 2 : 1;
+    // tanh.approx-based SiLU / GRU gates (error ~2^-11, the size of the operand rounding that follows) in the reduced-precision tensor-core
+    // variants; the fp32-accurate split variants use the ex2 / rcp forms (~1e-7) and un-halved SiLU layers
+    static constexpr bool FAST_ACT = TC && !SPLIT;
     static constexpr int CG = H16 ? 8 : 4;             // channels per 16-byte row of a conv-section operand buffer
     static constexpr int KEC = H16 ? 16 : 8;           // contraction length of one conv-section MMA
     static constexpr int C1P = H16 ? round_up(C::C1, 16) : C::C1;                 // conv channels padded to a k-step
