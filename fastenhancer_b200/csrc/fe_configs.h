@@ -25,15 +25,27 @@ using C48L = Cfg< 1024, 200, 128, 4, 96, 96, 5>;
 template <> struct Tune<C16T, 1> : TuneBase<C16T, 1> { static constexpr int STAGES = 3; };
 template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAGES = 3; };
 #endif
+// B, 4 streams per CTA (throughput variant for thousands of streams: the RNNFormer tiles carry 96 of 128 rows instead of 48, the conv
+// section runs two M tiles per layer): the activations of four streams leave room for a 2 x 16 KB weight ring only.
+template <> struct Tune<C16B, 4> : TuneBase<C16B, 4> { static constexpr int CHUNK = 4096; };
 }  // namespace fe
 
+// (B with 4 streams per CTA exists only with the tensor-core frequency-axis linears: the FMA-pipe form does not tile 4 streams)
+#ifndef FE_LIN_TC
+#define FE_LIN_TC 1
+#endif
+#if FE_LIN_TC
+#define FE_IF_LIN_TC(x) x
+#else
+#define FE_IF_LIN_TC(x)
+#endif
 // X(config id, Cfg type, S, PREC)   PREC: false / 0 = everything on the fp32 FMA pipe; true / 1 = contractions on tcgen05 (TF32);
 // 2 = as 1 with the conv section's operands in fp16 (K = 16 per MMA, half the shared memory); 3 = bfloat16 conv section, TF32 RNNFormer
 // (BASELINE config 3: "bf16 conv / fp32 GRU"); 4 = fp32-accurate split-fp16 operands, three MMAs per product (fe_plan.h)
 #define FE_VARIANTS_16T(X) X(0, C16T, 1, false) X(0, C16T, 2, false) X(0, C16T, 4, false) X(0, C16T, 1, true) X(0, C16T, 2, true) X(0, C16T, 4, true) \
     X(0, C16T, 1, 2) X(0, C16T, 2, 2) X(0, C16T, 4, 2) X(0, C16T, 2, 3) X(0, C16T, 1, 4) X(0, C16T, 2, 4)
 #define FE_VARIANTS_16B(X) X(1, C16B, 1, false) X(1, C16B, 2, false) X(1, C16B, 1, true) X(1, C16B, 2, true) X(1, C16B, 1, 2) X(1, C16B, 2, 2) \
-    X(1, C16B, 2, 3) X(1, C16B, 1, 4) X(1, C16B, 2, 4)
+    X(1, C16B, 2, 3) X(1, C16B, 1, 4) X(1, C16B, 2, 4) FE_IF_LIN_TC(X(1, C16B, 4, 2))
 #define FE_VARIANTS_16S(X) X(2, C16S, 1, false) X(2, C16S, 1, true) X(2, C16S, 1, 2) X(2, C16S, 2, 2) X(2, C16S, 1, 3)
 #define FE_VARIANTS_16M(X) X(3, C16M, 1, false) X(3, C16M, 1, true) X(3, C16M, 1, 2) X(3, C16M, 1, 3)
 #define FE_VARIANTS_16L(X) X(4, C16L, 1, false) X(4, C16L, 1, true) X(4, C16L, 1, 2) X(4, C16L, 1, 3)

@@ -103,6 +103,14 @@ template <class P> struct GpuCtx {
         d.hi = (128u >> 4) | (1u << 14);
         return d;
     }
+    // MN-major / no-swizzle operand (the N or M index is the contiguous one: 8 halves per 16-byte row, 8 k rows per 128-byte core
+    // matrix): LBO = 128 B between groups of 8 k rows, SBO = pitch between the 16-byte groups along N (validated by tools/tc_probe_mn.cu)
+    __device__ __forceinline__ Desc make_desc_mn(const float* p, int sbo_floats) const {
+        Desc d;
+        d.lo = ((smem_u32(p) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
+        d.hi = (((uint32_t)sbo_floats * 4u) >> 4) | (1u << 14);
+        return d;
+    }
     __device__ __forceinline__ Desc desc_add(Desc d, int floats) const { d.lo += (uint32_t)(floats >> 2); return d; }
     __device__ __forceinline__ Desc desc_set_lbo(Desc d, int lbo_floats) const {
         d.lo = (d.lo & 0x0000ffffu) | ((((uint32_t)lbo_floats * 4u) >> 4) << 16);
@@ -126,14 +134,16 @@ template <class P> struct GpuCtx {
     // M64: a 64-row MMA, whose accumulator row r lives in TMEM lane 32 * (r / 16) + r % 16 (tools/tc_bench2.cu probes the mapping).
     // FMT: 0 = kind::tf32; 1 / 2 = kind::f16 with fp16 / bfloat16 operands (8 per 16-byte row: K = 16 per MMA), same descriptors.
     static constexpr int FMT16 = P::BF16 ? 2 : 1;      // the 16-bit operand format of this variant's conv section
-    template <bool M64 = false, int FMT = 0>
+    // BMN: the B operand is MN-major (instruction-descriptor bit 16)
+    template <bool M64 = false, int FMT = 0, bool BMN = false>
     __device__ __forceinline__ void mma(int /*tid*/, Desc a, Desc b, int np, int col, bool acc, int /*rows*/) const {
         const uint64_t da = ((uint64_t)a.hi << 32) | a.lo, db = ((uint64_t)b.hi << 32) | b.lo;
+        static_assert(!BMN || FMT != 0, "MN-major operands: 16-bit kinds only");
         if constexpr (FMT != 0)
             asm volatile(
                 "{\n\t" FE_MMA_ELECT
                 FE_MMA_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_f16(M64 ? 64 : 128, np, FMT == 2)), "r"(acc ? 1u : 0u) : "memory");
+                ::"r"(tmem + (uint32_t)col), "l"(da), "l"(db), "r"(umma_idesc_f16(M64 ? 64 : 128, np, FMT == 2) | (BMN ? (1u << 16) : 0u)), "r"(acc ? 1u : 0u) : "memory");
         else
             asm volatile(
                 "{\n\t" FE_MMA_ELECT

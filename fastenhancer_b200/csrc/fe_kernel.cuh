@@ -45,6 +45,7 @@ inline f4 ldg4(const float* p) { return ld4(p); }
 inline float fe_exp(float x) { return expf(x); }
 inline float fe_exp2(float x) { return exp2f(x); }
 inline float fe_div(float a, float b) { return a / b; }
+inline float fe_rcp(float a) { return 1.0f / a; }
 inline float tf32_rna(float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline float tf32_pre(float x) { uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; std::memcpy(&x, &u, 4); return x; }
 inline void sth(float* base, int idx, float v) { reinterpret_cast<uint16_t*>(base)[idx] = f32_to_f16_bits(v); }      // store one half
@@ -69,6 +70,7 @@ FE_DEV f4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)
 FE_DEV float fe_exp(float x) { return __expf(x); }
 FE_DEV float fe_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 FE_DEV float fe_div(float a, float b) { return __fdividef(a, b); }
+FE_DEV float fe_rcp(float a) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; }
 // round to nearest TF32 so that the tensor core (which reads the top 19 bits) sees the value exactly
 FE_DEV float tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
 // Rounding for values that only the tensor core reads: the MMA ignores the low 13 bits, so adding half a TF32 ulp to the bit pattern
@@ -170,11 +172,9 @@ FE_DEV void split_h2(float a, float b, float& hi, float& lo) {
 }
 FE_DEV float silu(float x) { return fe_div(x, 1.0f + fe_exp(-x)); }
 // GRU gates: ex2.approx / rcp.approx based (absolute error ~1e-7, far inside the fp32 noise of the recurrence)
-FE_DEV float sigmoid_acc(float x) { return fe_div(1.0f, 1.0f + fe_exp(-x)); }
-FE_DEV float tanh_acc(float x) {
-    const float xc = fminf(fmaxf(x, -15.f), 15.f);
-    return 1.0f - fe_div(2.0f, 1.0f + fe_exp(2.0f * xc));
-}
+// (ex2 saturates to +inf / 0 and rcp(+inf) = 0, so neither form needs a clamp)
+FE_DEV float sigmoid_acc(float x) { return fe_rcp(1.0f + fe_exp2(-1.4426950408889634f * x)); }
+FE_DEV float tanh_acc(float x) { return fmaf(2.0f, fe_rcp(1.0f + fe_exp2(-2.8853900817779268f * x)), -1.0f); }
 // Single-MUFU forms for the tensor-core variants' epilogues (tanh.approx.f32, error ~2^-11 -- the same size as the
 // TF32 rounding the value gets right after): silu(x) = h + h tanh(h), sigmoid(x) = 0.5 + 0.5 tanh(h), h = x / 2.
 #if defined(FE_EMU)
@@ -209,6 +209,26 @@ FE_DEV f2 silu2_half(f2 h) {
 FE_DEV f2 silu2_acc(f2 x) { f2 y; y.x = silu(x.x); y.y = silu(x.y); return y; }
 FE_DEV f2 sigmoid2_acc(f2 x) { f2 y; y.x = sigmoid_acc(x.x); y.y = sigmoid_acc(x.y); return y; }
 FE_DEV f2 tanh2_acc(f2 x) { f2 y; y.x = tanh_acc(x.x); y.y = tanh_acc(x.y); return y; }
+// FE_H2_SILU (experiment, fp16 variants): SiLU of a pre-halved pair straight to packed halves -- cvt.rn.f16x2, ONE tanh.approx.f16x2
+// (two elements per MUFU op) and one fma.rn.f16x2 instead of two MUFU.TANH + FFMA2 + cvt: the conv epilogues are MUFU-bound
+// (16 ops / clk / SM on sm_100a).  Costs about one fp16 ulp of extra error per activation.
+#ifndef FE_H2_SILU
+#define FE_H2_SILU 0
+#endif
+#if defined(FE_EMU)
+FE_DEV float silu_half_h2(f2 h) {
+    const float a = rnd_h(h.x), b = rnd_h(h.y);
+    return pack_h2(fmaf(a, rnd_h(tanhf(a)), a), fmaf(b, rnd_h(tanhf(b)), b));
+}
+#else
+FE_DEV float silu_half_h2(f2 h) {
+    uint32_t u, t, r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(h.y), "f"(h.x));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(u), "r"(t));
+    return __uint_as_float(r);
+}
+#endif
 FE_DEV f2 sigmoid2(f2 x) {
 #if FE_FAST_ACT >= 2
     f2 hh; hh.x = hh.y = 0.5f;
@@ -452,7 +472,7 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
         x.sub_end(tid, PH_TC_WAITW);
         if ((tid >> 5) == 0) {
             x.mma_fence();
-            const typename X::Desc wd = x.make_desc(w, L::NP * 4);
+            const typename X::Desc wd = x.make_desc(w, L::WLBO);
             // one election per chunk: the elected lane issues the whole unrolled MMA sequence (x.mma itself does not elect)
             if (x.elect(tid)) {
 #pragma unroll
@@ -600,6 +620,23 @@ FE_DEV void rf_layer_ts(X& x, int tid, int ci, int a_col0, Epi epi, int alo = 0)
     tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
 }
 
+// Frequency-axis linear on the tensor cores (TcLin): the weights are the A operand (K-major tiles from the ring, 128 rows per M tile),
+// the activation buffer is the B operand, MN-major; b0 = its descriptor at the first slot of the contraction, blo = float offset to
+// its low parts (split variants: hi * hi, hi * lo, lo * hi with the roles of A and B swapped relative to the conv-type layers).
+template <class L, class X>
+FE_DEV void tc_lin_mmas(X& x, int tid, int ci, typename X::Desc b0, int blo) {
+    constexpr int FMT = X::FMT16;
+    tc_stream<L>(x, tid, ci, [&](int tile, typename X::Desc wd) {
+        const int mt = tile / L::NKS, j = tile % L::NKS;
+        const auto b = x.desc_add(b0, j * 16 * 4);                  // 16 slots of 16 bytes per k-step
+        x.template mma<false, FMT, true>(tid, wd, b, L::N, mt * L::N, j > 0, 128);
+        if constexpr (L::PARTS == 2) {
+            x.template mma<false, FMT, true>(tid, wd, x.desc_add(b, blo), L::N, mt * L::N, true, 128);
+            x.template mma<false, FMT, true>(tid, x.desc_add(wd, L::TILE1), b, L::N, mt * L::N, true, 128);
+        }
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // The frame.
 // ---------------------------------------------------------------------------------------------
@@ -678,6 +715,19 @@ template <class P> struct Frame {
             float o[4];
             const f4 b4 = ldg4(bias + 4 * g);
             f2 t01 = add2(mk2(v[0], v[1]), mk2(b4.x, b4.y)), t23 = add2(mk2(v[2], v[3]), mk2(b4.z, b4.w));
+#if FE_H2_SILU
+            if constexpr (P::H16 && !P::BF16 && !P::SPLIT) {
+                if (act && round) {           // every SiLU layer of the conv section feeds another MMA
+                    const int off = (g >> 1) * SLABF + (S + gp) * 4 + (g & 1) * 2;
+                    const f2 h = mk2(silu_half_h2(t01), silu_half_h2(t23));
+                    st2(dst + off, h);
+                    if constexpr (P::SKIP_SMEM < P::NSK) {
+                        if (gdst) st2(gdst + off, h);
+                    }
+                    return;
+                }
+            }
+#endif
             if (act) {
                 if constexpr (P::FAST_ACT) { t01 = silu2_half(t01); t23 = silu2_half(t23); }     // weights / bias pre-halved: t = x / 2
                 else { t01 = silu2_acc(t01); t23 = silu2_acc(t23); }
@@ -990,31 +1040,48 @@ template <class P> struct Frame {
             }
         };
 
-        // rf_pre: Linear(F1 -> F2) on the frequency axis (FMA pipe, reads the conv-section layout) ...
-        x.phase(PH_LIN_PRE, [&](int tid) {
-            // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
-            constexpr int XFMT = P::SPLIT ? 3 : (P::BF16 ? 2 : (P::H16 ? 1 : 0));
-            row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, !P::H16, XFMT>(x, tid, ci,
-                [&](int l) { return enc_last + (P::H16 ? act_off16(4 * (l / S), l % S, 0) : act_off(4 * (l / S), l % S, 0)); }, S * 4,
-                [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
-                float* yr = Y1 + (P::H16 ? rf_off16(4 * (l / S), l % S, 0) : rf_off(4 * (l / S), l % S, 0));
+        // rf_pre: Linear(F1 -> F2) on the frequency axis ...
+        if constexpr (P::LIN_TC) {      // ... on the tensor cores: a contraction over the slots of the last encoder output
+            x.phase(PH_LIN_PRE, [&](int tid) {
+                using L = typename P::TLinPre;
+                tc_lin_mmas<L>(x, tid, ci, x.make_desc_mn(enc_last + S * 4, SLABF), P::ACT1);
+                tc_epilogue<L>(x, tid, [&](int gp, int g, const float* v) {        // gp = RNNFormer slot f2 * S + s, g = 4-channel group
+                    float* yr = Y1 + (g >> 1) * RSLABF + gp * 4 + (g & 1) * 2;
+                    if constexpr (P::SPLIT) {
+                        f2 h, lo;
+                        split_h2(v[0], v[1], h.x, lo.x); split_h2(v[2], v[3], h.y, lo.y);
+                        st2(yr, h); st2(yr + P::Y1T1, lo);
+                    } else st2(yr, mk2(pack_h2<P::BF16>(v[0], v[1]), pack_h2<P::BF16>(v[2], v[3])));
+                });
+            });
+            ci += P::TLinPre::NCHUNK;
+        } else {
+        // ... on the FMA pipe, reading the conv-section layout
+            x.phase(PH_LIN_PRE, [&](int tid) {
+                // lane = (channel group c4, stream s): 4 channels x all F1 frequencies of one stream
+                constexpr int XFMT = P::SPLIT ? 3 : (P::BF16 ? 2 : (P::H16 ? 1 : 0));
+                row_gemm_k1v<typename P::LinPreT, (C1 / 4) * S, !P::H16, XFMT>(x, tid, ci,
+                    [&](int l) { return enc_last + (P::H16 ? act_off16(4 * (l / S), l % S, 0) : act_off(4 * (l / S), l % S, 0)); }, S * 4,
+                    [&](int l, int o0, const float (&a)[4][P::LinPreT::NO]) {
+                    float* yr = Y1 + (P::H16 ? rf_off16(4 * (l / S), l % S, 0) : rf_off(4 * (l / S), l % S, 0));
 #pragma unroll
-                for (int j = 0; j < P::LinPreT::NO; ++j)
-                    if (o0 + j < F2) {
-                        if constexpr (P::SPLIT) {
-                            f2 h, lo;
-                            split_h2(a[0][j], a[1][j], h.x, lo.x); split_h2(a[2][j], a[3][j], h.y, lo.y);
-                            st2(yr + (o0 + j) * S * 4, h); st2(yr + P::Y1T1 + (o0 + j) * S * 4, lo);
-                        } else if constexpr (P::H16) st2(yr + (o0 + j) * S * 4, mk2(pack_h2<P::BF16>(a[0][j], a[1][j]), pack_h2<P::BF16>(a[2][j], a[3][j])));
-                        else st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
-                    }
-            }, P::ACT1);
-            if constexpr (P::H16 && P::C1P > C1) {      // the slab that pads the channels to a whole k-step (scratch: re-zeroed every hop)
-                for (int idx = tid; idx < P::NPART * P::RSLOTS; idx += NT)
-                    st4(Y1 + (idx / P::RSLOTS) * P::Y1T1 + (P::C1P / 8 - 1) * RSLABF + (idx % P::RSLOTS) * 4, mk4(0.f, 0.f, 0.f, 0.f));
-            }
-        });
-        ci += P::LinPreT::NCHUNK;
+                    for (int j = 0; j < P::LinPreT::NO; ++j)
+                        if (o0 + j < F2) {
+                            if constexpr (P::SPLIT) {
+                                f2 h, lo;
+                                split_h2(a[0][j], a[1][j], h.x, lo.x); split_h2(a[2][j], a[3][j], h.y, lo.y);
+                                st2(yr + (o0 + j) * S * 4, h); st2(yr + P::Y1T1 + (o0 + j) * S * 4, lo);
+                            } else if constexpr (P::H16) st2(yr + (o0 + j) * S * 4, mk2(pack_h2<P::BF16>(a[0][j], a[1][j]), pack_h2<P::BF16>(a[2][j], a[3][j])));
+                            else st4(yr + (o0 + j) * S * 4, mk4(tf32_pre(a[0][j]), tf32_pre(a[1][j]), tf32_pre(a[2][j]), tf32_pre(a[3][j])));
+                        }
+                }, P::ACT1);
+                if constexpr (P::H16 && P::C1P > C1) {      // the slab that pads the channels to a whole k-step (scratch: re-zeroed every hop)
+                    for (int idx = tid; idx < P::NPART * P::RSLOTS; idx += NT)
+                        st4(Y1 + (idx / P::RSLOTS) * P::Y1T1 + (P::C1P / 8 - 1) * RSLABF + (idx % P::RSLOTS) * 4, mk4(0.f, 0.f, 0.f, 0.f));
+                }
+            });
+            ci += P::LinPreT::NCHUNK;
+        }
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
         x.phase(PH_RF_PRE, [&](int tid) {
             const auto a0 = x.make_desc(Y1, RSLABF);
@@ -1380,6 +1447,25 @@ template <class P> struct Frame {
 #pragma unroll
                     for (int e = 0; e < W; ++e) o[e] = xo[e] + v[e] + b[e];
                     store_x(p, c, o, valid, wt, WTag<0>{});
+                    if constexpr (P::LIN_TC && W == 4) {
+                        // the final x, as 16-bit values [C2H / 8][slot][8], is the B operand of the tensor-core rf_post linear: it takes the place
+                        // of the attention output (every MMA that read it has completed); the thread of the last real group zeroes the padding
+                        if (k == C::K - 1 && valid) {
+                            float* xh = ATT + (c >> 3) * RSLABF + p * 4 + ((c >> 2) & 1) * 2;
+                            if constexpr (P::SPLIT) {
+                                f2 h, lo;
+                                split_h2(o[0], o[1], h.x, lo.x); split_h2(o[2], o[3], h.y, lo.y);
+                                st2(xh, h); st2(xh + XTS, lo);
+                            } else st2(xh, mk2(pack_h2<P::BF16>(o[0], o[1]), pack_h2<P::BF16>(o[2], o[3])));
+                            if (c + 4 == C2) {
+                                for (int cc = C2; cc < P::C2H; cc += 4) {
+                                    float* zp = ATT + (cc >> 3) * RSLABF + p * 4 + ((cc >> 2) & 1) * 2;
+                                    st2(zp, mk2(0.f, 0.f));
+                                    if constexpr (P::SPLIT) st2(zp + XTS, mk2(0.f, 0.f));
+                                }
+                            }
+                        }
+                    }
                 }, XTS);
                 if constexpr (P::H_TMEM) x.tmem_st_wait();
             });
@@ -1883,7 +1969,31 @@ template <class P> struct Frame {
 
         // ================= rf_post: Linear(F2->F1), 1x1 conv =================
         float* Zb = AB + P::O_Z;
-        if constexpr (P::TC) {
+        if constexpr (P::LIN_TC) {
+            // rf_post: Linear(F2 -> F1) on the tensor cores, a contraction over the RNNFormer slots of the final x (16-bit copy left in the
+            // attention-output buffer by the last attn_fc epilogue), then the 1x1 conv C2 -> C1
+            float* XH = AB + P::O_ATT_T;
+            x.phase(PH_LIN_POST, [&](int tid) {
+                using L = typename P::TLinPost;
+                tc_lin_mmas<L>(x, tid, ci, x.make_desc_mn(XH, P::RSLABF), P::XTS);
+                tc_epilogue<L>(x, tid, [&](int gp, int g, const float* v) {        // gp = conv slot f1 * S + s, g = 4-channel group of C2Z
+                    float* zr = Zb + (g >> 1) * SLABF + (S + gp) * 4 + (g & 1) * 2;
+                    if constexpr (P::SPLIT) {
+                        f2 h, lo;
+                        split_h2(v[0], v[1], h.x, lo.x); split_h2(v[2], v[3], h.y, lo.y);
+                        st2(zr, h); st2(zr + P::ZB1, lo);
+                    } else st2(zr, mk2(pack_h2<P::BF16>(v[0], v[1]), pack_h2<P::BF16>(v[2], v[3])));
+                });
+            });
+            ci += P::TLinPost::NCHUNK;
+            TcEpiAct epi{W1, aux + A.rf_post_b, nullptr, false, true};
+            x.phase(PH_RF_POST, [&](int tid) {
+                zero_halo(W1, tid);          // W1 was FFT / RNNFormer scratch
+                const auto a0 = x.make_desc(Zb + S * 4, SLABF);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1);
+            });
+            ci += P::TRfPost::NCHUNK;
+        } else if constexpr (P::TC) {
             x.phase(PH_LIN_POST, [&](int tid) {
                 row_gemm_k1v<typename P::LinPostT, (C2 / 4) * S>(x, tid, ci, [&](int l) { return XR + rf_off(4 * (l / S), l % S, 0); }, S * 4,
                                                               [&](int l, int o0, const float (&a)[4][P::LinPostT::NO]) {

@@ -134,6 +134,30 @@ template <class P> class Packer {
         }
         off_ += L::FLOATS;
     }
+    // frequency-axis linear on the tensor cores (TcLin), w(f_out, f_in): tile (M tile mt, k-step j) = [2][128][8 halves] holding
+    // W[row 128 mt + r][slot 16 j + 8 kc2 + e] with row = f_out * S + s, slot = f_in * S + s' and W = (s == s') ? w(f_out, f_in) : 0
+    template <class L, class W> void lin(W w) {
+        for (int c = 0; c < L::NCHUNK; ++c) {
+            int tiles = cmin(L::TPC, L::NTILE - c * L::TPC);
+            table_.push_back((int)(off_ + (long)c * L::TPC * L::TILE));
+            table_.push_back(tiles * L::TILE);
+        }
+        for (int tile = 0; tile < L::NTILE; ++tile) {
+            const int mt = tile / L::NKS, j = tile % L::NKS;
+            uint16_t* h = reinterpret_cast<uint16_t*>(&blob_[off_ + (long)tile * L::TILE]);
+            uint16_t* lo = reinterpret_cast<uint16_t*>(&blob_[off_ + (long)tile * L::TILE + L::TILE1]);
+            for (int kc2 = 0; kc2 < 2; ++kc2)
+                for (int r = 0; r < 128; ++r)
+                    for (int e = 0; e < 8; ++e) {
+                        const int row = 128 * mt + r, k = 16 * j + 8 * kc2 + e;
+                        const float v = (row < L::NPOS && row % P::S == k % P::S) ? w(row / P::S, k / P::S) : 0.f;
+                        const uint16_t hb = f32_to_h16_bits<P::BF16>(v);
+                        h[(kc2 * 128 + r) * 8 + e] = hb;
+                        if constexpr (L::PARTS == 2) lo[(kc2 * 128 + r) * 8 + e] = f32_to_f16_bits(v - f16_bits_to_f32(hb));
+                    }
+        }
+        off_ += L::FLOATS;
+    }
     // fused GRU tiles, w(set, c, k) with sets W_ir W_iz W_in W_hr W_hz W_hn: tile (inp, j) = [R|Z: [2][2*NPG][4] | N: [2][NPG][4]]
     template <class L, class W> void gru(W w) {
         for (int c = 0; c < L::NCHUNK; ++c) {
@@ -298,7 +322,8 @@ public:
             tc<typename P::TEncPre>([&](int co, int v, int t) { return v < 8 ? w_enc_pre(co, v, t) : 0.f; }, HS);
             for (int i = 0; i < C::E; ++i)
                 tc<typename P::TConv3>([&](int co, int ci, int t) { return ci < C1 ? cw.enc_w[i][(co * C1 + ci) * 3 + t] : 0.f; }, HS);
-            rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
+            if constexpr (P::LIN_TC) lin<typename P::TLinPre>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
+            else rowk1<typename P::LinPreT>([&](int o, int k) { return cw.rf_pre_lin[o * F1 + k]; });
             tc<typename P::TRfPre>([&](int co, int ci, int) { return ci < C1 ? cw.rf_pre_w[co * C1 + ci] : 0.f; });
             for (int k = 0; k < C::K; ++k) {
                 const auto& b = cw.blk[k];
@@ -314,7 +339,8 @@ public:
                     });
                 tc<typename P::TFc>([&](int co, int ci, int) { return ci < C2 ? b.afc_w[co * C2 + ci] : 0.f; });
             }
-            rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+            if constexpr (P::LIN_TC) lin<typename P::TLinPost>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
+            else rowk1<typename P::LinPostT>([&](int o, int k) { return cw.rf_post_lin[o * F2 + k]; });
             tc<typename P::TRfPost>([&](int co, int ci, int) { return ci < C2 ? cw.rf_post_w[co * C2 + ci] : 0.f; });
             for (int i = 0; i < C::E; ++i) {
                 // cat([x, skip]) with each half padded to C1P channels: k < C1P is x channel k, k >= C1P is skip channel k - C1P

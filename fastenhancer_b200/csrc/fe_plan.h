@@ -131,6 +131,7 @@ struct TcGemm {
     static constexpr int NKS = KP / KE;                // k-steps per tap
     static constexpr int NTILE = TAPS * NKS;
     static constexpr int TILE1 = NP * 8;               // floats per tile part (32 bytes per output row)
+    static constexpr int WLBO = NP * 4;                // floats between the two k-chunks of a weight tile
     static constexpr int TILE = TILE1 * PARTS;
     static_assert(TILE <= CHUNK_, "one weight tile must fit a ring chunk");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
@@ -163,12 +164,34 @@ struct TcGru {
     static constexpr int NP = MERGED ? 4 * NPG : 2 * NPG;              // rows (LBO) of the tile / of its R|Z part
     static constexpr int NTILE = 2 * NKS;              // MERGED: h tiles, then x tiles; split: x tiles, then h tiles
     static constexpr int TILE1 = (MERGED ? 4 : 3) * NPG * 8;
+    static constexpr int WLBO = NP * 4;
     static constexpr int TILE = TILE1 * PARTS;
     static constexpr int COL_NX = MERGED ? 0 : 2 * NPG, COL_R = MERGED ? NPG : 0, COL_Z = MERGED ? 2 * NPG : NPG, COL_NH = 3 * NPG;
     static_assert(TILE <= CHUNK_ && NP <= 256, "GRU tile");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
     static constexpr int NCHUNK = cdiv(NTILE, TPC);
     static constexpr int FLOATS = NTILE * TILE;
+};
+
+// Frequency-axis linear on the tensor cores (16-bit variants): D[row][c] = sum_slot W[row][slot] X[slot][c], a contraction over the SLOTS
+// of an activation buffer [c / 8][slot][8 halves].  That buffer is the B operand, MN-major (its N index, the channel, is the contiguous
+// one: tools/tc_probe_mn.cu validated the descriptor on hardware -- LBO = 128 B between groups of 8 slots, SBO = the slab pitch).  The
+// weights are the A operand, K-major, 128 rows per M tile: row = output slot (frequency-major, streams interleaved), k = input slot,
+// W[(f_out, s)][(f_in, s')] = (s == s') * w[f_out][f_in] (streams share a tile, so the other streams' columns are zero).
+// Ring tiles, one per (M tile, k-step of 16 slots): [2][128][8 halves] (+ the tile of the low parts in the split variants).
+template <int ROWS_, int N_, int K_, int CHUNK_, int PARTS_ = 1>
+struct TcLin {
+    static constexpr int NPOS = ROWS_, N = N_, K = K_, KE = 16, PARTS = PARTS_, TAPS = 1;
+    static_assert(K % 16 == 0 && N % 16 == 0, "slot contraction: whole k-steps, N a multiple of 16");
+    static constexpr int NP = N, NKS = K / 16, NMT = cdiv(ROWS_, 128);
+    static constexpr int NTILE = NMT * NKS;             // M-tile major
+    static constexpr int TILE1 = 128 * 8, TILE = TILE1 * PARTS, WLBO = 128 * 4;
+    static_assert(TILE <= CHUNK_, "one weight tile must fit a ring chunk");
+    static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
+    static constexpr int NCHUNK = cdiv(NTILE, TPC);
+    static constexpr int FLOATS = NTILE * TILE;
+    static constexpr int NG = N / 4, NSPLIT = 1, NPS = N;
+    static_assert(N <= 256, "N");
 };
 
 // Row GEMM reading one k per step (frequency-axis linear on a tensor-core-layout activation, where
@@ -411,6 +434,14 @@ struct Plan {
     using TConvT = TcGemm<S * C::F1, 8, C1P, 3, CHUNK, 256, KEC, NPART>;
     using TRfPost = TcGemm<S * C::F1, C::C1, C2Z, 1, CHUNK, 256, KEC, NPART>;
     using LinPreT = RowGemmK1<C::C1 * S, C::F1, C::F2, NW, CHUNK>;
+#ifndef FE_LIN_TC
+#define FE_LIN_TC 1
+#endif
+    // frequency-axis linears on the tensor cores (16-bit variants; slot counts must be whole k-steps)
+    static constexpr bool LIN_TC = H16 && FE_LIN_TC && (S * C::F2) % 16 == 0 && (S * C::F1) % 16 == 0 && S * C::F2 <= 128;
+    using TLinPre = TcLin<S * C::F2, LIN_TC ? C1P : 16, S * C::F1, CHUNK, NPART>;
+    using TLinPost = TcLin<S * C::F1, LIN_TC ? C2Z : 16, LIN_TC ? S * C::F2 : 16, CHUNK, NPART>;
+    static_assert(!LIN_TC || (TLinPre::NMT * TLinPre::N <= ACCW && TLinPost::NMT * TLinPost::N <= ACCW), "frequency-axis linear accumulators exceed the TMEM window");
     static constexpr int TMEMC = pow2ceil(H_TMEM ? TM_COLS : ACCW);
     static_assert(TMEMC <= 512, "TMEM columns");
     using TRfPre = TcGemm<S * C::F2, C::C2, C1P, 1, CHUNK, 512, KEC, NPART>;
@@ -427,13 +458,14 @@ struct Plan {
     static constexpr int TBLK_CHUNKS = TGru::NCHUNK + 2 * TFc::NCHUNK + NQG * TQkv::NCHUNK;
     static constexpr long TBLK_FLOATS = (long)TGru::FLOATS + 2 * TFc::FLOATS + NQG * TQkv::FLOATS;
     static constexpr int NCHUNK_FRAME = TC
-        ? TEncPre::NCHUNK + C::E * TConv3::NCHUNK + LinPreT::NCHUNK + TRfPre::NCHUNK + C::K * TBLK_CHUNKS + LinPostT::NCHUNK +
+        ? TEncPre::NCHUNK + C::E * TConv3::NCHUNK + (LIN_TC ? TLinPre::NCHUNK : LinPreT::NCHUNK) + TRfPre::NCHUNK + C::K * TBLK_CHUNKS +
+              (LIN_TC ? TLinPost::NCHUNK : LinPostT::NCHUNK) +
               TRfPost::NCHUNK + C::E * (TPwCat::NCHUNK + TConv3::NCHUNK) + TPwCat::NCHUNK + TConvT::NCHUNK
         : EncPre::NCHUNK + C::E * Conv3::NCHUNK + LinPre::NCHUNK + RfPre::NCHUNK + C::K * BLK_CHUNKS + LinPost::NCHUNK +
               RfPost::NCHUNK + C::E * (PwCat::NCHUNK + Conv3::NCHUNK) + PwCat::NCHUNK + ConvT::NCHUNK;
     static constexpr long RING_FLOATS = TC
-        ? (long)TEncPre::FLOATS + (long)C::E * TConv3::FLOATS + LinPreT::FLOATS + TRfPre::FLOATS + (long)C::K * TBLK_FLOATS +
-              LinPostT::FLOATS + TRfPost::FLOATS + (long)C::E * (TPwCat::FLOATS + TConv3::FLOATS) + TPwCat::FLOATS + TConvT::FLOATS
+        ? (long)TEncPre::FLOATS + (long)C::E * TConv3::FLOATS + (LIN_TC ? TLinPre::FLOATS : LinPreT::FLOATS) + TRfPre::FLOATS + (long)C::K * TBLK_FLOATS +
+              (LIN_TC ? TLinPost::FLOATS : LinPostT::FLOATS) + TRfPost::FLOATS + (long)C::E * (TPwCat::FLOATS + TConv3::FLOATS) + TPwCat::FLOATS + TConvT::FLOATS
         : (long)EncPre::FLOATS + (long)C::E * Conv3::FLOATS + LinPre::FLOATS + RfPre::FLOATS + (long)C::K * BLK_FLOATS +
               LinPost::FLOATS + RfPost::FLOATS + (long)C::E * (PwCat::FLOATS + Conv3::FLOATS) + PwCat::FLOATS + ConvT::FLOATS;
 

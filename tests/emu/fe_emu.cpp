@@ -41,17 +41,24 @@ template <class P> struct EmuCtx {
     void warp_sync() const {}
     void sub_begin(int) const {}
     void sub_end(int, int) const {}
-    struct Desc { const float* p; int lbo; };
+    struct Desc { const float* p; int lbo; int sbo = 32; };     // float units; K-major operands have SBO = 128 bytes
     Desc make_desc(const float* p, int lbo_floats) const { return Desc{p, lbo_floats}; }
-    Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo}; }
-    Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats}; }
+    Desc make_desc_mn(const float* p, int sbo_floats) const { return Desc{p, 32, sbo_floats}; }      // LBO = 128 bytes
+    Desc desc_add(Desc d, int floats) const { return Desc{d.p + floats, d.lbo, d.sbo}; }
+    Desc desc_set_lbo(Desc d, int lbo_floats) const { return Desc{d.p, lbo_floats, d.sbo}; }
+    // element (n, k) of an MN-major / no-swizzle 16-bit operand: 8 n per 16-byte row, 8 k rows per 128-byte core matrix, groups of 8 k
+    // LBO apart, groups of 8 n SBO apart (canonical layout; tools/tc_probe_mn.cu checks it on hardware)
+    template <bool BF = false> static float h16mn(const Desc& d, int n, int k) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(d.p + (n / 8) * d.sbo + (k / 8) * d.lbo + (k % 8) * 4);
+        return h16_bits_to_f32<BF>(h[n % 8]);
+    }
     // element (row r, k) of a K-major / no-swizzle fp16 operand: 8 halves per 16-byte row, k-chunks of 8 LBO apart
     template <bool BF = false> static float h16(const float* p, int lbo, int r, int k) {
         const uint16_t* h = reinterpret_cast<const uint16_t*>(p + (k / 8) * lbo + r * 4);
         return h16_bits_to_f32<BF>(h[k % 8]);
     }
     static constexpr int FMT16 = P::BF16 ? 2 : 1;
-    template <bool M64 = false, int FMT = 0>
+    template <bool M64 = false, int FMT = 0, bool BMN = false>
     void mma(int tid, Desc a, Desc b, int NP, int col, bool acc, int rows) {
         constexpr bool F16 = FMT != 0, BF = FMT == 2;
         if (tid != 0) return;                       // one elected lane of warp 0 issues
@@ -61,7 +68,7 @@ template <class P> struct EmuCtx {
             for (int n = 0; n < NP; ++n) {
                 float sum = acc ? tmem[lane * 512 + col + n] : 0.f;
                 if (F16) {
-                    for (int k = 0; k < 16; ++k) sum += h16<BF>(a.p, a.lbo, m, k) * h16<BF>(b.p, b.lbo, n, k);
+                    for (int k = 0; k < 16; ++k) sum += h16<BF>(a.p, a.lbo, m, k) * (BMN ? h16mn<BF>(b, n, k) : h16<BF>(b.p, b.lbo, n, k));
                 } else {
                     for (int k = 0; k < 8; ++k)
                         sum += tf32_trunc(a.p[(k / 4) * a.lbo + m * 4 + (k % 4)]) * tf32_trunc(b.p[(k / 4) * b.lbo + n * 4 + (k % 4)]);

@@ -22,7 +22,7 @@ TOL = {False: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4), Tr
        2: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
        3: dict(wav=1e-4, state=5e-3, tap=2e-2, spec=1e-2, spec_abs=2e-2),
        4: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4)}
-F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_s", 2), ("16k_m", 1), ("48k_t", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
+F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 4), ("16k_s", 2), ("16k_m", 1), ("48k_t", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
 BF16_VARIANTS = [("16k_b", 2), ("16k_m", 1), ("48k_l", 1)]
 SPLIT_VARIANTS = [("16k_t", 2), ("16k_b", 2), ("16k_b", 1), ("48k_b", 1)]
 
