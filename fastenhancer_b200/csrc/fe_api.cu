@@ -85,6 +85,51 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
     if (s == 12345.678f) out[0] = s;          // never true: keeps the chains alive
 }
 
+// ---- checkpoint folding on the device (fe_fold_device): one launch per rule of ONNXModel.remove_weight_reparameterizations
+//      (models/fastenhancer/default/model.py:532-608, 215-258, 74-81); scale factors in double, rounded once, like the host oracle
+//      fastenhancer_b200/fold.py ----
+__device__ double block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    __syncthreads();
+    return t;
+}
+// one block per row (kinds 1, 2); one block for the whole tensor (kind 3); grid-stride copy (kind 0)
+__global__ void __launch_bounds__(128) fold_kernel(fe_fold_op op, float* __restrict__ canon)
+{
+    __shared__ double red[4];
+    float* dst = canon + op.dst;
+    if (op.kind == FE_FOLD_COPY) {
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)op.rows * op.cols; i += (long)gridDim.x * blockDim.x) dst[i] = op.w[i];
+        return;
+    }
+    if (op.kind == FE_FOLD_FINAL_CONV) {          // scale * W / max(||W||_F, 1e-12)  (normalize_final_conv) or scale * W
+        const long n = (long)op.rows * op.cols;
+        double ss = 0.0;
+        for (long i = threadIdx.x; i < n; i += blockDim.x) ss += (double)op.w[i] * (double)op.w[i];
+        ss = block_sum(ss, red);
+        double f = (double)op.a[0];
+        if (op.flag) f /= fmax(sqrt(ss), 1e-12);
+        for (long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (float)((double)op.w[i] * f);
+        return;
+    }
+    const int r = blockIdx.x;
+    const float* wr = op.w + (long)r * op.cols;
+    double f;
+    if (op.kind == FE_FOLD_WEIGHT_NORM) {         // g[r] * v[r][:] / ||v[r]||   (torch _weight_norm, dim = 0)
+        double ss = 0.0;
+        for (int i = threadIdx.x; i < op.cols; i += blockDim.x) ss += (double)wr[i] * (double)wr[i];
+        f = (double)op.a[r] / sqrt(block_sum(ss, red));
+    } else {                                      // eval-mode BatchNorm folded into the preceding bias-free conv / linear
+        f = (double)op.a[r] / sqrt((double)op.d[r] + (double)op.eps);
+        if (threadIdx.x == 0 && op.bias_dst >= 0) canon[op.bias_dst + r] = (float)((double)op.b[r] - (double)op.c[r] * f);
+    }
+    for (int i = threadIdx.x; i < op.cols; i += blockDim.x) dst[(long)r * op.cols + i] = (float)((double)wr[i] * f);
+}
+
 struct Variant {
     fe::VariantOps ops;
     float* blob = nullptr;     // device
@@ -229,6 +274,37 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     }
     *out = e;
     return FE_OK;
+}
+
+// Checkpoint ingestion on the device: `ops` (host array) lists one fold rule per tensor of the canonical array; all sources are device
+// pointers (the reference's pre-fold parameters, e.g. torch tensors of ckpt['model'] moved to the GPU).  Replaces the host-side
+// remove_weight_reparameterizations() call of scripts/export_onnx.py:78.
+FE_API int fe_fold_device(const fe_fold_op* ops, int n_ops, float* canonical_device, void* cuda_stream) {
+    if (!ops || n_ops <= 0 || !canonical_device) return fail(FE_ERR_ARG, "fe_fold_device: bad argument");
+    for (int i = 0; i < n_ops; ++i) {
+        const fe_fold_op& op = ops[i];
+        if (op.kind < FE_FOLD_COPY || op.kind > FE_FOLD_FINAL_CONV || op.rows <= 0 || op.cols <= 0 || !op.w || op.dst < 0)
+            return fail(FE_ERR_ARG, "fe_fold_device: malformed rule " + std::to_string(i));
+        if ((op.kind == FE_FOLD_WEIGHT_NORM || op.kind == FE_FOLD_FINAL_CONV) && !op.a) return fail(FE_ERR_ARG, "fe_fold_device: missing gain / scale");
+        if (op.kind == FE_FOLD_BATCH_NORM && (!op.a || !op.b || !op.c || !op.d)) return fail(FE_ERR_ARG, "fe_fold_device: missing BatchNorm statistics");
+        const int grid = (op.kind == FE_FOLD_COPY) ? (int)std::min<long>(((long)op.rows * op.cols + 127) / 128, 1024) : (op.kind == FE_FOLD_FINAL_CONV ? 1 : op.rows);
+        fold_kernel<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(op, canonical_device);
+        FE_CUDA(cudaGetLastError());
+    }
+    return FE_OK;
+}
+
+// fe_create on a canonical array that already lives on `device` (the output of fe_fold_device).
+FE_API int fe_create_from_device(const fe_config* cfg, const float* canonical_device, size_t n_floats, int device, fe_engine** out) {
+    if (!cfg || !canonical_device || !out) return fail(FE_ERR_ARG, "fe_create_from_device: null argument");
+    if (n_floats != weight_count(*cfg)) return fail(FE_ERR_ARG, "fe_create_from_device: canonical weight array has the wrong length");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FE_ERR_NO_DEVICE, "fe_create_from_device: no CUDA device visible (the engine has no CPU fallback)");
+    FE_CUDA(cudaSetDevice(device));
+    std::vector<float> host(n_floats);        // the packer (fe_pack.h) lays the blob out on the host, once per kernel variant
+    FE_CUDA(cudaMemcpy(host.data(), canonical_device, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return fe_create(cfg, host.data(), n_floats, device, out);
 }
 
 FE_API void fe_destroy(fe_engine* e) {

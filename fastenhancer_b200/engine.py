@@ -24,7 +24,8 @@ ABI_SYMBOLS = (
     "fe_state_destroy", "fe_state_reset", "fe_state_export", "fe_state_import", "fe_stream", "fe_stream_host",
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
-    "fe_state_create_on", "fe_state_planes", "fe_microbench_fma",
+    "fe_state_create_on", "fe_state_planes", "fe_microbench_fma", "fe_fold_device", "fe_create_from_device",
+    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16",
 )
 
 #: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
@@ -64,6 +65,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_state_floats.restype = ctypes.c_size_t
     lib.fe_state_floats.argtypes = [cfgp]
     lib.fe_create.argtypes = [cfgp, fp, ctypes.c_size_t, ip, ctypes.POINTER(vp)]
+    lib.fe_create_from_device.argtypes = [cfgp, fp, ctypes.c_size_t, ip, ctypes.POINTER(vp)]
     lib.fe_destroy.argtypes = [vp]
     lib.fe_destroy.restype = None
     lib.fe_state_create.argtypes = [vp, ip, ctypes.POINTER(vp)]
@@ -90,6 +92,9 @@ def load_library(build_if_missing: bool = True):
     lib.fe_stream_taps.argtypes = [vp, vp, fp, fp, ip, ll, ll, fp, ip, vp]
     lib.fe_profile_slots.argtypes = []
     lib.fe_set_profile.argtypes = [vp, vp]
+    lib.fe_pcm16_to_float.argtypes = [fp, ll, ip, fp, vp]
+    lib.fe_resample_poly.argtypes = [fp, ll, ip, ip, fp, ip, fp, ll, vp]
+    lib.fe_float_to_pcm16.argtypes = [fp, ll, fp, vp]
     lib.fe_microbench_fma.argtypes = [ip, ctypes.POINTER(ctypes.c_double)]
     lib.fe_set_precision.argtypes = [vp, ip]
     lib.fe_get_precision.argtypes = [vp]
@@ -205,18 +210,36 @@ class Engine:
         if dev.type != "cuda":
             raise RuntimeError(f"fastenhancer_b200: device must be a CUDA device, got {dev}")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
-        canonical = np.ascontiguousarray(canonical, dtype=np.float32)
         self._c = CConfig.from_cfg(cfg)
         need = self._lib.fe_weight_count(ctypes.byref(self._c))
-        if canonical.size != need:
-            raise ValueError(f"canonical weights: got {canonical.size} floats, need {need}")
         h = ctypes.c_void_p()
-        _check(self._lib.fe_create(ctypes.byref(self._c), canonical.ctypes.data, canonical.size, self.device.index,
-                                   ctypes.byref(h)), "fe_create")
+        if isinstance(canonical, torch.Tensor) and canonical.is_cuda:      # already on the device (checkpoint.fold_on_device)
+            canonical = canonical.to(device=self.device, dtype=torch.float32).contiguous()
+            if canonical.numel() != need:
+                raise ValueError(f"canonical weights: got {canonical.numel()} floats, need {need}")
+            _check(self._lib.fe_create_from_device(ctypes.byref(self._c), canonical.data_ptr(), canonical.numel(), self.device.index,
+                                                   ctypes.byref(h)), "fe_create_from_device")
+        else:
+            canonical = np.ascontiguousarray(canonical, dtype=np.float32)
+            if canonical.size != need:
+                raise ValueError(f"canonical weights: got {canonical.size} floats, need {need}")
+            _check(self._lib.fe_create(ctypes.byref(self._c), canonical.ctypes.data, canonical.size, self.device.index,
+                                       ctypes.byref(h)), "fe_create")
         self._h = h
         self.state_floats = int(self._lib.fe_state_floats(ctypes.byref(self._c)))
         if precision is not None:
             self.set_precision(precision)
+
+    @classmethod
+    def from_checkpoint(cls, path: str, device: tp.Union[int, str, None] = None, precision: tp.Optional[str] = None) -> "Engine":
+        """``logs/<name>`` (or one of its ``NNNNN.pth`` files) -> engine, with the reference's pre-fold parameters folded on the
+        device (fastenhancer_b200.checkpoint; replaces wrapper.load() + remove_weight_reparameterizations(),
+        /root/reference/wrappers/ns.py:308-321, models/fastenhancer/default/model.py:532-608)."""
+        import torch
+        from .checkpoint import fold_on_device, load_checkpoint
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        cfg, sd = load_checkpoint(path, device=dev)
+        return cls(cfg, fold_on_device(cfg, sd, dev), dev, precision=precision)
 
     def __del__(self):
         if getattr(self, "_h", None):

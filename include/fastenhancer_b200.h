@@ -57,6 +57,26 @@ size_t fe_state_floats(const fe_config* cfg);   /* 2*(n_fft-hop) + n_blocks*f2*c
 int fe_create(const fe_config* cfg, const float* canonical, size_t n_floats, int device, fe_engine** out);
 void fe_destroy(fe_engine* e);
 
+/* Checkpoint ingestion on the device.  Replaces: ModelWrapper.load() + remove_weight_reparameterizations()
+ * (wrappers/ns.py:308-321, model.py:532-608, block part :215-258, final transposed conv :74-81) without the reference classes.
+ * One rule per tensor of the canonical array; every source pointer is DEVICE memory holding a pre-fold parameter of
+ * ckpt['model'] (element order of the canonical tensor = element order of the source weight):
+ *   FE_FOLD_COPY         dst = w                                               (filterbanks, biases, positional embedding)
+ *   FE_FOLD_WEIGHT_NORM  dst[r][:] = a[r] * w[r][:] / ||w[r]||                 (w = original1, a = original0: GRU weights, qkv)
+ *   FE_FOLD_BATCH_NORM   dst[r][:] = w[r][:] * a[r] / sqrt(d[r] + eps);  canonical[bias_dst + r] = b[r] - c[r] * a[r] / sqrt(d[r] + eps)
+ *                        (a = gamma, b = beta, c = running_mean, d = running_var; bias_dst < 0: no bias output)
+ *   FE_FOLD_FINAL_CONV   dst = a[0] * w / max(||w||_F, 1e-12) when flag != 0 (normalize_final_conv), else a[0] * w
+ * Scale factors are computed in double and the product rounded once (fastenhancer_b200/fold.py is the host oracle). */
+enum { FE_FOLD_COPY = 0, FE_FOLD_WEIGHT_NORM = 1, FE_FOLD_BATCH_NORM = 2, FE_FOLD_FINAL_CONV = 3 };
+typedef struct fe_fold_op {
+    int kind, rows, cols, flag;
+    const float *w, *a, *b, *c, *d;
+    long long dst, bias_dst;      /* float offsets into the canonical array */
+    float eps;
+} fe_fold_op;
+int fe_fold_device(const fe_fold_op* ops, int n_ops, float* canonical_device, void* cuda_stream);
+int fe_create_from_device(const fe_config* cfg, const float* canonical_device, size_t n_floats, int device, fe_engine** out);
+
 /* Replaces: ONNXSTFT.initialize_cache + ONNXModel.initialize_cache (audio_modules.py:238-241,
  * model.py:614-618): zeroed cache_stft [n, n_fft-hop], cache_istft [n, n_fft-hop], h_k [n*f2, c2] x K. */
 int fe_state_create(fe_engine* e, int n_streams, fe_state** out);
@@ -138,6 +158,18 @@ int fe_tap_floats(fe_engine* e);
  * (layout of oracle/fe_oracle.c::core) into taps_device [fe_tap_floats]. */
 int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops,
                    long long ld_in, long long ld_out, float* taps_device, int tap_hop, void* cuda_stream);
+
+/* The audio front door of the directory-level runner, on the device.  Replace: librosa.load(path, sr=wrapper.sr, mono=True) and
+ * soundfile.write(path, enhanced, fs) around the model in scripts/test_pytorch.py:29,37 --
+ *   fe_pcm16_to_float   interleaved int16 PCM [n_frames][n_channels] -> mono float32 [n_frames] (mean of the channels / 32768)
+ *   fe_resample_poly    rational-ratio polyphase FIR resampling, out[m] = sum_j in[j] * taps[m*down - j*up + (n_taps-1)/2]
+ *                       (scipy.signal.resample_poly semantics; n_taps odd, taps already scaled by `up`)
+ *   fe_float_to_pcm16   float32 -> int16 PCM, round to nearest, clipped (soundfile's default WAV subtype)
+ * All pointers are device memory. */
+int fe_pcm16_to_float(const short* pcm_device, long long n_frames, int n_channels, float* wav_device, void* cuda_stream);
+int fe_resample_poly(const float* in_device, long long n_in, int up, int down, const float* taps_device, int n_taps,
+                     float* out_device, long long n_out, void* cuda_stream);
+int fe_float_to_pcm16(const float* wav_device, long long n, short* pcm_device, void* cuda_stream);
 
 /* Measured fp32 FMA-pipe throughput of `device` in TFLOP/s (a short FFMA microbenchmark): the roofline denominator of the fp32
  * FMA-pipe kernel family (mode 1) in bench.py. */

@@ -55,3 +55,43 @@ def test_scatter_gather_world2_gloo(n_streams):
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, n_streams, 16, ret), nprocs=world, join=True)
         assert all(ret.get(r) for r in range(world))
+
+
+def _nccl_worker(rank, world, port, n_streams, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import numpy as np
+        from fastenhancer_b200.config import PRESETS
+        from fastenhancer_b200.engine import Engine
+        from fastenhancer_b200.fold import fold_to_canonical
+        from fastenhancer_b200.schema import synthetic_state_dict
+        from fastenhancer_b200.synth import synthetic_noisy
+        cfg = PRESETS["16k_t"]
+        canon = fold_to_canonical(cfg, synthetic_state_dict(cfg, 0))
+        x = torch.from_numpy(synthetic_noisy(n_streams, 12 * cfg.hop_size, cfg.sample_rate))
+        eng = Engine(cfg, canon, dev)
+        # the batch lives on rank 0: NCCL scatter -> every rank enhances its contiguous slice on its own GPU -> NCCL gather
+        local = scatter_streams(x.to(dev) if rank == 0 else None, n_streams, x.size(1), 0, dev)
+        out = gather_streams(eng.stream(eng.new_state(local.size(0)), local), n_streams)
+        if rank == 0:
+            want = eng.stream(eng.new_state(n_streams), x.to(dev))          # the same batch on one GPU
+            assert torch.equal(out, want)                                   # streams never interact: sharding changes no bit
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_streams", [6, 5])
+def test_scatter_enhance_gather_world2_nccl(n_streams):
+    """the N > 1 path on real GPUs (needs 2): NCCL scatter / gather of the audio around per-rank engines == one GPU, bit for bit"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_nccl_worker, args=(world, port, n_streams, ret), nprocs=world, join=True)
+        assert all(ret.get(r) for r in range(world))
