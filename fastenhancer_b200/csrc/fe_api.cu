@@ -3,6 +3,7 @@
 // Host-side responsibilities only: pick the (config, streams-per-CTA) variant, pack the canonical
 // weights into the variant's blob once, own device buffers for weights / state / spill scratch,
 // launch.  There is no CPU compute path: without a CUDA device every entry point fails loudly.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -146,6 +147,7 @@ struct fe_engine {
     int forced_s = 0;
     int tc = 1;                          // kernel family (Plan::PREC): 0 fp32 FMA pipe, 1 TF32, 2 fp16, 3 bf16 conv section, 4 split fp16 (fp32-accurate)
     long long* prof = nullptr;           // optional per-phase cycle counters (device)
+    int hop_tma = 1;                     // hop tiles by TMA where the variant supports it (FE_HOP_TMA=0 in the environment: plain loads / stores)
     std::atomic<long long> launches{0};
     std::mutex mu;
 };
@@ -159,6 +161,7 @@ struct fe_state {
     bool owns_data = true;      // false: the caller's buffer (fe_state_create_on)
     float* scratch = nullptr;   // spill scratch for the largest grid (S = 1)
     size_t scratch_floats = 0;
+    CUtensorMap* tmaps = nullptr;   // device copy of the two hop-tile tensor maps of the launch in flight (fe_stream)
     // pipelined host path (fe_stream_host): staging buffers, streams and events of THIS state, created by fe_state_reserve_host
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     float* h_in[2] = {nullptr, nullptr}; float* h_out[2] = {nullptr, nullptr}; size_t h_floats = 0;
@@ -208,7 +211,30 @@ size_t scratch_need(const fe_engine* e, int n_streams) {
     return need;
 }
 
-int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st) {
+// 2-D tensor map of a [n_streams][ld] float array restricted to its first `width` columns, box [S][tile]: the TMA descriptor of the
+// input / output hop tiles.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+bool hop_tensor_map(CUtensorMap* tm, const float* base, long long ld, long long width, int n_streams, int S, int tile) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn || (reinterpret_cast<size_t>(base) & 15) != 0 || (ld % 4) != 0 || width <= 0) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)n_streams};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)S}, estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st, CUtensorMap* tmaps_device = nullptr) {
     if (prm.n_streams <= 0 || prm.n_hops <= 0) return FE_OK;
     const int vi = pick_variant(e, prm.n_streams);
     int rc = ensure_variant(e, vi);
@@ -219,6 +245,22 @@ int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st) {
     prm.compression = e->cfg.compression;
     prm.prof = e->prof;
     const int grid = (prm.n_streams + v.ops.S - 1) / v.ops.S;
+    // streaming launches of the variants whose rings are hop-tiled: the input hop arrives and the output hop leaves as 2-D TMA tiles
+    // [S streams][hop tile] (cp.async.bulk.tensor); plain loads / stores when the caller's arrays are not 16-byte aligned / pitched
+    // (single-hop launches keep the plain path: nothing to prefetch, and the descriptors would cost an upload per hop)
+    prm.hop_tma = 0;
+    prm.tmaps = nullptr;
+    if (prm.mode == fe::MODE_STREAM && v.ops.hop_ring && e->hop_tma && tmaps_device && prm.n_hops >= 2) {
+        CUtensorMap tm[2];
+        const long long width = (long long)prm.n_hops * e->cfg.hop;
+        if (hop_tensor_map(&tm[0], prm.in, prm.ld_in, width, prm.n_streams, v.ops.S, v.ops.hop_tile) &&
+            hop_tensor_map(&tm[1], prm.out, prm.ld_out, width, prm.n_streams, v.ops.S, v.ops.hop_tile)) {
+            // pageable source: staged before the call returns; stream order puts it ahead of this launch and behind the previous one
+            FE_CUDA(cudaMemcpyAsync(tmaps_device, tm, sizeof(tm), cudaMemcpyHostToDevice, st));
+            prm.hop_tma = 1;
+            prm.tmaps = tmaps_device;
+        }
+    }
     FE_CUDA(v.ops.launch(prm, grid, st));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     return FE_OK;
@@ -262,6 +304,7 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     e->canonical.assign(canonical, canonical + n_floats);
     e->variants = std::move(vs);
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
+    if (const char* env = std::getenv("FE_HOP_TMA")) e->hop_tma = std::atoi(env);
     // Default arithmetic = results identical to the fp32 reference: the fp32-accurate tensor-core family where the model has one
     // (split-fp16 operands, three MMAs per product), else the fp32 FMA pipe.  The faster reduced-precision families are opt-in.
     e->tc = 0;
@@ -329,6 +372,7 @@ static int state_create(fe_engine* e, int n_streams, float* external, fe_state**
     }
     s->scratch_floats = scratch_need(e, n_streams);
     if (ce == cudaSuccess) ce = cudaMalloc(&s->scratch, s->scratch_floats * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->tmaps, 2 * sizeof(CUtensorMap));
     if (ce != cudaSuccess) { fe_state_destroy(s); return cuda_fail(ce, "fe_state_create"); }
     *out = s;
     return FE_OK;
@@ -346,6 +390,7 @@ FE_API void fe_state_destroy(fe_state* s) {
     cudaSetDevice(s->e->device);
     if (s->data && s->owns_data) cudaFree(s->data);
     if (s->scratch) cudaFree(s->scratch);
+    if (s->tmaps) cudaFree(s->tmaps);
     for (int i = 0; i < 2; ++i) {
         if (s->h_in[i]) cudaFree(s->h_in[i]);
         if (s->h_out[i]) cudaFree(s->h_out[i]);
@@ -393,7 +438,7 @@ FE_API int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float*
     prm.state = s->data; prm.in = wav_in; prm.out = wav_out; prm.ld_in = ld_in; prm.ld_out = ld_out;
     prm.n_streams = s->n_streams; prm.n_hops = n_hops; prm.mode = fe::MODE_STREAM;
     prm.dbg = taps_device; prm.dbg_hop = tap_hop;
-    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream);
+    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream, s->tmaps);
 }
 
 FE_API int fe_stream(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops, long long ld_in,

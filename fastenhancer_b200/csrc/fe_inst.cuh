@@ -1,6 +1,7 @@
 // fe_inst.cuh -- device entry point of the fused kernel and the per-variant host glue.
 // Included by the per-configuration translation units fe_inst_*.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "fe_kernel.cuh"
@@ -41,6 +42,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// ---- 2-D TMA tiles (cp.async.bulk.tensor; SASS: UTMALDG / UTMASTG) ----
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int x, int y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(src) : "memory");
+}
 // ---- tcgen05 (UMMA) primitives; encodings validated on hardware by tools/tc_probe.cu ----
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor: element (row r, k) at
 //   start + (r % 8) * 16 + (r / 8) * SBO + (k / 4) * LBO + (k % 4) * 4   bytes (tf32: 4 elements per 16 B)
@@ -79,6 +89,48 @@ template <int NT> __device__ __forceinline__ void bar_consumers() { asm volatile
 template <class P> struct GpuCtx {
     float* sm; const float* blob; KParams prm; int s0; float* gs; int cta;
     int tid; unsigned seq_base; uint32_t bars;     // bars: full[STAGES] then empty[STAGES], 8 bytes each
+    // ---- hop tiles by TMA (HOP_RING variants, prm.hop_tma): hop_full mbarrier behind the accumulator barrier ----
+    // the thread that issues the hop tiles: first lane of the LAST consumer warp (warp 0 issues the MMAs and is the critical one)
+    static constexpr int HOP_TID = P::NT - 32;
+    static __device__ __forceinline__ uint32_t hop_full_bar(uint32_t bars_) { return bars_ + 8u * (2 * P::STAGES) + 16u; }
+    // the input tile of hop `hop` has landed in the input ring
+    __device__ __forceinline__ void hop_wait(int hop) const { mbar_wait(hop_full_bar(bars), (unsigned)hop & 1u); }
+    // (after the barrier that ends a window phase / the one-time init) the ring tile that hop `hop` overwrites has been read by every
+    // thread: consumer thread 0 issues its 2-D TMA tiles right away, a whole frame before they are needed -- nothing ever waits for a
+    // free tile, so no thread has to poll for one.  Generic-proxy reads before an async-proxy write: proxy fence first.
+    __device__ __forceinline__ void hop_prefetch(int hop) const {
+        if (tid == HOP_TID && hop < prm.n_hops) {
+            constexpr int H = P::Cf::HOP, HT = P::HT, N = P::Cf::N_FFT;
+            fence_async_smem();
+            mbar_expect_tx(hop_full_bar(bars), (uint32_t)(P::S * H * 4));
+#pragma unroll
+            for (int k = 0; k < H / HT; ++k) {
+                const int pos = (hop * H + k * HT) & (N - 1);
+                tma_load_2d(smem_u32(sm + P::SM_TIN + (pos / HT) * P::S * HT), static_cast<const CUtensorMap*>(prm.tmaps), hop * H + k * HT, s0,
+                            hop_full_bar(bars));
+            }
+        }
+    }
+    // (after the barrier that ends an overlap-add phase) the output hop leaves from the overlap-add ring, one 2-D tile [S][HT] per ring tile
+    __device__ __forceinline__ void hop_store(int hop) const {
+        if (tid == HOP_TID) {
+            fence_async_smem();
+#pragma unroll
+            for (int k = 0; k < P::Cf::HOP / P::HT; ++k) {
+                const int pos = (hop * P::Cf::HOP + k * P::HT) & (P::Cf::N_FFT - 1);
+                tma_store_2d(static_cast<const CUtensorMap*>(prm.tmaps) + 1, hop * P::Cf::HOP + k * P::HT, s0,
+                             smem_u32(sm + P::SM_OLA + (pos / P::HT) * P::S * P::HT));
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    // the stores of the previous hop have read their tiles (before the ring is written again) / have completed (end of the launch)
+    __device__ __forceinline__ void hop_store_wait(bool all) const {
+        if (tid == HOP_TID) {
+            if (all) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
     __device__ __forceinline__ const float* acquire(int ci, int) const {
         const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES, par = (seq / P::STAGES) & 1u;
         mbar_wait(bars + 8u * stage, par);
@@ -274,6 +326,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
             mbar_init(bars + 8u * (P::STAGES + i), P::NW);      // empty: one arrival per consumer warp
         }
         if constexpr (P::TC) mbar_init(bars + 8u * (2 * P::STAGES), 1);   // accumulator-ready barrier
+        mbar_init(GpuCtx<P>::hop_full_bar(bars), 1);                     // hop tile landed (expect_tx arrival of the issuing thread + bytes)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P::SM_BAR + 4 * P::STAGES + 2);
@@ -335,6 +388,7 @@ template <class P> struct VariantImpl {
         v.shape = ShapeKey{C::N_FFT, C::HOP, C::C1, C::E, C::C2, C::F2, C::K, C::NH};
         v.smem_bytes = P::SMEM_BYTES; v.nthreads = P::NTHREADS; v.gs_floats = P::GS_TOTAL; v.state_floats = C::STATE;
         v.tap_floats = Frame<P>::TAP_TOTAL; v.nchunk_frame = P::NCHUNK_FRAME; v.blob_floats = P::make_aux().total;
+        v.hop_ring = P::HOP_RING; v.hop_tile = P::HT;
         v.pack = &pack; v.prepare = &prepare; v.launch = &launch;
         return v;
     }

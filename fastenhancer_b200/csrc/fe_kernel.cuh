@@ -818,8 +818,8 @@ template <class P> struct Frame {
                     if (gs < prm.n_streams) {
                         a = prm.state[st_cache(prm, 0, gs) + i]; b = prm.state[st_cache(prm, 1, gs) + i];
                     }
-                    sm[P::SM_TIN + s * N + ((H + i) & NMASK)] = a;
-                    sm[P::SM_OLA + s * N + i] = b;
+                    sm[P::SM_TIN + P::ring_off(s, (H + i) & NMASK)] = a;
+                    sm[P::SM_OLA + P::ring_off(s, i)] = b;
                 }
             });
         }
@@ -880,10 +880,13 @@ template <class P> struct Frame {
                 }
             });
         }
+        const bool hop_tma = P::HOP_RING && prm.hop_tma;          // streaming launches: hop tiles move by TMA
+        if (hop_tma) x.hop_prefetch(0);                           // the rings are initialised: the tile of hop 0 may land
         for (int hop = 0; hop < prm.n_hops; ++hop) {
             frame(x, hop);
             x.next_frame();
         }
+        if (hop_tma) x.hop_store_wait(true);
         if (P::H_TMEM && has_model) {
             x.phase(PH_STATE, [&](int tid) {
                 constexpr int NGX = C2 / 4, GH = (NGX + 1) / 2;
@@ -918,8 +921,8 @@ template <class P> struct Frame {
                     int s = idx / C::CL, i = idx % C::CL;
                     int gs = x.s0 + s;
                     if (gs < prm.n_streams) {
-                        if (prm.mode != MODE_ISTFT) prm.state[st_cache(prm, 0, gs) + i] = sm[P::SM_TIN + s * N + ((n * H + H + i) & NMASK)];
-                        if (prm.mode != MODE_STFT) prm.state[st_cache(prm, 1, gs) + i] = sm[P::SM_OLA + s * N + ((n * H + i) & NMASK)];
+                        if (prm.mode != MODE_ISTFT) prm.state[st_cache(prm, 0, gs) + i] = sm[P::SM_TIN + P::ring_off(s, (n * H + H + i) & NMASK)];
+                        if (prm.mode != MODE_STFT) prm.state[st_cache(prm, 1, gs) + i] = sm[P::SM_OLA + P::ring_off(s, (n * H + i) & NMASK)];
                     }
                 }
             });
@@ -1500,6 +1503,35 @@ template <class P> struct Frame {
         return ci;
     }
 
+    // ---- hop-tiled rings without TMA (arrays that are not 16-byte aligned / pitched, the standalone STFT / iSTFT modes): the same
+    //      tiles moved with plain loads / stores by the threads t of nt; each is followed by a barrier before the ring is used ----
+    template <class X> FE_DEV static void fill_hop(X& x, int hop, int t, int nt) {
+        const KParams& prm = x.prm;
+        float* TIN = x.sm + P::SM_TIN;
+        const int wpos = (hop * H) & NMASK;
+        for (int idx = t; idx < S * H; idx += nt) {
+            const int s = idx / H, j = idx % H, gs = x.s0 + s;
+            TIN[P::ring_off(s, (wpos + j) & NMASK)] = gs < prm.n_streams ? prm.in[(size_t)gs * prm.ld_in + (size_t)hop * H + j] : 0.f;
+        }
+    }
+    template <class X> FE_DEV static void drain_hop(X& x, int hop, int t, int nt) {
+        const KParams& prm = x.prm;
+        const float* OLA = x.sm + P::SM_OLA;
+        const int base = (hop * H) & NMASK;
+        for (int idx = t; idx < S * H; idx += nt) {
+            const int s = idx / H, i = idx % H, gs = x.s0 + s;
+            if (gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = OLA[P::ring_off(s, (base + i) & NMASK)];
+        }
+    }
+    // the output hop leaves the overlap-add ring (after the barrier that ends the overlap-add phase)
+    template <class X> FE_DEV static void emit_hop(X& x, int hop) {
+        if constexpr (P::HOP_RING) {
+            if (x.prm.mode == MODE_OFFLINE) return;
+            if (x.prm.hop_tma) x.hop_store(hop);
+            else x.phase(PH_OLA, [&](int tid) { drain_hop(x, hop, tid, NT); });
+        }
+    }
+
     // ---- irFFT (packed real), synthesis window, overlap-add, emit one hop.  The decompressed spectrum (bins 0..M-1)
     //      is in W0; the Nyquist bin is zero in the fused path and SPEC[s] (real part) for the standalone inverse ----
     template <class X> FE_DEV static void back_end(X& x, int hop, bool have_z) {
@@ -1526,6 +1558,7 @@ template <class P> struct Frame {
         });
         const float* Y = have_z ? fft(x, W0, W1, true) : fft(x, W1, W0, true);
         x.phase(PH_OLA, [&](int tid) { ola_items(x, Y, hop, tid, NT); });
+        emit_hop(x, hop);
     }
     // synthesis window, overlap-add, emit one hop: items of threads t of nt.  Y = output of the inverse FFT.
     template <class X> FE_DEV static void ola_items(X& x, const float* Y, int hop, int t, int nt) {
@@ -1540,12 +1573,15 @@ template <class P> struct Frame {
             const float invM = 1.0f / (float)M;
             for (int idx = t; idx < S * N; idx += nt) {
                 const int s = idx / N, i = idx % N, gs = x.s0 + s;
-                const int slot = s * N + ((base + i) & NMASK);
+                const int slot = P::ring_off(s, (base + i) & NMASK);
                 float y = Y[s * N + i] * invM;
                 if (mode != MODE_OFFLINE) {
                     float v = y * ldg(aux + A.window_istft + i) + (i < C::CL ? OLA[slot] : 0.f);
                     OLA[slot] = v;
-                    if (i < H && gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = v;
+                    // (hop-tiled rings: the hop leaves from the ring once the phase is complete, as TMA tiles or through drain_hop)
+                    if constexpr (!P::HOP_RING) {
+                        if (i < H && gs < prm.n_streams) prm.out[(size_t)gs * prm.ld_out + (size_t)hop * H + i] = v;
+                    }
                 } else {          // torch.istft(center=True): window, overlap-add, / sum of window^2, trim N/2
                     float v = y * ldg(aux + A.window + i) + (i < C::CL ? OLA[slot] : 0.f);
                     OLA[slot] = v;
@@ -1591,12 +1627,17 @@ template <class P> struct Frame {
                 for (int idx = t; idx < S * M; idx += nt) {
                     int s = idx / M, n2 = 2 * (idx % M), gs = x.s0 + s;
                     float a, b;
-                    if (mode != MODE_OFFLINE) {
+                    if (P::HOP_RING && mode != MODE_OFFLINE) {
+                        // hop-tiled rings: the new hop is already in the ring (a 2-D TMA tile [S][HT] per ring tile, or fill_hop), so the
+                        // frame [N-H cached samples | new hop] is N consecutive ring positions from wpos + H
+                        a = TIN[P::ring_off(s, (wpos + H + n2) & NMASK)];
+                        b = TIN[P::ring_off(s, (wpos + H + n2 + 1) & NMASK)];
+                    } else if (mode != MODE_OFFLINE) {
                         // frame = [N-H cached samples | the new hop]: the new samples come straight from global memory
                         // and are filed into the ring on the way (slots disjoint from the cached part)
                         if (n2 < C::CL) {
-                            a = TIN[s * N + ((wpos + H + n2) & NMASK)];
-                            b = TIN[s * N + ((wpos + H + n2 + 1) & NMASK)];
+                            a = TIN[P::ring_off(s, (wpos + H + n2) & NMASK)];
+                            b = TIN[P::ring_off(s, (wpos + H + n2 + 1) & NMASK)];
                         } else {
                             const int j = n2 - C::CL;
                             a = b = 0.f;
@@ -1604,8 +1645,8 @@ template <class P> struct Frame {
                                 const float* src_hop = prm.in + (size_t)gs * prm.ld_in + (size_t)hop_ * H + j;
                                 a = src_hop[0]; b = src_hop[1];
                             }
-                            TIN[s * N + ((wpos + j) & NMASK)] = a;
-                            TIN[s * N + ((wpos + j + 1) & NMASK)] = b;
+                            TIN[P::ring_off(s, (wpos + j) & NMASK)] = a;
+                            TIN[P::ring_off(s, (wpos + j + 1) & NMASK)] = b;
                         }
                     } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
                         a = b = 0.f;
@@ -1655,7 +1696,12 @@ template <class P> struct Frame {
             back_end(x, hop, false);
             return;
         } else if (mode != MODE_SPEC && !(ovl && hop > 0)) {
-            x.phase(PH_WINDOW, [&](int tid) { window_items(hop, W0, tid, NT); });
+            if (P::HOP_RING && mode != MODE_OFFLINE && !prm.hop_tma) x.phase(PH_LOAD, [&](int tid) { fill_hop(x, hop, tid, NT); });
+            x.phase(PH_WINDOW, [&](int tid) {
+                if (P::HOP_RING && prm.hop_tma) x.hop_wait(hop);
+                window_items(hop, W0, tid, NT);
+            });
+            if (P::HOP_RING && prm.hop_tma) x.hop_prefetch(hop + 1);
             float* Z = fft(x, W0, W1, false);
             if (mode == MODE_STFT) {      // ONNXSTFT.forward: all n_fft/2 + 1 bins, no compression
                 x.phase(PH_COMPRESS, [&](int tid) {
@@ -2123,6 +2169,8 @@ template <class P> struct Frame {
         if constexpr (P::TC) {
             TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};     // the mask is not a conv input: no halo
             x.phase(PH_CONVT, [&](int tid) {
+                // overlapped schedule without TMA: the next hop's tile is filled here, a barrier ahead of the phase that windows it
+                if (P::HOP_RING && ovl && !prm.hop_tma && hop + 1 < prm.n_hops) fill_hop(x, hop + 1, tid, NT);
                 const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                 tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ACT1);
             });
@@ -2196,9 +2244,14 @@ template <class P> struct Frame {
             float* F0 = sm + P::SM_FF;
             float* F1 = F0 + S * N;
             x.phase(PH_MASK, [&](int tid) {
+                if (P::HOP_RING && prm.hop_tma) x.hop_store_wait(false);      // the previous hop's tile has left the overlap-add ring
                 if (tid < NH) mask_items(tid, NH);
-                else if (next) window_items(hop + 1, F0, tid - NH, NH);
+                else if (next) {
+                    if (P::HOP_RING && prm.hop_tma) x.hop_wait(hop + 1);
+                    window_items(hop + 1, F0, tid - NH, NH);
+                }
             });
+            if (P::HOP_RING && prm.hop_tma && next) x.hop_prefetch(hop + 2);
             float *bs = W0, *bd = W1, *fs = F0, *fd = F1;
             for (int si = 0; si < NSTAGE; ++si) {
                 x.phase(PH_IFFT, [&](int tid) {
@@ -2212,9 +2265,13 @@ template <class P> struct Frame {
                 if (tid < NH) ola_items(x, bs, hop, tid, NH);
                 else if (next) compress_items(fs, tid - NH, NH);
             });
+            emit_hop(x, hop);
             return;
         }
-        x.phase(PH_MASK, [&](int tid) { mask_items(tid, NT); });
+        x.phase(PH_MASK, [&](int tid) {
+            if (P::HOP_RING && prm.hop_tma) x.hop_store_wait(false);
+            mask_items(tid, NT);
+        });
         back_end(x, hop, true);
     }
 };

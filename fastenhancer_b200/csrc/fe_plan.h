@@ -335,7 +335,7 @@ struct Plan {
     // TC variants: [QKV | Y1T | Zb from 0 ... | ATT (= h scratch when h is not resident) | XT | XR at the tail].
     // XT is a TF32-rounded copy of x for the MMAs; when it does not fit (48 kHz L) the MMAs read the fp32 master
     // (the tensor core then truncates instead of rounding).
-    static constexpr int SM_REST = SPECF + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 4;
+    static constexpr int SM_REST = SPECF + 32 + 2 * S * C::N_FFT + T::STAGES * T::CHUNK + 4 * T::STAGES + 8;   // (+32: TMA alignment of the rings)
     static constexpr int XRT = (C::C2 / 4) * RSLABF;   // fp32 master of x when a separate rounded copy exists: no K-padding group
     static constexpr int RF_NEED1 = cmax(QKVS + XTS, Y1TS) + XTS;
     static constexpr int RF_NEED2 = RF_NEED1 + XRT;
@@ -388,11 +388,26 @@ struct Plan {
     // TC variants keep the GRU state of all K blocks on chip across hops: in TMEM, else in shared memory when it fits
     static constexpr bool H_RES = TC && (H_TMEM || SM_FIXED + SKIP_SMEM * ACT + C::K * XTS <= 227 * 256);
     static constexpr int SM_SK = 0;
+    // position `pos` (0 .. N-1) of stream s in an input / overlap-add ring
+    FE_HD static constexpr int ring_off(int s, int pos) {
+        return HOP_RING ? ((pos / HT) * S + s) * HT + pos % HT : s * C::N_FFT + pos;
+    }
     static constexpr int SM_HST = SM_SK + SKIP_SMEM * ACT;          // [K][XTS] resident GRU state (GeoR) unless it lives in TMEM
     static constexpr int SM_W = SM_HST + ((H_RES && !H_TMEM) ? C::K * XTS : 0);
     static constexpr int SM_SPEC = SM_W + AB;
-    static constexpr int SM_TIN = SM_SPEC + SPECF;             // last N input samples per stream (circular)
-    static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;       // overlap-add accumulator per stream (circular)
+    // Input / overlap-add rings: the last N input samples and the N-sample overlap-add accumulator of every stream, circular.
+    // HOP_RING (hop divides n_fft: T / B / S): the rings are tiled [N / HT][S][HT] so that one hop of all S streams is a dense [S][HT]
+    // box (HT = hop, or 256 when the hop is longer: TMA boxes hold at most 256 elements per dimension) -- the 2-D TMA tile
+    // (cp.async.bulk.tensor) of the input hop lands straight in the input ring and the output hop leaves straight from the
+    // overlap-add ring.  Otherwise (M / L: hop does not divide n_fft) the rings are [S][N] and the hop moves with plain loads / stores.
+#ifndef FE_HOP_RING
+#define FE_HOP_RING 1
+#endif
+    static constexpr bool HOP_RING = TC && FE_HOP_RING && C::N_FFT % C::HOP == 0;
+    static constexpr int HT = C::HOP > 256 ? 256 : C::HOP;
+    static_assert(!HOP_RING || (C::HOP % HT == 0 && (HT * 4) % 16 == 0), "hop tile");
+    static constexpr int SM_TIN = round_up(SM_SPEC + SPECF, 32);      // 128-byte aligned (TMA destination)
+    static constexpr int SM_OLA = SM_TIN + S * C::N_FFT;
     // Streaming launches overlap the back end of hop t (mask, inverse FFT, overlap-add: half of the threads) with the front end of
     // hop t + 1 (window, FFT, compression: the other half) when two more FFT buffers fit: half as many barrier-separated phases.
 #ifndef FE_FB_OVL
@@ -400,10 +415,10 @@ struct Plan {
 #endif
     static constexpr int SM_FF = SM_OLA + S * C::N_FFT;        // [2][S][N] front-end FFT buffers of the overlapped schedule
     static constexpr bool FB_OVL = TC && FE_FB_OVL &&
-        (SM_FF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES + 4) * 4 <= 227 * 1024;
+        (SM_FF + 2 * S * C::N_FFT + STAGES * CHUNK + 4 * STAGES + 8) * 4 <= 227 * 1024;
     static constexpr int SM_RING = SM_FF + (FB_OVL ? 2 * S * C::N_FFT : 0);
     static constexpr int SM_BAR = SM_RING + STAGES * CHUNK;    // 2*STAGES mbarriers (8 bytes each)
-    static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES + 4;   // + accumulator-ready mbarrier, TMEM base slot
+    static constexpr int SM_TOTAL = SM_BAR + 4 * STAGES + 8;   // + accumulator-ready mbarrier, TMEM base slot, hop-tile full / empty mbarriers
     static_assert(SM_RING % 4 == 0 && SM_BAR % 2 == 0, "alignment");
     static constexpr int SMEM_BYTES = SM_TOTAL * 4;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
@@ -537,6 +552,8 @@ struct KParams {
     long long ld_in, ld_out;
     int n_streams, n_hops;    // n_hops = T frames in modes 1, 2
     int mode, L, dbg_hop;
+    int hop_tma;              // streaming launches of HOP_RING variants: the input hop arrives / the output hop leaves as 2-D TMA tiles
+    const void* tmaps;        // ... described by two CUtensorMap (input, output) in global memory (device; 64-byte aligned)
     float compression;
 };
 

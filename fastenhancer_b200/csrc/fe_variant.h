@@ -1,5 +1,6 @@
 // fe_variant.h -- type-erased handle on one instantiated (config, streams-per-CTA) kernel variant.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -13,6 +14,7 @@ struct VariantOps {
     ShapeKey shape;
     int smem_bytes, nthreads, gs_floats, state_floats, tap_floats, nchunk_frame;
     long blob_floats;
+    int hop_ring, hop_tile;                                        // hop tiles by 2-D TMA (cp.async.bulk.tensor): supported, tile width
     void (*pack)(const float* canonical, std::vector<float>& blob);
     cudaError_t (*prepare)();                                      // one-time function attributes
     cudaError_t (*launch)(const KParams& prm, int grid, cudaStream_t stream);

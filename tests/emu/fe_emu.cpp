@@ -7,6 +7,7 @@
 #define FE_EMU 1
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -26,6 +27,35 @@ template <class P> struct EmuCtx {
         return blob + table[2 * ci];
     }
     void release(int) const {}
+    // ---- hop tiles by TMA (HOP_RING variants): consumer thread 0 issues the tile of hop t right after the window phase of frame t - 1
+    //      (when its ring tile has been read): emulated at that point, zero-filled rows for streams past the end like the hardware's
+    //      out-of-bounds fill ----
+    int hops_loaded = 0;
+    void hop_prefetch(int hop) {
+        if (hop != hops_loaded) throw std::runtime_error("emu: hop tiles prefetched out of order");
+        ++hops_loaded;
+        if (hop >= prm.n_hops) return;
+        constexpr int H = P::Cf::HOP, HT = P::HT, N = P::Cf::N_FFT;
+        for (int k = 0; k < H / HT; ++k) {
+            const int pos = (hop * H + k * HT) & (N - 1);
+            float* dst = sm + P::SM_TIN + (pos / HT) * P::S * HT;
+            for (int s = 0; s < P::S; ++s)
+                for (int i = 0; i < HT; ++i)
+                    dst[s * HT + i] = (s0 + s < prm.n_streams) ? prm.in[(size_t)(s0 + s) * prm.ld_in + (size_t)hop * H + k * HT + i] : 0.f;
+        }
+    }
+    void hop_wait(int hop) const { if (hop >= hops_loaded) throw std::runtime_error("emu: hop tile awaited before it was prefetched"); }
+    void hop_store(int hop) {
+        constexpr int H = P::Cf::HOP, HT = P::HT, N = P::Cf::N_FFT;
+        for (int k = 0; k < H / HT; ++k) {
+            const int pos = (hop * H + k * HT) & (N - 1);
+            const float* src = sm + P::SM_OLA + (pos / HT) * P::S * HT;
+            for (int s = 0; s < P::S; ++s)
+                if (s0 + s < prm.n_streams)
+                    for (int i = 0; i < HT; ++i) prm.out[(size_t)(s0 + s) * prm.ld_out + (size_t)hop * H + k * HT + i] = src[s * HT + i];
+        }
+    }
+    void hop_store_wait(bool) const {}
     template <class F> void phase(int, F&& f) { for (int t = 0; t < P::NT; ++t) f(t); }
     template <class A, class F1, class F2> void phase2(int, F1&& f1, F2&& f2) {
         std::vector<A> acc(P::NT);
@@ -131,6 +161,7 @@ template <class P> int run_variant(const float* canonical, KParams prm) {
         for (auto& v : sm) v = std::nanf("");
         EmuCtx<P> x;
         x.sm = sm.data(); x.blob = blob.data(); x.prm = prm; x.prm.blob = blob.data();
+        x.prm.hop_tma = (P::HOP_RING && prm.mode == MODE_STREAM && !std::getenv("FE_EMU_NO_HOP_TMA")) ? 1 : 0;
         x.s0 = cta * P::S; x.gs = gs.data(); x.cta = cta;
         x.table = reinterpret_cast<const int*>(blob.data() + A.table);
         Frame<P>::run(x);

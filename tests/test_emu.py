@@ -135,3 +135,23 @@ def test_nonzero_attention_bias(name, S, tc, canonical):
     emu.run(cfg, S, canon, emu.MODE_STREAM, stn, x, got, n_streams=B, n_hops=nh, ld_in=nh * H, ld_out=nh * H, tc=tc)
     assert np.sqrt(np.mean((got - want) ** 2)) < TOL[tc]["wav"]
     assert np.abs(emu.to_canonical(cfg, stn) - st).max() < TOL[tc]["state"]
+
+
+@pytest.mark.parametrize("name,S,tc", [("16k_b", 2, 2), ("16k_t", 2, 4), ("48k_t", 2, True)])
+def test_hop_tiles_without_tma(name, S, tc, canonical, monkeypatch):
+    """hop-tiled rings filled / drained with plain loads and stores (the path taken for arrays that are not 16-byte aligned / pitched)
+    give the same bits as the emulated TMA tiles"""
+    cfg = PRESETS[name]
+    canon = canonical(name)
+    B, nh, H = 3, 4, cfg.hop_size
+    x = synthetic_noisy(B, nh * H, cfg.sample_rate)
+    outs = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("FE_EMU_NO_HOP_TMA", "1")
+        stn = emu.to_native(cfg, np.zeros((B, cfg.state_floats), np.float32))
+        y = np.zeros_like(x)
+        emu.run(cfg, S, canon, emu.MODE_STREAM, stn, x, y, n_streams=B, n_hops=nh, ld_in=nh * H, ld_out=nh * H, tc=tc)
+        outs.append((y, stn))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.abs(outs[0][0]).max() > 0.01

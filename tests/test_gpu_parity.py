@@ -357,3 +357,19 @@ def test_two_states_stream_host_concurrently(engines):
     for t in th:
         t.join()
     assert torch.equal(outs[0], want[0]) and torch.equal(outs[1], want[1])
+
+
+@pytest.mark.parametrize("name", ["16k_t", "16k_b", "48k_b"])
+def test_hop_tiles_by_tma_equal_plain_loads(name, engines):
+    """Streaming launches of the hop-tiled variants move the input / output hop as 2-D TMA tiles (cp.async.bulk.tensor, box
+    [S streams][hop tile]) when the caller's arrays are 16-byte aligned and pitched; otherwise they use plain loads / stores.
+    Same bits either way, ragged last CTA included (out-of-bounds rows of the box are zero-filled / clipped by the TMA unit)."""
+    cfg, eng = PRESETS[name], engines(name)
+    H, B, nh = cfg.hop_size, 5, 7
+    x = torch.from_numpy(synthetic_noisy(B, nh * H, cfg.sample_rate)).cuda()
+    y_tma = eng.stream(eng.new_state(B), x)
+    pad = torch.zeros(B, nh * H + 1, device="cuda")
+    pad[:, 1:] = x                                            # rows start 4 bytes off a 16-byte boundary, pitch not a multiple of 4 floats
+    out = torch.empty(B, nh * H + 1, device="cuda")
+    y_plain = eng.stream(eng.new_state(B), pad[:, 1:], out=out[:, 1:])
+    assert torch.equal(y_tma, y_plain)
