@@ -638,6 +638,122 @@ FE_DEV void tc_lin_mmas(X& x, int tid, int ci, typename X::Desc b0, int blo) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Attention over the F2 frequency tokens of one (stream, head) on warp-level tensor-core MMAs (mma.sync.m16n8k8, TF32 operands, fp32
+// accumulate): the scores, the softmax and P V of 16 query rows live in the registers of one warp.
+//   task = (stream, head, 16-row query tile); Q K^T: A = Q tile (rows = queries, k = head dim), B = K (k = head dim, n = keys);
+//   softmax in the log2 domain on the accumulator fragments (row max / sum across the 4 lanes of a quad);
+//   P V: the accumulator layout of a score tile (thread (g, t): row g, columns 2t, 2t + 1) IS the A-operand layout of the next MMA if its
+//   k index is read as  k = t -> key 2t,  k = t + 4 -> key 2t + 1  -- a permutation of the summation index, applied to V's rows as well,
+//   so no shuffle is needed between the two products.
+// X3 (fp32-accurate variants): every operand is split  v = hi + lo  (cvt.rna.tf32) and every product is hi*hi + lo*hi + hi*lo.
+// Q / K / V are read from the position-major QKV rows [slot][head][q | k | v][HDP]; out(i, d, value) stores one output element.
+// (GPU only: the CPU emulation keeps the scalar form, which is also what the fp32 FMA-pipe variants run.)
+// ---------------------------------------------------------------------------------------------
+#ifndef FE_EMU
+#ifndef FE_ATTN_MMA
+#define FE_ATTN_MMA 1
+#endif
+FE_DEV void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+FE_DEV uint32_t tf32_bits(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+template <bool X3, int NA, int NB2>
+FE_DEV void mma_tf32_acc(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+    uint32_t ah[4], bh[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ah[i] = X3 ? tf32_bits(a[i]) : __float_as_uint(a[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) bh[i] = X3 ? tf32_bits(b[i]) : __float_as_uint(b[i]);
+    if constexpr (X3) {
+        uint32_t al[4], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) al[i] = tf32_bits(a[i] - __uint_as_float(ah[i]));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bl[i] = tf32_bits(b[i] - __uint_as_float(bh[i]));
+        mma_tf32_16x8x8(c, al, bh);
+        mma_tf32_16x8x8(c, ah, bl);
+    }
+    mma_tf32_16x8x8(c, ah, bh);
+}
+// F2 tokens, HD real / HDP padded head dim, row pitch (floats) between consecutive tokens of the same stream; qb = row of token 0:
+// [q (HDP) | k (HDP) | v (HDP)] of this head.  m0 = first query row of the tile.  scale = log2(e) / sqrt(HD).
+template <int F2, int HD, int HDP, bool X3, class Out>
+FE_DEV void attention_tile_mma(const float* qb, int pitch, int m0, float scale, int lane, Out out) {
+    constexpr int NJ = (F2 + 7) / 8, KS = (HDP + 7) / 8, ND = (HD + 7) / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = m0 + g, r1 = m0 + g + 8;
+    const float* q0 = qb + (r0 < F2 ? r0 : 0) * pitch;
+    const float* q1 = qb + (r1 < F2 ? r1 : 0) * pitch;
+    // ---- scores: S[i][j] = sum_d q[i][d] k[j][d], all key tiles of this query tile ----
+    float sc[NJ][4];
+#pragma unroll
+    for (int nj = 0; nj < NJ; ++nj) sc[nj][0] = sc[nj][1] = sc[nj][2] = sc[nj][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int d0 = 8 * ks + t, d1 = 8 * ks + t + 4;
+        float a[4];
+        a[0] = d0 < HDP ? q0[d0] * scale : 0.f; a[1] = d0 < HDP ? q1[d0] * scale : 0.f;
+        a[2] = d1 < HDP ? q0[d1] * scale : 0.f; a[3] = d1 < HDP ? q1[d1] * scale : 0.f;
+#pragma unroll
+        for (int nj = 0; nj < NJ; ++nj) {
+            const int j = 8 * nj + g;
+            const float* kr = qb + (j < F2 ? j : 0) * pitch + HDP;
+            float b[2];
+            b[0] = d0 < HDP ? kr[d0] : 0.f; b[1] = d1 < HDP ? kr[d1] : 0.f;
+            mma_tf32_acc<X3, 4, 2>(sc[nj], a, b);
+        }
+    }
+    // ---- softmax over the keys (thread (g, t) holds rows r0 / r1, keys 8 nj + 2t, + 1) ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nj = 0; nj < NJ; ++nj) {
+        if (F2 % 8 != 0 && nj == NJ - 1) {           // keys past the last token of a ragged tile
+            if (8 * nj + 2 * t >= F2) sc[nj][0] = sc[nj][2] = -INFINITY;
+            if (8 * nj + 2 * t + 1 >= F2) sc[nj][1] = sc[nj][3] = -INFINITY;
+        }
+        mx0 = fmaxf(mx0, fmaxf(sc[nj][0], sc[nj][1])); mx1 = fmaxf(mx1, fmaxf(sc[nj][2], sc[nj][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float den0 = 0.f, den1 = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < NJ; ++nj) {
+        sc[nj][0] = fe_exp2(sc[nj][0] - mx0); sc[nj][1] = fe_exp2(sc[nj][1] - mx0);
+        sc[nj][2] = fe_exp2(sc[nj][2] - mx1); sc[nj][3] = fe_exp2(sc[nj][3] - mx1);
+        den0 += sc[nj][0] + sc[nj][1]; den1 += sc[nj][2] + sc[nj][3];
+    }
+    den0 += __shfl_xor_sync(0xffffffffu, den0, 1); den0 += __shfl_xor_sync(0xffffffffu, den0, 2);
+    den1 += __shfl_xor_sync(0xffffffffu, den1, 1); den1 += __shfl_xor_sync(0xffffffffu, den1, 2);
+    // ---- O = P V with the permuted key index: A = (P[r0][2t], P[r1][2t], P[r0][2t+1], P[r1][2t+1]), B = (V[8nj+2t][d], V[8nj+2t+1][d]) ----
+    float o[ND][4];
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < NJ; ++nj) {
+        const float a[4] = {sc[nj][0], sc[nj][2], sc[nj][1], sc[nj][3]};
+        const int j0 = 8 * nj + 2 * t, j1 = j0 + 1;
+        const float* v0 = qb + (j0 < F2 ? j0 : 0) * pitch + 2 * HDP;
+        const float* v1 = qb + (j1 < F2 ? j1 : 0) * pitch + 2 * HDP;
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+            const int d = 8 * nd + g;
+            float b[2];
+            b[0] = d < HDP ? v0[d] : 0.f; b[1] = d < HDP ? v1[d] : 0.f;       // (P is exactly zero for keys past the end)
+            mma_tf32_acc<X3, 4, 2>(o[nd], a, b);
+        }
+    }
+    const float i0 = 1.0f / den0, i1 = 1.0f / den1;
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+        const int d = 8 * nd + 2 * t;
+        if (r0 < F2) { if (d < HD) out(r0, d, o[nd][0] * i0); if (d + 1 < HD) out(r0, d + 1, o[nd][1] * i0); }
+        if (r1 < F2) { if (d < HD) out(r1, d, o[nd][2] * i1); if (d + 1 < HD) out(r1, d + 1, o[nd][3] * i1); }
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // The frame.
 // ---------------------------------------------------------------------------------------------
 template <class P> struct Frame {
@@ -1364,7 +1480,34 @@ template <class P> struct Frame {
                                 ATT[rf_off(C2 + idx / P::RSLOTS, (idx % P::RSLOTS) % S, (idx % P::RSLOTS) / S)] = 0.f;
                         }
                     }
-                    for (int it = tid; it < S * P::HG * F2; it += NT) {
+                    // one output element (channel c of token i of stream s) as the attn_fc operand of this variant
+                    auto put_att = [&](int c, int s, int i, float ov) {
+                        if constexpr (P::SPLIT) {       // hi part, and the remainder in the XT region (unused: x lives in tensor memory)
+                            const int o = att_off16(c, s, i);
+                            sth(ATT, o, ov);
+                            sth(ATT + XTS, o, ov - rnd_h(ov));
+                        } else if constexpr (P::RF16) sth(ATT, att_off16(c, s, i), ov);
+                        else ATT[rf_off(c, s, i)] = tf32_pre(ov);
+                    };
+#if !defined(FE_EMU) && FE_ATTN_MMA
+                    // warp-level tensor-core form (reduced-precision families): tasks (stream, head, 16-row query tile) dealt round-robin
+                    // to the consumer warps.  The fp32-accurate split family keeps the fp32 FMA form below: with three MMAs and the
+                    // operand splits per product the warp-level form measured slower there (12.7 k vs 10.3 k cycles per hop, B).
+                    constexpr bool ATT_MMA = !P::SPLIT;
+#else
+                    constexpr bool ATT_MMA = false;
+#endif
+#if !defined(FE_EMU)
+                    if constexpr (ATT_MMA) {
+                        constexpr int NMI = (F2 + 15) / 16, NTASK = S * P::HG * NMI;
+                        for (int task = tid >> 5; task < NTASK; task += NT / 32) {
+                            const int mi = task % NMI, hh = (task / NMI) % P::HG, s = task / (NMI * P::HG);
+                            attention_tile_mma<F2, HD, HDP, false>(QKV + s * P::QROW + hh * 3 * HDP, S * P::QROW, 16 * mi, scale, tid & 31,
+                                [&](int i, int d, float ov) { put_att((hg * P::HG + hh) * HD + d, s, i, ov); });
+                        }
+                    }
+#endif
+                    for (int it = tid; !ATT_MMA && it < S * P::HG * F2; it += NT) {
                         const int i = it % F2, hh = (it / F2) % P::HG, s = it / (F2 * P::HG);
                         const float* qb = QKV + s * P::QROW + hh * 3 * HDP;        // row of position (f = 0, s); next f: S * QROW further
                         f2 q[2 * H4], o[2 * H4];             // packed fp32 pairs (FFMA2)
@@ -1426,12 +1569,7 @@ template <class P> struct Frame {
 #pragma unroll
                         for (int d = 0; d < HD; ++d) {
                             const float ov = ((d & 1) ? o[d >> 1].y : o[d >> 1].x) * inv;
-                            if constexpr (P::SPLIT) {       // hi part, and the remainder in the XT region (unused: x lives in tensor memory)
-                                const int o = att_off16((hg * P::HG + hh) * HD + d, s, i);
-                                sth(ATT, o, ov);
-                                sth(ATT + XTS, o, ov - rnd_h(ov));
-                            } else if constexpr (P::RF16) sth(ATT, att_off16((hg * P::HG + hh) * HD + d, s, i), ov);
-                            else ATT[rf_off((hg * P::HG + hh) * HD + d, s, i)] = tf32_pre(ov);
+                            put_att((hg * P::HG + hh) * HD + d, s, i, ov);
                         }
                     }
                 });
