@@ -371,23 +371,30 @@ def reference_shaped_calls(args, cfg, dev, x_host, n_hops, precision):
             "value": B * nh / dt, "unit": "frames/s", "us_per_hop": dt / nh * 1e6, "rtf": dt / (nh * H / cfg.sample_rate), "hops": nh,
             "h2d_bytes_per_hop": B * H * 4, "d2h_bytes_per_hop": B * H * 4, "kernel_launches_per_hop": 1,
             "api": "StreamingModel.forward(wav_in, cache_stft, cache_istft, *h) with the returned caches fed back (zero-copy views)"}
-    # offline Model.forward on the whole batch of utterances
+    # offline Model.forward on one utterance (BASELINE config 1's own call) and on the whole batch of utterances
     m = Model(**kw).eval().to(dev)
     m.precision = precision
     L = int(args.seconds * cfg.sample_rate)
-    wav_h = x_host[:, :L].contiguous().pin_memory()
-    out_h = torch.empty(wav_h.size(0), H * (L // H)).pin_memory()
-    for it in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        wav, _spec = m(wav_h.to(dev, non_blocking=True))
-        out_h.copy_(wav, non_blocking=True)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    frames = wav_h.size(0) * (1 + L // H)
-    out["model_forward_offline"] = {"value": frames / dt, "unit": "frames/s", "ms": dt * 1e3, "rtf": dt / args.seconds,
-                                    "h2d_bytes": wav_h.numel() * 4, "d2h_bytes": out_h.numel() * 4,
-                                    "api": "Model.forward(noisy [B, L]) -> wav (spec_hat stays on the device, as in scripts/test_pytorch.py:34-37)"}
+    for B in sorted({1, args.streams}):
+        wav_h = x_host[:B, :L].contiguous().pin_memory()
+        out_h = torch.empty(B, H * (L // H)).pin_memory()
+        for it in range(4):
+            torch.cuda.synchronize()
+            n0 = m.engine.kernel_launches if it else 0
+            t0 = time.perf_counter()
+            wav, _spec = m(wav_h.to(dev, non_blocking=True))
+            out_h.copy_(wav, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        launches = m.engine.kernel_launches - n0
+        frames = B * (1 + L // H)
+        out[f"model_forward_offline_batch{B}"] = {
+            "value": frames / dt, "unit": "frames/s", "ms": dt * 1e3, "rtf": dt / (B * args.seconds), "h2d_bytes": wav_h.numel() * 4,
+            "d2h_bytes": out_h.numel() * 4, "fused_kernel_launches": launches,
+            "schedule": "sequential walk (one CTA per group of utterances)" if launches == 1 else
+                        "frame-parallel (stage A, GRU scan + stage B per block, overlap-add)",
+            "api": "Model.forward(noisy [B, L]) -> wav (spec_hat stays on the device, as in scripts/test_pytorch.py:34-37)"}
+    out["model_forward_offline"] = out[f"model_forward_offline_batch{args.streams}"]
     return out
 
 

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -131,6 +132,95 @@ __global__ void __launch_bounds__(128) fold_kernel(fe_fold_op op, float* __restr
     for (int i = threadIdx.x; i < op.cols; i += blockDim.x) dst[(long)r * op.cols + i] = (float)((double)wr[i] * f);
 }
 
+// ---- frame-parallel offline schedule: the two small kernels between the staged launches of the fused kernel ----
+// The GRU recurrence of one RNNFormer block (models/fastenhancer/default/model.py:266-272: nn.GRU over time with the sub-bands as batch),
+// the only sequential part of Model.forward: one CTA per (utterance, sub-band) row walks t = 0 .. T-1.  Thread (j, q) keeps the
+// hidden-to-hidden weights of output channel j for the q-th part of the input channels in registers (3 gates x CQ weights), partial
+// sums meet through a shuffle butterfly over the Q lanes, h goes through a double-buffered shared-memory vector (one barrier per
+// step), the input-side pre-activations gx (computed frame-parallel by the previous stage) are prefetched four steps ahead.
+//   gx [B*T][F2][3][C2] (W_ir x | W_iz x | W_in x, no bias), w_hh [3][C2][C2], b_ih / b_hh [3][C2]  ->  hseq [B*T][F2][C2]
+template <int C2, int Q> __global__ void __launch_bounds__(((C2 * Q + 31) / 32) * 32)
+fe_gru_scan_kernel(const float* __restrict__ gx, float* __restrict__ hseq, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                   const float* __restrict__ b_hh, int T, int F2)
+{
+    constexpr int CQ = (C2 + Q - 1) / Q, NTH = ((C2 * Q + 31) / 32) * 32, HP = CQ * Q + 4;
+    constexpr int NSTG = 8, GROW = 3 * C2;          // gx ring: the pre-activations of the next NSTG steps (cp.async, 16-byte pieces)
+    static_assert((Q & (Q - 1)) == 0 && Q <= 32 && (CQ % 2 == 0 || Q == 1), "input parts: a power of two of lanes, 8-byte aligned slices of h");
+    static_assert(GROW % 4 == 0, "a step's pre-activations are whole 16-byte pieces");
+    __shared__ __align__(16) float hbuf[2][HP];
+    __shared__ __align__(16) float gbuf[NSTG][GROW];
+    const int tid = threadIdx.x, j = tid / Q, q = tid % Q, c0 = q * CQ;
+    const bool live = j < C2;
+    const int u = blockIdx.x / F2, f = blockIdx.x % F2;
+    const float* g0 = gx + (((size_t)u * T) * F2 + f) * GROW;              // + t * F2 * GROW
+    const size_t gstep = (size_t)F2 * GROW, hstep = (size_t)F2 * C2;
+    auto issue = [&](int t) {          // every thread commits one (possibly empty) group per call: the wait below counts groups
+        if (t < T)
+            for (int i = tid; i < GROW / 4; i += NTH)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&gbuf[t % NSTG][4 * i])),
+                             "l"(g0 + (size_t)t * gstep + 4 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int t = 0; t < NSTG; ++t) issue(t);
+    float wr[CQ], wz[CQ], wn[CQ];
+#pragma unroll
+    for (int i = 0; i < CQ; ++i) {
+        const bool ok = live && c0 + i < C2;
+        wr[i] = ok ? w_hh[(0 * C2 + j) * C2 + c0 + i] : 0.f;
+        wz[i] = ok ? w_hh[(1 * C2 + j) * C2 + c0 + i] : 0.f;
+        wn[i] = ok ? w_hh[(2 * C2 + j) * C2 + c0 + i] : 0.f;
+    }
+    const int jj = live ? j : 0;
+    const float br = b_ih[jj] + b_hh[jj], bz = b_ih[C2 + jj] + b_hh[C2 + jj], bin = b_ih[2 * C2 + jj], bhn = b_hh[2 * C2 + jj];
+    for (int i = tid; i < 2 * HP; i += NTH) (&hbuf[0][0])[i] = 0.f;
+    asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 1) : "memory");      // step 0 has landed
+    if (NTH > 32) __syncthreads(); else __syncwarp();
+    float* h0 = hseq + (((size_t)u * T) * F2 + f) * C2 + jj;
+    float hj = 0.f;                // h[j] of this thread's channel (lanes q == 0)
+    for (int t = 0; t < T; ++t) {
+        if (t > 0) issue(t - 1 + NSTG);         // the slot of step t - 1 is free: every thread passed the barrier that ended it
+        const float* hb = hbuf[t & 1];
+        float ar0 = 0.f, az0 = 0.f, an0 = 0.f, ar1 = 0.f, az1 = 0.f, an1 = 0.f;
+#pragma unroll
+        for (int i = 0; i + 1 < CQ; i += 2) {
+            const float2 hv = *reinterpret_cast<const float2*>(hb + c0 + i);
+            ar0 = fmaf(wr[i], hv.x, ar0); az0 = fmaf(wz[i], hv.x, az0); an0 = fmaf(wn[i], hv.x, an0);
+            ar1 = fmaf(wr[i + 1], hv.y, ar1); az1 = fmaf(wz[i + 1], hv.y, az1); an1 = fmaf(wn[i + 1], hv.y, an1);
+        }
+        if (CQ & 1) { const float hv = hb[c0 + CQ - 1]; ar0 = fmaf(wr[CQ - 1], hv, ar0); az0 = fmaf(wz[CQ - 1], hv, az0); an0 = fmaf(wn[CQ - 1], hv, an0); }
+        float ar = ar0 + ar1, az = az0 + az1, an = an0 + an1;
+#pragma unroll
+        for (int o = 1; o < Q; o <<= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o); az += __shfl_xor_sync(0xffffffffu, az, o); an += __shfl_xor_sync(0xffffffffu, an, o);
+        }
+        if (q == 0) {
+            const float* gb = gbuf[t % NSTG];
+            const float r = fe::sigmoid_acc(gb[jj] + br + ar), z = fe::sigmoid_acc(gb[C2 + jj] + bz + az);
+            const float n = fe::tanh_acc(gb[2 * C2 + jj] + bin + r * (an + bhn));
+            hj = (1.0f - z) * n + z * hj;
+            if (live) { hbuf[(t + 1) & 1][j] = hj; h0[(size_t)t * hstep] = hj; }
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");  // step t + 1 has landed (this thread's pieces; the barrier publishes all)
+        if (NTH > 32) __syncthreads(); else __syncwarp();
+    }
+}
+
+// out[u][n] = sum_t y_t[n + N/2 - t H] / sum_t w^2[n + N/2 - t H], n < H (T - 1): torch.istft(center=True) over the windowed frames
+// y [B*T][N] (functional/audio_modules.py:108-121); frames summed in ascending t like the sequential walk.
+__global__ void fe_overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ wsq, float* __restrict__ out, int B, int T, int N, int H)
+{
+    const long len = (long)H * (T - 1), total = (long)B * len;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long u = i / len, n = i % len, npad = n + N / 2;
+        long t0 = npad < N ? 0 : (npad - N + H) / H, t1 = npad / H;
+        if (t1 > T - 1) t1 = T - 1;
+        float v = 0.f, env = 0.f;
+        for (long t = t0; t <= t1; ++t) { v += frames[((size_t)u * T + t) * N + (npad - t * H)]; env += __ldg(wsq + (npad - t * H)); }
+        out[i] = v / env;
+    }
+}
+
 struct Variant {
     fe::VariantOps ops;
     float* blob = nullptr;     // device
@@ -150,6 +240,9 @@ struct fe_engine {
     int hop_tma = 1;                     // hop tiles by TMA where the variant supports it (FE_HOP_TMA=0 in the environment: plain loads / stores)
     std::atomic<long long> launches{0};
     std::mutex mu;
+    cudaMemPool_t pool = nullptr;        // stream-ordered scratch of fe_offline: an engine-owned pool that keeps its memory between calls
+    int offline_mode = 0;                // fe_offline: 0 = automatic, 1 = sequential walk (one CTA per stream group), 2 = frame-parallel schedule
+    float* canon_dev = nullptr;          // canonical weights on the device (hidden-to-hidden GRU weights of the scan), uploaded on first use
 };
 
 // Everything a call mutates lives in the state (or on the call's stream), never in the engine: two states of one engine can be
@@ -266,6 +359,114 @@ int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st, CUten
     return FE_OK;
 }
 
+cudaError_t pool_alloc(fe_engine* e, float** p, size_t floats, cudaStream_t st) {
+    return e->pool ? cudaMallocFromPoolAsync((void**)p, floats * sizeof(float), e->pool, st) : cudaMallocAsync((void**)p, floats * sizeof(float), st);
+}
+
+// ---- Model.forward on few long utterances: the frame-parallel schedule ----
+// float offsets of block k's GRU tensors in the canonical array (fe_pack.h::Canon)
+struct GruOff { size_t w_hh, b_ih, b_hh; };
+GruOff gru_offsets(const fe_config& c, int k) {
+    const size_t C1 = c.c1, C2 = c.c2, F1 = c.n_fft / 8, F2 = c.f2;
+    size_t o = C1 * 16 + C1 + (size_t)c.n_enc * (C1 * C1 * 3 + C1) + F2 * F1 + C2 * C1 + C2;
+    for (int b = 0; b < k; ++b)
+        o += 2 * 3 * C2 * C2 + 2 * 3 * C2 + C2 * C2 + C2 + (b == 0 ? F2 * C2 : 0) + 3 * C2 * C2 + 3 * C2 + C2 * C2 + C2;
+    return GruOff{o + 3 * C2 * C2, o + 6 * C2 * C2, o + 6 * C2 * C2 + 3 * C2};
+}
+template <int C2, int Q> void scan_launch(const float* gx, float* h, const float* canon, const GruOff& g, int rows, int T, int F2, cudaStream_t st) {
+    fe_gru_scan_kernel<C2, Q><<<rows, ((C2 * Q + 31) / 32) * 32, 0, st>>>(gx, h, canon + g.w_hh, canon + g.b_ih, canon + g.b_hh, T, F2);
+}
+int gru_scan(const fe_config& c, int k, const float* gx, float* h, const float* canon, int B, int T, cudaStream_t st) {
+    const GruOff g = gru_offsets(c, k);
+    const int rows = B * c.f2;
+    switch (c.c2) {
+        case 20: scan_launch<20, 1>(gx, h, canon, g, rows, T, c.f2, st); break;
+        case 36: scan_launch<36, 2>(gx, h, canon, g, rows, T, c.f2, st); break;
+        case 48: scan_launch<48, 2>(gx, h, canon, g, rows, T, c.f2, st); break;
+        case 72: scan_launch<72, 4>(gx, h, canon, g, rows, T, c.f2, st); break;
+        case 96: scan_launch<96, 4>(gx, h, canon, g, rows, T, c.f2, st); break;
+        default: return fail(FE_ERR_UNSUPPORTED, "fe_offline: no GRU scan kernel for this rf_channels");
+    }
+    FE_CUDA(cudaGetLastError());
+    return FE_OK;
+}
+
+// the fp32-family variant the frame-parallel schedule runs on: the largest S that still gives every SM a frame group, else the smallest
+int pick_tp_variant(const fe_engine* e, long n_frames) {
+    int first = -1;
+    if (e->forced_s > 0)
+        for (size_t i = 0; i < e->variants.size(); ++i)
+            if (e->variants[i].ops.tc == 0 && e->variants[i].ops.S == e->forced_s) return (int)i;
+    for (int i = (int)e->variants.size() - 1; i >= 0; --i) {
+        if (e->variants[i].ops.tc != 0) continue;
+        first = i;
+        if ((n_frames + e->variants[i].ops.S - 1) / e->variants[i].ops.S >= e->num_sms) return i;
+    }
+    return first;
+}
+
+int offline_tp(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, cudaStream_t st) {
+    const fe_config& c = e->cfg;
+    const int T = 1 + L / c.hop;
+    const long nf = (long)B * T;
+    const int vi = pick_tp_variant(e, nf);
+    if (vi < 0) return fail(FE_ERR_UNSUPPORTED, "fe_offline: this model has no fp32-family kernel variant for the frame-parallel schedule");
+    if (int rc = ensure_variant(e, vi)) return rc;
+    const Variant& v = e->variants[vi];
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (!e->canon_dev) {
+            FE_CUDA(cudaMalloc(&e->canon_dev, e->canonical.size() * sizeof(float)));
+            FE_CUDA(cudaMemcpy(e->canon_dev, e->canonical.data(), e->canonical.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    const int ngroups = (int)((nf + v.ops.S - 1) / v.ops.S), grid = std::min(ngroups, e->num_sms);
+    const size_t n_scr = (size_t)ngroups * v.ops.tp_group, n_gx = (size_t)nf * c.f2 * 3 * c.c2, n_h = (size_t)nf * c.f2 * c.c2, n_fr = (size_t)nf * c.n_fft;
+    float* buf = nullptr;
+    FE_CUDA(pool_alloc(e, &buf, n_scr + n_gx + n_h + n_fr, st));
+    fe::KParams prm{};
+    prm.blob = v.blob; prm.in = wav; prm.out = wav_out; prm.spec_out = spec_out; prm.compression = c.compression; prm.prof = e->prof;
+    prm.n_streams = B; prm.n_hops = T; prm.L = L; prm.mode = fe::MODE_OFFLINE; prm.dbg_hop = -1;
+    prm.tp_scr = buf; prm.tp_gx = buf + n_scr; prm.tp_h = buf + n_scr + n_gx; prm.tp_frames = buf + n_scr + n_gx + n_h;
+    int rc = FE_OK;
+    cudaError_t ce = cudaSuccess;
+    // FE_TP_TIMING=1 (debugging aid): CUDA-event time of every launch of the schedule on stderr
+    static const bool timing = std::getenv("FE_TP_TIMING") && std::atoi(std::getenv("FE_TP_TIMING")) != 0;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (timing) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); evs.push_back(ev); } };
+    auto stage = [&](int stg, int blk) {
+        if (rc != FE_OK || ce != cudaSuccess) return;
+        prm.tp_stage = stg; prm.tp_blk = blk;
+        ce = v.ops.launch(prm, grid, st);
+        e->launches.fetch_add(1, std::memory_order_relaxed);
+        mark();
+    };
+    mark();
+    stage(1, 0);
+    for (int k = 0; k < c.n_blocks; ++k) {
+        if (rc == FE_OK && ce == cudaSuccess) rc = gru_scan(c, k, prm.tp_gx, buf + n_scr + n_gx, e->canon_dev, B, T, st);
+        mark();
+        stage(2, k);
+    }
+    if (rc == FE_OK && ce == cudaSuccess) {
+        const long total = (long)B * c.hop * (T - 1);
+        fe_overlap_add_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(prm.tp_frames, v.blob + v.ops.aux_window_sq, wav_out, B, T,
+                                                                                                c.n_fft, c.hop);
+        ce = cudaGetLastError();
+    }
+    cudaFreeAsync(buf, st);
+    if (timing && !evs.empty()) {
+        mark();
+        cudaEventSynchronize(evs.back());
+        std::string line = "fe_offline frame-parallel, ms per launch [stage A | scan, stage B per block | overlap-add]:";
+        for (size_t i = 1; i < evs.size(); ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, evs[i - 1], evs[i]); line += " " + std::to_string(ms); }
+        std::fprintf(stderr, "%s\n", line.c_str());
+        for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    }
+    if (rc == FE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "fe_offline (frame-parallel schedule)");
+    return rc;
+}
+
 }  // namespace
 
 #define FE_API __attribute__((visibility("default")))
@@ -303,8 +504,20 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount;
     e->canonical.assign(canonical, canonical + n_floats);
     e->variants = std::move(vs);
+    {
+        // (the default pool hands its memory back to the driver at every synchronisation: a repeated Model.forward would pay the
+        // allocation of its scratch again and again)
+        cudaMemPoolProps pp{};
+        pp.allocType = cudaMemAllocationTypePinned; pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice; pp.location.id = device;
+        if (cudaMemPoolCreate(&e->pool, &pp) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else { e->pool = nullptr; cudaGetLastError(); }
+    }
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
     if (const char* env = std::getenv("FE_HOP_TMA")) e->hop_tma = std::atoi(env);
+    if (const char* env = std::getenv("FE_OFFLINE_MODE")) e->offline_mode = std::max(0, std::min(2, std::atoi(env)));
     // Default arithmetic = results identical to the fp32 reference: the fp32-accurate tensor-core family where the model has one
     // (split-fp16 operands, three MMAs per product), else the fp32 FMA pipe.  The faster reduced-precision families are opt-in.
     e->tc = 0;
@@ -354,6 +567,8 @@ FE_API void fe_destroy(fe_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (Variant& v : e->variants) if (v.blob) cudaFree(v.blob);
+    if (e->canon_dev) cudaFree(e->canon_dev);
+    if (e->pool) cudaMemPoolDestroy(e->pool);
     delete e;
 }
 
@@ -480,11 +695,27 @@ FE_API int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_o
     if (L <= e->cfg.n_fft / 2) return fail(FE_ERR_ARG, "fe_offline: input shorter than n_fft/2 + 1 samples (reflect padding needs more)");
     FE_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // Few long utterances leave the one-CTA-per-stream-group walk with most SMs idle: outside the GRU recurrence the frames of an utterance
+    // are independent, so the fp32-accurate families switch to the frame-parallel schedule (same kernels, same weights, frames instead of
+    // streams in the CTA slots; the recurrence runs as a scan between the launches).  Automatic when the walk would fill less than half
+    // of the SMs and the scratch (about 100 KB per frame) stays below 2 GB.
+    {
+        const long T = 1 + L / e->cfg.hop, nf = (long)B * T;
+        const int vi = pick_tp_variant(e, nf);
+        bool tp = false;
+        if (vi >= 0 && T >= 2 && (e->tc == 0 || e->tc == 4)) {
+            const int S_walk = e->variants[pick_variant(e, B)].ops.S;
+            const double scr_bytes = (double)((nf + e->variants[vi].ops.S - 1) / e->variants[vi].ops.S) * e->variants[vi].ops.tp_group * 4.0;
+            tp = e->offline_mode == 2 || (e->offline_mode == 0 && (B + S_walk - 1) / S_walk * 2 <= e->num_sms && scr_bytes < 2e9);
+        }
+        if (e->offline_mode == 2 && !tp) return fail(FE_ERR_UNSUPPORTED, "fe_offline: the frame-parallel schedule needs an fp32-accurate precision mode");
+        if (tp) return offline_tp(e, wav, B, L, wav_out, spec_out, st);
+    }
     // zero state + spill scratch of THIS call, allocated and freed in stream order: concurrent calls on other streams share nothing
     const size_t sf = fe_state_floats(&e->cfg), need = (size_t)B * sf, sneed = scratch_need(e, B);
     float *off_state = nullptr, *off_scratch = nullptr;
-    FE_CUDA(cudaMallocAsync(&off_state, need * sizeof(float), st));
-    cudaError_t ce = cudaMallocAsync(&off_scratch, sneed * sizeof(float), st);
+    FE_CUDA(pool_alloc(e, &off_state, need, st));
+    cudaError_t ce = pool_alloc(e, &off_scratch, sneed, st);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(off_state, 0, need * sizeof(float), st);
     int rc = FE_OK;
     if (ce != cudaSuccess) rc = cuda_fail(ce, "fe_offline: scratch allocation");
@@ -606,6 +837,11 @@ FE_API int fe_set_precision(fe_engine* e, int mode) {
     for (const Variant& v : e->variants) ok = ok || (v.ops.tc == tc && (e->forced_s == 0 || v.ops.S == e->forced_s));
     if (!ok) return fail(FE_ERR_UNSUPPORTED, "fe_set_precision: this model has no kernel variant for the requested mode");
     e->tc = tc;
+    return FE_OK;
+}
+FE_API int fe_set_offline_mode(fe_engine* e, int mode) {
+    if (!e || mode < 0 || mode > 2) return fail(FE_ERR_ARG, "fe_set_offline_mode: mode must be 0 (automatic), 1 (sequential walk) or 2 (frame-parallel)");
+    e->offline_mode = mode;
     return FE_OK;
 }
 FE_API int fe_get_precision(fe_engine* e) {

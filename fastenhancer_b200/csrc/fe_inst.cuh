@@ -87,8 +87,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int NT> __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 template <class P> struct GpuCtx {
-    float* sm; const float* blob; KParams prm; int s0; float* gs; int cta;
+    float* sm; const float* blob; KParams prm; int s0; float* gs; int cta, ncta;
     int tid; unsigned seq_base; uint32_t bars;     // bars: full[STAGES] then empty[STAGES], 8 bytes each
+    int ci0, nci;           // weight chunks of one iteration: [ci0, ci0 + nci) (the whole frame, or one stage of the frame-parallel schedule)
     // ---- hop tiles by TMA (HOP_RING variants, prm.hop_tma): hop_full mbarrier behind the accumulator barrier ----
     // the thread that issues the hop tiles: first lane of the LAST consumer warp (warp 0 issues the MMAs and is the critical one)
     static constexpr int HOP_TID = P::NT - 32;
@@ -132,12 +133,12 @@ template <class P> struct GpuCtx {
         }
     }
     __device__ __forceinline__ const float* acquire(int ci, int) const {
-        const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES, par = (seq / P::STAGES) & 1u;
+        const unsigned seq = seq_base + (unsigned)(P::TC ? ci : ci - ci0), stage = seq % P::STAGES, par = (seq / P::STAGES) & 1u;
         mbar_wait(bars + 8u * stage, par);
         return sm + P::SM_RING + stage * P::CHUNK;
     }
     __device__ __forceinline__ void release(int ci) const {
-        const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES;
+        const unsigned seq = seq_base + (unsigned)(P::TC ? ci : ci - ci0), stage = seq % P::STAGES;
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(bars + 8u * (P::STAGES + stage));
     }
@@ -221,7 +222,7 @@ template <class P> struct GpuCtx {
     // ring stage release in a tensor-core layer: thread 0's arrival is a tcgen05.commit (fires when its MMAs, which read
     // the stage, are done); the other warps never touch the stage and arrive at once
     __device__ __forceinline__ void release_mma(int ci) const {
-        const unsigned seq = seq_base + (unsigned)ci, stage = seq % P::STAGES;
+        const unsigned seq = seq_base + (unsigned)(P::TC ? ci : ci - ci0), stage = seq % P::STAGES;
         __syncwarp();
         if (tid < 32) {
             if (elect_one()) umma_commit(bars + 8u * (P::STAGES + stage));      // the lane that issued this warp's MMAs
@@ -311,7 +312,7 @@ template <class P> struct GpuCtx {
         phase_sync();
         stamp(id);
     }
-    __device__ __forceinline__ void next_frame() { seq_base += P::NCHUNK_FRAME; }
+    __device__ __forceinline__ void next_frame() { seq_base += (unsigned)(P::TC ? P::NCHUNK_FRAME : nci); }       // (staged schedule: fp32 family only)
     __device__ __forceinline__ void check_frame(int) const {}
 };
 
@@ -346,8 +347,15 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
             const int* table = reinterpret_cast<const int*>(prm.blob + A.table);
             const uint32_t ring = smem_u32(sm + P::SM_RING);
             unsigned seq = 0;
-            for (int hop = 0; hop < prm.n_hops; ++hop) {
-                for (int ci = 0; ci < P::NCHUNK_FRAME; ++ci, ++seq) {
+            int iters = prm.n_hops, c0 = 0, c1 = P::NCHUNK_FRAME;
+            if (!P::TC && prm.tp_stage != 0) {       // frame-parallel offline schedule: one iteration per frame group of this CTA, one stage's chunks
+                const long nf = (long)prm.n_streams * prm.n_hops;
+                const int ngroups = (int)((nf + P::S - 1) / P::S);
+                iters = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+                c0 = Frame<P>::tp_ci0(prm); c1 = Frame<P>::tp_ci1(prm);
+            }
+            for (int hop = 0; hop < iters; ++hop) {
+                for (int ci = c0; ci < c1; ++ci, ++seq) {
                     const unsigned stage = seq % P::STAGES, use = seq / P::STAGES;
                     const int off = __ldg(table + 2 * ci), nfl = __ldg(table + 2 * ci + 1);
                     if (use > 0) mbar_wait(bars + 8u * (P::STAGES + stage), (use - 1) & 1u);
@@ -359,7 +367,9 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
         return;
     }
     GpuCtx<P> x;
-    x.sm = sm; x.blob = prm.blob; x.prm = prm; x.cta = blockIdx.x; x.s0 = blockIdx.x * P::S;
+    x.sm = sm; x.blob = prm.blob; x.prm = prm; x.cta = blockIdx.x; x.ncta = gridDim.x; x.s0 = blockIdx.x * P::S;
+    x.ci0 = 0; x.nci = P::NCHUNK_FRAME;
+    if constexpr (!P::TC) { x.ci0 = Frame<P>::tp_ci0(prm); x.nci = Frame<P>::tp_ci1(prm) - x.ci0; }
     x.gs = prm.scratch + (size_t)blockIdx.x * P::GS_TOTAL;
     x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64(); x.cur_phase = 0;
     x.tmem = 0; x.acc_bar = bars + 8u * (2 * P::STAGES); x.acc_uses = 0;
@@ -389,6 +399,7 @@ template <class P> struct VariantImpl {
         v.smem_bytes = P::SMEM_BYTES; v.nthreads = P::NTHREADS; v.gs_floats = P::GS_TOTAL; v.state_floats = C::STATE;
         v.tap_floats = Frame<P>::TAP_TOTAL; v.nchunk_frame = P::NCHUNK_FRAME; v.blob_floats = P::make_aux().total;
         v.hop_ring = P::HOP_RING; v.hop_tile = P::HT;
+        v.tp_group = P::TP_GROUP; v.aux_window_sq = P::make_aux().window_sq;
         v.pack = &pack; v.prepare = &prepare; v.launch = &launch;
         return v;
     }

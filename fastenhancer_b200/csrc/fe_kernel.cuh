@@ -917,6 +917,17 @@ template <class P> struct Frame {
         }
     };
 
+    // frame-parallel offline schedule (fp32 family): first chunk / chunk count of the weight stream of one stage
+    static constexpr int TP_CI_BLK0 = P::EncPre::NCHUNK + E * P::Conv3::NCHUNK + P::LinPre::NCHUNK + P::RfPre::NCHUNK;
+    FE_DEV static int tp_ci0(const KParams& prm) {
+        return prm.tp_stage == 2 ? TP_CI_BLK0 + prm.tp_blk * P::BLK_CHUNKS + P::Gru::NCHUNK : 0;
+    }
+    FE_DEV static int tp_ci1(const KParams& prm) {
+        if (prm.tp_stage == 0) return P::NCHUNK_FRAME;
+        const int next = prm.tp_stage == 1 ? 0 : prm.tp_blk + 1;               // the block whose input-side GRU half ends the stage
+        return next < C::K ? TP_CI_BLK0 + next * P::BLK_CHUNKS + P::Gru::NCHUNK : P::NCHUNK_FRAME;
+    }
+
     template <class X> FE_DEV static void run(X& x) {
         const KParams& prm = x.prm;
         float* sm = x.sm;
@@ -924,6 +935,18 @@ template <class P> struct Frame {
         x.phase(PH_INIT, [&](int tid) {
             for (int i = tid * 4; i < P::SM_RING; i += NT * 4) st4(sm + i, mk4(0.f, 0.f, 0.f, 0.f));
         });
+        if (!P::TC && prm.tp_stage != 0) {         // frame-parallel offline schedule: this CTA takes the frame groups cta, cta + ncta, ...
+            if constexpr (!P::TC) {
+                const long nf = (long)prm.n_streams * prm.n_hops;
+                const int ngroups = (int)((nf + S - 1) / S);
+                for (int g = x.cta; g < ngroups; g += x.ncta) {
+                    x.gs = prm.tp_scr + (size_t)g * P::TP_GROUP;
+                    frame(x, g);
+                    x.next_frame();
+                }
+            }
+            return;
+        }
         const bool has_model = prm.mode <= MODE_OFFLINE;
         if (prm.mode == MODE_STREAM || prm.mode >= MODE_STFT) {
             x.phase(PH_STATE, [&](int tid) {
@@ -1695,6 +1718,19 @@ template <class P> struct Frame {
             }
         });
         const float* Y = have_z ? fft(x, W0, W1, true) : fft(x, W1, W0, true);
+        if (!P::TC && prm.tp_stage != 0) {
+            // frame-parallel offline schedule: the windowed frames of this group go to global memory; fe_overlap_add_kernel sums them
+            x.phase(PH_OLA, [&](int tid) {
+                const float invM = 1.0f / (float)M;
+                const long nf = (long)prm.n_streams * prm.n_hops;
+                for (int idx = tid; idx < S * N; idx += NT) {
+                    const int s = idx / N, i = idx % N;
+                    const long q = (long)hop * S + s;
+                    if (q < nf) prm.tp_frames[q * N + i] = Y[s * N + i] * invM * ldg(aux + A.window + i);
+                }
+            });
+            return;
+        }
         x.phase(PH_OLA, [&](int tid) { ola_items(x, Y, hop, tid, NT); });
         emit_hop(x, hop);
     }
@@ -1759,6 +1795,13 @@ template <class P> struct Frame {
         // With the overlapped schedule (P::FB_OVL, streaming launches) the front end of hop t + 1 runs beside the back end of hop t,
         // so only hop 0 runs its front end here.
         const bool ovl = P::FB_OVL && mode == MODE_STREAM;
+        // frame-parallel offline schedule (fp32 family only): `hop` is the frame GROUP of this iteration; slot s holds frame q = hop * S + s
+        const int tp = P::TC ? 0 : prm.tp_stage;
+        const long tp_nf = P::TC ? 0 : (long)prm.n_streams * prm.n_hops;
+        // (stream / utterance, frame index, live) of slot s
+        auto slot_gs = [&](int s) { if constexpr (P::TC) return x.s0 + s; else return tp ? (int)(((long)hop * S + s) / T) : x.s0 + s; };
+        auto slot_hop = [&](int s) { if constexpr (P::TC) return hop; else return tp ? (int)(((long)hop * S + s) % T) : hop; };
+        auto slot_live = [&](int s) { if constexpr (P::TC) return x.s0 + s < prm.n_streams; else return tp ? ((long)hop * S + s) < tp_nf : x.s0 + s < prm.n_streams; };
         // analysis window of frame hop_ -> wdst (items of threads t of nt); the new samples are also filed into the input ring
         auto window_items = [&](int hop_, float* wdst, int t, int nt) {
             const int wpos = (hop_ * H) & NMASK;
@@ -1788,9 +1831,9 @@ template <class P> struct Frame {
                         }
                     } else {      // offline framing: torch.stft(center=True, pad_mode='reflect')
                         a = b = 0.f;
-                        if (gs < prm.n_streams) {
-                            const float* w = prm.in + (size_t)gs * prm.L;
-                            long j0 = (long)hop_ * H + n2 - N / 2, j1 = j0 + 1;
+                        if (slot_live(s)) {
+                            const float* w = prm.in + (size_t)slot_gs(s) * prm.L;
+                            long j0 = (long)(tp ? slot_hop(s) : hop_) * H + n2 - N / 2, j1 = j0 + 1;
                             if (j0 < 0) j0 = -j0;
                             if (j0 >= prm.L) j0 = 2L * (prm.L - 1) - j0;
                             if (j1 < 0) j1 = -j1;
@@ -1833,7 +1876,7 @@ template <class P> struct Frame {
             });
             back_end(x, hop, false);
             return;
-        } else if (mode != MODE_SPEC && !(ovl && hop > 0)) {
+        } else if (mode != MODE_SPEC && !(ovl && hop > 0) && tp != 2) {
             if (P::HOP_RING && mode != MODE_OFFLINE && !prm.hop_tma) x.phase(PH_LOAD, [&](int tid) { fill_hop(x, hop, tid, NT); });
             x.phase(PH_WINDOW, [&](int tid) {
                 if (P::HOP_RING && prm.hop_tma) x.hop_wait(hop);
@@ -1899,7 +1942,7 @@ template <class P> struct Frame {
 
         // ================= encoder =================
         const float* src = SPEC;
-        for (int i = 0; i <= E; ++i) {
+        for (int i = 0; i <= E && tp != 2; ++i) {
             float* dst = skip_dst(x, i);
             const float* bias = aux + (i == 0 ? A.enc_pre_b : A.enc_b(i - 1));
             if constexpr (P::TC) {
@@ -1951,6 +1994,7 @@ template <class P> struct Frame {
             ci = rnnformer_tc(x, hop, ci, src, dbg);
         } else {
             // ================= rf_pre: Linear(F1->F2) on the frequency axis, then 1x1 conv =================
+            if (tp != 2) {
             x.phase(PH_LIN_PRE, [&](int tid) {
                 row_gemm<typename P::LinPre>(x, tid, ci, src + 4, P1, [&](int r, int o0, const float* v) {
 #pragma unroll
@@ -1968,20 +2012,37 @@ template <class P> struct Frame {
             });
             ci += P::RfPre::NCHUNK;
             if (dbg) dump_rf(XR, TAP_RFPRE);
+            } else ci = tp_ci0(prm);      // stage B resumes behind the GRU of block tp_blk
 
             // ================= RNNFormer blocks =================
             float* HB = AB + P::O_HB;
             float* G = AB + P::O_G;
             float* QKV = AB + P::O_QKV;
             float* ATT = AB + P::O_ATT;
-            for (int k = 0; k < C::K; ++k) {
+            // Frame-parallel schedule: the recurrence runs between the launches (fe_gru_scan_kernel).  A stage ends with the INPUT half of
+            // the next GRU (x_only: h = 0, the three input-side pre-activations go to tp_gx); stage B starts behind the GRU of block
+            // tp_blk with x reloaded from the group scratch and G = the scanned hidden states.
+            for (int k = (tp == 2 ? prm.tp_blk : 0); k < C::K; ++k) {
                 const auto ab = A.blk(k);
+                const bool x_only = (tp == 1) || (tp == 2 && k == prm.tp_blk + 1);
+                const bool resume = tp == 2 && k == prm.tp_blk;
+                if (resume) {
+                    x.phase(PH_HLOAD, [&](int tid) {
+                        const float* xsrc = x.gs + P::TP_O_XR;
+                        for (int idx = tid * 4; idx < P::XRS; idx += NT * 4) st4(XR + idx, ld4(xsrc + idx));
+                        for (int idx = tid; idx < S * C2 * F2; idx += NT) {
+                            const int s = idx / (C2 * F2), r = idx % (C2 * F2), f = r / C2, c = r % C2;
+                            const long q = (long)hop * S + s;
+                            G[c * PR + s * F2P + f] = q < tp_nf ? prm.tp_h[(q * F2 + f) * C2 + c] : 0.f;
+                        }
+                    });
+                } else {
                 // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
                 x.phase(PH_HLOAD, [&](int tid) {
                     for (int idx = tid; idx < S * C2 * F2; idx += NT) {
                         int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
                         float v = 0.f;
-                        if (gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
+                        if (!x_only && gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
                         HB[c * PR + s * F2P + f] = v;
                     }
                 });
@@ -2024,7 +2085,22 @@ template <class P> struct Frame {
                             }
                             x.release(ci + pass * L::NCHUNK_PASS + c);
                         }
-                        if (active) {
+                        if (active && x_only) {
+                            const long q = (long)hop * S + g.s;
+                            if (q < tp_nf) {
+#pragma unroll
+                                for (int i = 0; i < CT; ++i) {
+                                    const int c = co0 + i;
+                                    if (c < C2) {
+#pragma unroll
+                                        for (int j = 0; j < PT; ++j) {
+                                            float* gx = prm.tp_gx + ((q * F2 + g.f + j) * 3) * C2 + c;
+                                            gx[0] = ar[i][j]; gx[C2] = az[i][j]; gx[2 * C2] = anx[i][j];
+                                        }
+                                    }
+                                }
+                            }
+                        } else if (active) {
                             const int gs = x.s0 + g.s;
 #pragma unroll
                             for (int i = 0; i < CT; ++i) {
@@ -2052,6 +2128,19 @@ template <class P> struct Frame {
                     }
                 });
                 ci += P::Gru::NCHUNK;
+                }
+                if (x_only) {       // end of the stage: the residual stream waits in the group scratch for the scan
+                    x.phase(PH_STATE, [&](int tid) {
+                        float* xdst = x.gs + P::TP_O_XR;
+                        for (int idx = tid * 4; idx < P::XRS; idx += NT * 4) st4(xdst + idx, ld4(XR + idx));
+                        if (tp == 1) {      // ... and so do the spectrum and the resident skip tensors (the others were spilled there by the encoder)
+                            for (int idx = tid * 4; idx < P::SPECF; idx += NT * 4) st4(x.gs + P::TP_O_SPEC + idx, ld4(SPEC + idx));
+                            for (int i = 0; i < P::SKIP_SMEM; ++i)
+                                for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(x.gs + P::TP_O_SK + i * ACT + idx, ld4(sm + P::SM_SK + i * ACT + idx));
+                        }
+                    });
+                    return;
+                }
                 // rnn_fc (+ folded BN) + residual (+ positional embedding in block 0)
                 x.phase(PH_RNN_FC, [&](int tid) {
                     pos_gemm<typename P::Fc>(x, tid, ci, [&](int kk) { return G + kk * PR; }, F2P, 0,
@@ -2151,6 +2240,13 @@ template <class P> struct Frame {
             }
         }
 
+        if (tp == 2) {        // last stage of the frame-parallel schedule: the spectrum and the resident skip tensors come back from the group scratch
+            x.phase(PH_SKIP_LOAD, [&](int tid) {
+                for (int idx = tid * 4; idx < P::SPECF; idx += NT * 4) st4(SPEC + idx, ld4(x.gs + P::TP_O_SPEC + idx));
+                for (int i = 0; i < P::SKIP_SMEM; ++i)
+                    for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(sm + P::SM_SK + i * ACT + idx, ld4(x.gs + P::TP_O_SK + i * ACT + idx));
+            });
+        }
         // ================= rf_post: Linear(F2->F1), 1x1 conv =================
         float* Zb = AB + P::O_Z;
         if constexpr (P::LIN_TC) {
@@ -2348,14 +2444,14 @@ template <class P> struct Frame {
         // with E = (Y[k] + conj(Y[M-k])) / 2, O = (Y[k] - conj(Y[M-k])) / 2 * exp(+2 pi i k / N); imag of DC ignored, Nyquist = 0.
         auto mask_items = [&](int t, int nt) {
             for (int idx = t; idx < S * (M / 2); idx += nt) {          // item 0 takes the two unpaired bins 0 and M/2
-                const int s = idx / (M / 2), k = idx % (M / 2), gs = x.s0 + s;
+                const int s = idx / (M / 2), k = idx % (M / 2), gs = slot_gs(s);
                 auto bin = [&](int kk) {
                     const int o0 = spec_off(0, s, kk), o1 = spec_off(1, s, kk);
                     const float xr = SPEC[o0], xi = SPEC[o1], mr = MASK[o0], mi = MASK[o1];
                     const float yr = xr * mr - xi * mi, yi = xr * mi + xi * mr;
                     if (dbg && s == 0) { prm.dbg[TAP_SPECHAT + kk] = yr; prm.dbg[TAP_SPECHAT + FIN + kk] = yi; }
-                    if (mode == MODE_OFFLINE && prm.spec_out != nullptr && gs < prm.n_streams)
-                        st2(prm.spec_out + (((size_t)gs * FIN + kk) * T + hop) * 2, mk2(yr, yi));
+                    if (mode == MODE_OFFLINE && prm.spec_out != nullptr && slot_live(s))
+                        st2(prm.spec_out + (((size_t)gs * FIN + kk) * T + slot_hop(s)) * 2, mk2(yr, yi));
                     const float g = powf(sqrtf(yr * yr + yi * yi), decomp_e);
                     return mk2(yr * g, yi * g);
                 };

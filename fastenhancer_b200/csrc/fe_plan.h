@@ -425,6 +425,9 @@ struct Plan {
     // global scratch per CTA: spilled skip tensors
     static constexpr int GS_TOTAL = (NSK - SKIP_SMEM) * ACT + 4;
     static_assert(C1P == C::C1 || SKIP_SMEM == NSK, "a channel-padding slab and spilled skip tensors do not mix (the spill never holds the zero slab)");
+    // frame-parallel offline schedule (fp32 family): per-group scratch between the stages = [spilled skips | spectrum | resident skips | x]
+    static constexpr int TP_O_SPEC = round_up(GS_TOTAL, 4), TP_O_SK = TP_O_SPEC + round_up(SPECF, 4), TP_O_XR = TP_O_SK + SKIP_SMEM * round_up(ACT, 4);
+    static constexpr int TP_GROUP = TP_O_XR + round_up(XRS, 4);
 
     // ---- layers (weight-stream order) ----
     using EncPre = PosGemm<S * C::F1, C::F1, C::C1, 8, 3, 4, T::CT_CONV, NW, CHUNK>;
@@ -555,6 +558,15 @@ struct KParams {
     int hop_tma;              // streaming launches of HOP_RING variants: the input hop arrives / the output hop leaves as 2-D TMA tiles
     const void* tmaps;        // ... described by two CUtensorMap (input, output) in global memory (device; 64-byte aligned)
     float compression;
+    // ---- frame-parallel offline schedule (MODE_OFFLINE, fp32 family; fe_api.cu::offline_tp): the CTAs take groups of S FRAMES (slot =
+    //      frame q = group * S + s of the n_streams * n_hops frames; utterance q / n_hops, frame q % n_hops) instead of S streams ----
+    int tp_stage;             // 0 = off; 1 = stage A: front end, encoder, rf_pre, input half of GRU 0; 2 = stage B of block tp_blk: rnn_fc,
+                              // attention, attn_fc, then the input half of GRU tp_blk + 1 or (last block) rf_post .. inverse FFT
+    int tp_blk;
+    float* tp_scr;            // [groups][Plan::TP_GROUP] spectrum, skip tensors, residual stream between the stages
+    float* tp_gx;             // [frames][F2][3][C2] input-side gate pre-activations (W_ir x | W_iz x | W_in x, no bias)
+    const float* tp_h;        // [frames][F2][C2] hidden states of block tp_blk (output of the scan)
+    float* tp_frames;         // [frames][N] windowed output frames (input of the overlap-add)
 };
 
 // MODE_STFT / MODE_ISTFT: the front / back end alone (ONNXSTFT.forward / .inverse, functional/audio_modules.py:243-303);

@@ -14,6 +14,8 @@ struct VariantOps {
     ShapeKey shape;
     int smem_bytes, nthreads, gs_floats, state_floats, tap_floats, nchunk_frame;
     long blob_floats;
+    int tp_group;                                                  // floats of per-group scratch of the frame-parallel offline schedule (fp32 family)
+    int aux_window_sq;                                             // float offset of window^2 [N] in the blob
     int hop_ring, hop_tile;                                        // hop tiles by 2-D TMA (cp.async.bulk.tensor): supported, tile width
     void (*pack)(const float* canonical, std::vector<float>& blob);
     cudaError_t (*prepare)();                                      // one-time function attributes

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
     "fe_state_create_on", "fe_state_planes", "fe_microbench_fma", "fe_fold_device", "fe_create_from_device",
-    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16",
+    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode",
 )
 
 #: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
@@ -98,6 +98,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_microbench_fma.argtypes = [ip, ctypes.POINTER(ctypes.c_double)]
     lib.fe_set_precision.argtypes = [vp, ip]
     lib.fe_get_precision.argtypes = [vp]
+    lib.fe_set_offline_mode.argtypes = [vp, ip]
     _lib = lib
     return lib
 
@@ -271,6 +272,14 @@ class Engine:
         if precision not in PRECISION_MODES:
             raise ValueError(f"precision must be one of {sorted(PRECISION_MODES)}")
         _check(self._lib.fe_set_precision(self._h, PRECISION_MODES[precision]), "fe_set_precision")
+
+    def set_offline_mode(self, mode: str) -> None:
+        """Schedule of ``offline`` (``Model.forward``): 'auto', 'walk' (one CTA per group of utterances steps through the frames) or
+        'frame_parallel' (CTAs take groups of frames, the GRU recurrence runs as a scan between the launches; fp32-accurate modes)."""
+        modes = {"auto": 0, "walk": 1, "frame_parallel": 2}
+        if mode not in modes:
+            raise ValueError(f"offline mode must be one of {sorted(modes)}")
+        _check(self._lib.fe_set_offline_mode(self._h, modes[mode]), "fe_set_offline_mode")
 
     @property
     def precision(self) -> str:

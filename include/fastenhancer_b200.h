@@ -125,6 +125,14 @@ int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, in
 /* Replaces: Model.forward(noisy) (model.py:728-735): wav [B][L] -> wav_out [B][hop*(L/hop)] and (optional)
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
+/* Schedule of fe_offline.  0 (default) = automatic; 1 = sequential walk: one CTA per group of utterances steps through the frames
+ * (best for large batches); 2 = frame-parallel: outside the GRU recurrence (nn.GRU over time, model.py:266-272) the frames of an
+ * utterance are independent, so the CTAs take groups of FRAMES -- front end, encoder, rf_pre and the input half of the GRU for all
+ * frames at once, the recurrence as a scan (one CTA per (utterance, sub-band) row), then attention / decoder / inverse FFT for all
+ * frames at once, then one overlap-add pass -- which is what Model.forward(noisy [B, L]) on a few long utterances needs to fill the GPU
+ * (reference: models/fastenhancer/default/model.py:711-735).  fp32-accurate precision modes only (it runs the fp32 kernel family);
+ * automatic mode picks it when the walk would occupy fewer than half of the SMs.  Results equal the walk's up to fp32 summation order. */
+int fe_set_offline_mode(fe_engine* e, int mode);
 
 /* Arithmetic of the channel contractions (conv-type layers, RNNFormer linears, GRU matrix products).
  * The DEFAULT of a new engine reproduces the fp32 reference: mode 4 where the model has such kernels (T / B), else mode 1.

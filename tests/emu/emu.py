@@ -42,6 +42,7 @@ def _load():
         _lib.fee_run.argtypes = [ctypes.c_int] * 10 + [fp, ctypes.c_int, fp, fp, fp, fp] + [ctypes.c_int] * 3 + \
             [ctypes.c_longlong] * 2 + [fp, ctypes.c_int, ctypes.c_float]
         _lib.fee_tap_total.argtypes = [ctypes.c_int] * 8
+        _lib.fee_offline_tp.argtypes = [ctypes.c_int] * 9 + [fp, fp, fp, fp] + [ctypes.c_int] * 3 + [ctypes.c_float]
     return _lib
 
 
@@ -84,3 +85,14 @@ def run(cfg, S, canonical, mode, state_native, inp, out, spec_out=None, n_stream
 
 def tap_total(cfg):
     return _load().fee_tap_total(*_shape(cfg))
+
+
+def offline_tp(cfg, S, canonical, wav, out, spec_out=None, grid=3):
+    """Model.forward on wav [B, L] through the frame-parallel offline schedule (fp32 family): staged launches of the fused kernel body on
+    `grid` emulated CTAs, the GRU scan and the overlap-add restated on the host."""
+    lib = _load()
+    B, L = wav.shape
+    rc = lib.fee_offline_tp(*_shape(cfg), S, _p(np.ascontiguousarray(canonical, np.float32)), _p(wav), _p(out), _p(spec_out), B, L, grid,
+                            cfg.input_compression)
+    if rc != 0:
+        raise RuntimeError(f"fee_offline_tp failed rc={rc}")

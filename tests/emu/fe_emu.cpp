@@ -18,7 +18,7 @@
 namespace fe {
 
 template <class P> struct EmuCtx {
-    float* sm; const float* blob; KParams prm; int s0; float* gs; int cta;
+    float* sm; const float* blob; KParams prm; int s0; float* gs; int cta, ncta = 1;
     long frames_done = 0;
     const int* table;
     const float* acquire(int ci, int expect_floats) const {
@@ -162,11 +162,77 @@ template <class P> int run_variant(const float* canonical, KParams prm) {
         EmuCtx<P> x;
         x.sm = sm.data(); x.blob = blob.data(); x.prm = prm; x.prm.blob = blob.data();
         x.prm.hop_tma = (P::HOP_RING && prm.mode == MODE_STREAM && !std::getenv("FE_EMU_NO_HOP_TMA")) ? 1 : 0;
-        x.s0 = cta * P::S; x.gs = gs.data(); x.cta = cta;
+        x.s0 = cta * P::S; x.gs = gs.data(); x.cta = cta; x.ncta = grid;
         x.table = reinterpret_cast<const int*>(blob.data() + A.table);
         Frame<P>::run(x);
     }
     return 0;
+}
+
+// Frame-parallel offline schedule (fe_api.cu::offline_tp) on the host: the staged launches of the fused kernel body with a plain C
+// restatement of the two small kernels that run between them (fe_gru_scan_kernel, fe_overlap_add_kernel) -- checks the stage
+// boundaries, the group scratch and the chunk ranges of the weight stream.
+template <class P> int run_offline_tp(const float* canonical, KParams prm, int grid) {
+    if constexpr (P::TC) { (void)canonical; (void)prm; (void)grid; return -3; }
+    else {
+        using C = typename P::Cf;
+        constexpr int C2 = C::C2, F2 = C::F2, N = C::N_FFT, H = C::HOP;
+        std::vector<float> blob = pack_blob<P>(canonical);
+        constexpr auto A = P::make_aux();
+        const int B = prm.n_streams, T = prm.n_hops;
+        const long nf = (long)B * T;
+        const int ngroups = (int)((nf + P::S - 1) / P::S);
+        std::vector<float> scr((size_t)ngroups * P::TP_GROUP, std::nanf("")), gx((size_t)nf * F2 * 3 * C2, std::nanf("")), hs((size_t)nf * F2 * C2, std::nanf("")),
+            frames((size_t)nf * N, std::nanf("")), sm(P::SM_TOTAL);
+        auto stage = [&](int st, int blk) {
+            for (int cta = 0; cta < grid; ++cta) {
+                for (auto& v : sm) v = std::nanf("");
+                EmuCtx<P> x;
+                x.sm = sm.data(); x.blob = blob.data(); x.prm = prm; x.prm.blob = blob.data(); x.prm.hop_tma = 0;
+                x.prm.tp_stage = st; x.prm.tp_blk = blk; x.prm.tp_scr = scr.data(); x.prm.tp_gx = gx.data(); x.prm.tp_h = hs.data(); x.prm.tp_frames = frames.data();
+                x.s0 = cta * P::S; x.gs = nullptr; x.cta = cta; x.ncta = grid;
+                x.table = reinterpret_cast<const int*>(blob.data() + A.table);
+                Frame<P>::run(x);
+            }
+        };
+        Canon<C> cw(canonical);
+        auto sig = [](float v) { return 1.0f / (1.0f + std::exp(-v)); };
+        stage(1, 0);
+        for (int k = 0; k < C::K; ++k) {
+            const auto& b = cw.blk[k];
+            for (int u = 0; u < B; ++u)
+                for (int f = 0; f < F2; ++f) {
+                    std::vector<float> h(C2, 0.f), hn(C2);
+                    for (int t = 0; t < T; ++t) {
+                        const long q = (long)u * T + t;
+                        const float* g = gx.data() + ((q * F2 + f) * 3) * C2;
+                        for (int j = 0; j < C2; ++j) {
+                            float ar = 0.f, az = 0.f, an = 0.f;
+                            for (int c = 0; c < C2; ++c) {
+                                ar += b.w_hh[(0 * C2 + j) * C2 + c] * h[c]; az += b.w_hh[(1 * C2 + j) * C2 + c] * h[c]; an += b.w_hh[(2 * C2 + j) * C2 + c] * h[c];
+                            }
+                            const float r = sig(g[j] + b.b_ih[j] + b.b_hh[j] + ar), z = sig(g[C2 + j] + b.b_ih[C2 + j] + b.b_hh[C2 + j] + az);
+                            const float n = std::tanh(g[2 * C2 + j] + b.b_ih[2 * C2 + j] + r * (an + b.b_hh[2 * C2 + j]));
+                            hn[j] = (1.0f - z) * n + z * h[j];
+                        }
+                        h = hn;
+                        for (int j = 0; j < C2; ++j) hs[(q * F2 + f) * C2 + j] = h[j];
+                    }
+                }
+            stage(2, k);
+        }
+        const float* wsq = blob.data() + A.window_sq;
+        for (int u = 0; u < B; ++u)
+            for (long n = 0; n < (long)H * (T - 1); ++n) {
+                const long npad = n + N / 2;
+                long t0 = npad < N ? 0 : (npad - N + H) / H, t1 = npad / H;
+                if (t1 > T - 1) t1 = T - 1;
+                float v = 0.f, env = 0.f;
+                for (long t = t0; t <= t1; ++t) { v += frames[((size_t)u * T + t) * N + (npad - t * H)]; env += wsq[npad - t * H]; }
+                prm.out[(size_t)u * H * (T - 1) + n] = v / env;
+            }
+        return 0;
+    }
 }
 
 }  // namespace fe
@@ -205,6 +271,13 @@ extern "C" int FE_CAT(fee_run_g, FE_EMU_GROUP)(const fe::ShapeKey* key, int S, i
 #undef X
     return -1;
 }
+extern "C" int FE_CAT(fee_tp_g, FE_EMU_GROUP)(const fe::ShapeKey* key, int S, const float* canonical, const fe::KParams* prm, int grid)
+{
+#define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(*key) && S == SV && (int)(TCV) == 0) return fe::run_offline_tp<fe::Plan<fe::CFG, SV, 0>>(canonical, *prm, grid);
+    FE_GROUP_VARIANTS(X)
+#undef X
+    return -1;
+}
 extern "C" int FE_CAT(fee_tap_g, FE_EMU_GROUP)(const fe::ShapeKey* key)
 {
 #define X(id, CFG, SV, TCV) if (fe::shape_matches<fe::CFG>(*key)) return fe::Frame<fe::Plan<fe::CFG, SV, TCV>>::TAP_TOTAL;
@@ -216,7 +289,8 @@ extern "C" int FE_CAT(fee_tap_g, FE_EMU_GROUP)(const fe::ShapeKey* key)
 
 #ifdef FE_EMU_MAIN
 #define FE_GROUPS(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
-#define X(g) extern "C" int fee_run_g##g(const fe::ShapeKey*, int, int, const float*, const fe::KParams*); extern "C" int fee_tap_g##g(const fe::ShapeKey*);
+#define X(g) extern "C" int fee_run_g##g(const fe::ShapeKey*, int, int, const float*, const fe::KParams*); extern "C" int fee_tap_g##g(const fe::ShapeKey*); \
+    extern "C" int fee_tp_g##g(const fe::ShapeKey*, int, const float*, const fe::KParams*, int);
 FE_GROUPS(X)
 #undef X
 extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S, int tc,
@@ -235,6 +309,25 @@ extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, in
 #undef X
     } catch (const std::exception& e) {
         std::fprintf(stderr, "fee_run: %s\n", e.what());
+        return -2;
+    }
+    return -1;
+}
+
+// Model.forward on [B, L] through the frame-parallel schedule (fp32 family), `grid` emulated CTAs
+extern "C" int fee_offline_tp(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S, const float* canonical,
+                              const float* in, float* out, float* spec_out, int B, int L, int grid, float compression)
+{
+    fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
+    fe::KParams prm{};
+    prm.in = in; prm.out = out; prm.spec_out = spec_out; prm.n_streams = B; prm.n_hops = 1 + L / hop; prm.mode = fe::MODE_OFFLINE; prm.L = L;
+    prm.dbg_hop = -1; prm.compression = compression;
+    try {
+#define X(g) { const int rc = fee_tp_g##g(&key, S, canonical, &prm, grid); if (rc != -1) return rc; }
+        FE_GROUPS(X)
+#undef X
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "fee_offline_tp: %s\n", e.what());
         return -2;
     }
     return -1;

@@ -155,3 +155,21 @@ def test_hop_tiles_without_tma(name, S, tc, canonical, monkeypatch):
         outs.append((y, stn))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][0]).max() > 0.01
+
+
+@pytest.mark.parametrize("name,S,grid", [("16k_t", 2, 3), ("16k_t", 4, 2), ("16k_b", 2, 4), ("16k_b", 1, 5), ("16k_m", 1, 3), ("48k_s", 1, 2)])
+def test_offline_frame_parallel_schedule(name, S, grid, canonical):
+    """Model.forward through the frame-parallel offline schedule (fp32 family: stage A -> GRU scan -> stage B per block -> overlap-add,
+    frames instead of streams in the CTA slots) equals the sequential offline walk: ragged length, frame count not a multiple of S,
+    more frame groups than CTAs, two utterances whose frames share a group."""
+    cfg = PRESETS[name]
+    canon = canonical(name)
+    o = Oracle(cfg, canon)
+    B, H = 2, cfg.hop_size
+    L = 6 * H + 37
+    w = synthetic_noisy(B, L, cfg.sample_rate)
+    w_ref, sp_ref = o.offline(w)
+    w_out, sp_out = np.full_like(w_ref, np.nan), np.full_like(sp_ref, np.nan)
+    emu.offline_tp(cfg, S, canon, w, w_out, spec_out=sp_out, grid=grid)
+    assert np.sqrt(np.mean((w_out - w_ref) ** 2)) < TOL[False]["wav"]
+    assert np.abs(sp_out - sp_ref).max() < TOL[False]["spec_abs"] * max(1.0, np.abs(sp_ref).max())

@@ -144,6 +144,63 @@ def test_offline_matches_reference_golden(name, golden, engines, precision):
 
 
 @pytest.mark.parametrize("name", ALL)
+def test_offline_schedules_agree_and_match_reference_golden(name, golden, canonical):
+    """Model.forward through both schedules of fe_offline: the sequential walk (one CTA per group of utterances) and the
+    frame-parallel schedule (stage A -> GRU scan -> stage B per block -> overlap-add).  Both must reproduce the reference's golden
+    output; between themselves they differ by fp32 summation order only."""
+    from fastenhancer_b200.engine import Engine
+    cfg, g = PRESETS[name], golden(name)
+    eng = Engine(cfg, canonical(name), "cuda:0", precision="fp32")
+    L = int(g["offline_len"])
+    x = torch.from_numpy(synthetic_noisy(2, L, cfg.sample_rate)).cuda()
+    out = {}
+    for mode in ("walk", "frame_parallel"):
+        eng.set_offline_mode(mode)
+        n0 = eng.kernel_launches
+        wav, spec = eng.offline(x)
+        out[mode] = (wav.cpu().numpy(), spec.cpu().numpy(), eng.kernel_launches - n0)
+        assert rms(out[mode][0] - g["offline_wav"]) < TOL["fp32"]["wav"], mode
+        sp = out[mode][1][:, :, g["offline_spec_frames"]] if "offline_spec_frames" in g.files else out[mode][1]
+        assert np.abs(sp - g["offline_spec"]).max() < TOL["fp32"]["spec_abs"] * max(1.0, np.abs(g["offline_spec"]).max()), mode
+    assert out["walk"][2] == 1 and out["frame_parallel"][2] == cfg.rf_blocks + 1        # fused-kernel launches: 1 vs stage A + one stage B per block
+    assert rms(out["walk"][0] - out["frame_parallel"][0]) < 2e-6
+    assert np.abs(out["walk"][1] - out["frame_parallel"][1]).max() < 2e-5 * max(1.0, np.abs(out["walk"][1]).max())
+
+
+@pytest.mark.parametrize("name,B,seconds", [("16k_t", 1, 10.0), ("16k_b", 1, 10.0), ("16k_b", 3, 2.5), ("48k_b", 2, 1.0), ("16k_l", 1, 2.0)])
+def test_offline_frame_parallel_long_utterance(name, B, seconds, canonical):
+    """BASELINE config 1 (T, batch 1, one 10 s utterance through Model.forward) and friends on the frame-parallel schedule against the
+    oracle: hundreds of sequential scan steps, more frame groups than SMs, ragged lengths, several utterances."""
+    from fastenhancer_b200.engine import Engine
+    cfg = PRESETS[name]
+    eng = Engine(cfg, canonical(name), "cuda:0")                  # default precision: fp32x3 where it exists, else fp32
+    eng.set_offline_mode("frame_parallel")
+    L = int(seconds * cfg.sample_rate) + 77
+    x = synthetic_noisy(B, L, cfg.sample_rate)
+    w_ref, sp_ref = _oracle(name, canonical).offline(x)
+    wav, spec = eng.offline(torch.from_numpy(x).cuda())
+    assert rms(wav.cpu().numpy() - w_ref) < TOL["fp32"]["wav"]
+    assert np.abs(spec.cpu().numpy() - sp_ref).max() < TOL["fp32"]["spec_abs"] * max(1.0, np.abs(sp_ref).max())
+    eng.set_offline_mode("auto")                                  # few utterances: automatic mode picks the same schedule
+    n0 = eng.kernel_launches
+    wav2, _ = eng.offline(torch.from_numpy(x).cuda())
+    assert eng.kernel_launches - n0 == cfg.rf_blocks + 1 and torch.equal(wav, wav2)
+
+
+def test_offline_frame_parallel_needs_accurate_mode(canonical):
+    from fastenhancer_b200.engine import Engine
+    cfg = PRESETS["16k_b"]
+    eng = Engine(cfg, canonical("16k_b"), "cuda:0", precision="f16")
+    eng.set_offline_mode("frame_parallel")
+    with pytest.raises(RuntimeError, match="fp32-accurate"):
+        eng.offline(torch.zeros(1, 4000).cuda())
+    eng.set_offline_mode("auto")                                  # reduced-precision modes keep the walk
+    n0 = eng.kernel_launches
+    eng.offline(torch.zeros(1, 4000).cuda())
+    assert eng.kernel_launches - n0 == 1
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_spec2spec_matches_reference_golden(name, golden, engines, precision):
     cfg, g, eng = PRESETS[name], golden(name), engines(name)
     st = eng.new_state(2)
