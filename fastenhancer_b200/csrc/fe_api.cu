@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include "../../include/fastenhancer_b200.h"
 #include "fe_variant.h"
 #include "fe_kernel.cuh"
+#include "fe_stft_gemm.h"
 
 namespace {
 
@@ -242,6 +244,7 @@ struct fe_engine {
     std::mutex mu;
     cudaMemPool_t pool = nullptr;        // stream-ordered scratch of fe_offline: an engine-owned pool that keeps its memory between calls
     int offline_mode = 0;                // fe_offline: 0 = automatic, 1 = sequential walk (one CTA per stream group), 2 = frame-parallel schedule
+    float* basis_dev = nullptr;          // windowed DFT basis of the tensor-core STFT (hi | lo, [2][N][N]), built on first use
     float* canon_dev = nullptr;          // canonical weights on the device (hidden-to-hidden GRU weights of the scan), uploaded on first use
 };
 
@@ -568,6 +571,7 @@ FE_API void fe_destroy(fe_engine* e) {
     cudaSetDevice(e->device);
     for (Variant& v : e->variants) if (v.blob) cudaFree(v.blob);
     if (e->canon_dev) cudaFree(e->canon_dev);
+    if (e->basis_dev) cudaFree(e->basis_dev);
     if (e->pool) cudaMemPoolDestroy(e->pool);
     delete e;
 }
@@ -839,6 +843,32 @@ FE_API int fe_set_precision(fe_engine* e, int mode) {
     e->tc = tc;
     return FE_OK;
 }
+// The STFT of many frames at once as a tensor-core GEMM (fe_stft_gemm.cu): frame t of utterance b = wav[b][t*hop .. t*hop + n_fft - 1]
+// (no centering and no cache: a streaming caller prepends its n_fft - hop cached samples), periodic Hann window of the model.
+FE_API int fe_stft_gemm(fe_engine* e, const float* wav, int B, long long ld, int T, float* spec_out, int accurate, void* cuda_stream) {
+    if (!e || !wav || !spec_out || B <= 0 || T <= 0) return fail(FE_ERR_ARG, "fe_stft_gemm: bad argument");
+    const int N = e->cfg.n_fft, H = e->cfg.hop;
+    if (ld < (long long)(T - 1) * H + N) return fail(FE_ERR_ARG, "fe_stft_gemm: leading dimension smaller than (T-1)*hop + n_fft");
+    FE_CUDA(cudaSetDevice(e->device));
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (!e->basis_dev) {
+            std::vector<float> win(N), hi, lo;
+            for (int i = 0; i < N; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / N));       // periodic Hann, as fe_pack.h
+            fe::stft_gemm_basis(N, win.data(), hi, lo);
+            FE_CUDA(cudaMalloc(&e->basis_dev, 2 * hi.size() * sizeof(float)));
+            FE_CUDA(cudaMemcpy(e->basis_dev, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+            FE_CUDA(cudaMemcpy(e->basis_dev + hi.size(), lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    cudaError_t ce = cudaSuccess;
+    const int rc = fe::stft_gemm_launch(wav, ld, B, T, N, H, e->basis_dev, e->basis_dev + (size_t)N * N, spec_out, accurate, (cudaStream_t)cuda_stream, &ce);
+    if (rc == 1) return fail(FE_ERR_ARG, "fe_stft_gemm: wav must be 16-byte aligned with ld % 4 == 0 (TMA tensor map over the waveform)");
+    if (rc == 2) return fail(FE_ERR_UNSUPPORTED, "fe_stft_gemm: cuTensorMapEncodeTiled rejected the tensor map");
+    if (rc == 3) return cuda_fail(ce, "fe_stft_gemm");
+    return FE_OK;
+}
+
 FE_API int fe_set_offline_mode(fe_engine* e, int mode) {
     if (!e || mode < 0 || mode > 2) return fail(FE_ERR_ARG, "fe_set_offline_mode: mode must be 0 (automatic), 1 (sequential walk) or 2 (frame-parallel)");
     e->offline_mode = mode;

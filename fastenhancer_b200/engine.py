@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
     "fe_state_create_on", "fe_state_planes", "fe_microbench_fma", "fe_fold_device", "fe_create_from_device",
-    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode",
+    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode", "fe_stft_gemm",
 )
 
 #: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
@@ -99,6 +99,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_set_precision.argtypes = [vp, ip]
     lib.fe_get_precision.argtypes = [vp]
     lib.fe_set_offline_mode.argtypes = [vp, ip]
+    lib.fe_stft_gemm.argtypes = [vp, fp, ip, ll, ip, fp, ip, vp]
     _lib = lib
     return lib
 
@@ -393,6 +394,24 @@ class Engine:
         out = torch.empty((B, T * self.cfg.hop_size), dtype=torch.float32, device=self.device)
         _check(self._lib.fe_istft(self._h, state._h, x.data_ptr(), out.data_ptr(), T, out.stride(0), _stream_ptr(self.device)), "fe_istft")
         return out
+
+    def stft_gemm(self, wav, n_frames: tp.Optional[int] = None, accurate: bool = True):
+        """STFT of wav [B, L] as a tensor-core GEMM (ConvSTFT.forward over a whole signal): frame t = wav[:, t*hop : t*hop + n_fft];
+        returns spec [B, n_fft/2+1, T, 2] with T = 1 + (L - n_fft) // hop (or ``n_frames``)."""
+        import torch
+        x = self._dev(wav)
+        B, L = x.shape
+        N, H = self.cfg.n_fft, self.cfg.hop_size
+        T = 1 + (L - N) // H if n_frames is None else n_frames
+        if T < 1 or (T - 1) * H + N > L:
+            raise ValueError(f"signal of {L} samples holds fewer than {T} frames")
+        if x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:          # TMA tensor map: 16-byte aligned rows
+            pad = (-L) % 4
+            x = torch.nn.functional.pad(x, (0, pad)).contiguous()
+        spec = torch.empty((B, N // 2 + 1, T, 2), dtype=torch.float32, device=self.device)
+        _check(self._lib.fe_stft_gemm(self._h, x.data_ptr(), B, x.stride(0), T, spec.data_ptr(), 1 if accurate else 0, _stream_ptr(self.device)),
+               "fe_stft_gemm")
+        return spec
 
     def offline(self, wav, want_spec: bool = True):
         """Model.forward: wav [B, L] -> (wav_hat [B, hop*(L//hop)], spec_hat [B, n_fft/2, 1+L//hop, 2] or None)."""

@@ -122,6 +122,13 @@ int fe_spec(fe_engine* e, fe_state* s, const float* spec_in, float* spec_out, in
 int fe_stft(fe_engine* e, fe_state* s, const float* wav_in, float* spec_out, int n_hops, long long ld_in, void* cuda_stream);
 int fe_istft(fe_engine* e, fe_state* s, const float* spec_in, float* wav_out, int n_hops, long long ld_out, void* cuda_stream);
 
+/* The STFT as a tensor-core GEMM -- the reference's ConvSTFT front end (models/fastenhancer/conv_stft/model.py:55-63, 110-114:
+ * F.conv1d of the waveform with the windowed DFT basis, stride = hop) for callers that transform many frames at once:
+ * spec_out [B][n_fft/2+1][T][2] (device), frame t of utterance b = wav[b][t*hop .. t*hop + n_fft - 1] (wav [B][ld] device, 16-byte
+ * aligned, ld % 4 == 0, ld >= (T-1)*hop + n_fft; no centering, no cache), periodic Hann window.  accurate != 0: fp32-accurate 3xTF32
+ * (hi / lo split of both operands); 0: one TF32 pass.  An alternative to fe_stft's in-kernel FFT, not used by the fused path. */
+int fe_stft_gemm(fe_engine* e, const float* wav, int B, long long ld, int T, float* spec_out, int accurate, void* cuda_stream);
+
 /* Replaces: Model.forward(noisy) (model.py:728-735): wav [B][L] -> wav_out [B][hop*(L/hop)] and (optional)
  * the compressed masked spectrum spec_out [B][n_fft/2][1 + L/hop][2].  Zero initial GRU state. */
 int fe_offline(fe_engine* e, const float* wav, int B, int L, float* wav_out, float* spec_out, void* cuda_stream);
