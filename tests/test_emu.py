@@ -22,13 +22,14 @@ TOL = {False: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4), Tr
        2: dict(wav=5e-5, state=3e-3, tap=3e-3, spec=1e-3, spec_abs=3e-3),
        3: dict(wav=1e-4, state=5e-3, tap=2e-2, spec=1e-2, spec_abs=2e-2),
        4: dict(wav=2e-6, state=5e-6, tap=2e-5, spec=1e-5, spec_abs=1e-4)}
-F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 4), ("16k_s", 2), ("16k_m", 1), ("48k_t", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
-BF16_VARIANTS = [("16k_b", 2), ("16k_m", 1), ("48k_l", 1)]
-SPLIT_VARIANTS = [("16k_t", 2), ("16k_b", 2), ("16k_b", 1), ("48k_b", 1)]
+F16_VARIANTS = [("16k_t", 4), ("16k_b", 2), ("16k_b", 4), ("16k_s", 2), ("16k_m", 1), ("16k_m", 2), ("48k_t", 2), ("48k_s", 2), ("48k_l", 1)]    # a sample of the fp16 conv-section variants
+BF16_VARIANTS = [("16k_b", 2), ("16k_s", 2), ("16k_m", 1), ("16k_m", 2), ("48k_l", 1)]
+TF32_EXTRA = [("16k_s", 2), ("48k_b", 2)]           # two-stream variants that exist in the tensor-core families only
+SPLIT_VARIANTS = [("16k_t", 2), ("16k_b", 2), ("16k_b", 1), ("48k_b", 1), ("48k_b", 2)]
 
 
 @pytest.mark.parametrize("name,S,tc", [(n, s, t) for n, s in VARIANTS for t in (False, True)] + [(n, s, 2) for n, s in F16_VARIANTS] +
-                         [(n, s, 3) for n, s in BF16_VARIANTS] + [(n, s, 4) for n, s in SPLIT_VARIANTS])
+                         [(n, s, 3) for n, s in BF16_VARIANTS] + [(n, s, 4) for n, s in SPLIT_VARIANTS] + [(n, s, True) for n, s in TF32_EXTRA])
 def test_streaming_and_state_round_trip(name, S, tc, canonical):
     cfg = PRESETS[name]
     canon = canonical(name)
