@@ -239,6 +239,7 @@ struct fe_engine {
     int forced_s = 0;
     int tc = 1;                          // kernel family (Plan::PREC): 0 fp32 FMA pipe, 1 TF32, 2 fp16, 3 bf16 conv section, 4 split fp16 (fp32-accurate)
     long long* prof = nullptr;           // optional per-phase cycle counters (device)
+    int hop_slicing = 1;                 // multi-round streaming launches are cut into hop ranges on a persistent grid (FE_HOP_SLICING=0: off)
     int hop_tma = 1;                     // hop tiles by TMA where the variant supports it (FE_HOP_TMA=0 in the environment: plain loads / stores)
     std::atomic<long long> launches{0};
     std::mutex mu;
@@ -258,6 +259,8 @@ struct fe_state {
     float* scratch = nullptr;   // spill scratch for the largest grid (S = 1)
     size_t scratch_floats = 0;
     CUtensorMap* tmaps = nullptr;   // device copy of the two hop-tile tensor maps of the launch in flight (fe_stream)
+    int* flags = nullptr;           // item-done flags of a hop-sliced launch (zeroed in stream order before it)
+    size_t flags_n = 0;
     // pipelined host path (fe_stream_host): staging buffers, streams and events of THIS state, created by fe_state_reserve_host
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
     float* h_in[2] = {nullptr, nullptr}; float* h_out[2] = {nullptr, nullptr}; size_t h_floats = 0;
@@ -330,7 +333,37 @@ bool hop_tensor_map(CUtensorMap* tm, const float* base, long long ld, long long 
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st, CUtensorMap* tmaps_device = nullptr) {
+// Hop-sliced streaming launches (fe_kernel.cuh::Frame::run): with more stream groups than SMs the last round of CTAs leaves SMs idle
+// (256 groups on 148 SMs: 2 rounds for 1.73 rounds of work).  Cutting the launch into R hop ranges and dealing the items (range, group)
+// round-robin to one persistent CTA per SM evens it out.  Returns the hops per range that minimises the simulated makespan (items wait
+// for the previous range of their streams), or 0 when slicing gains less than 4 %.
+int plan_slices(int ngrp, int n_hops, int num_sms) {
+    if (ngrp <= num_sms || n_hops < 8) return 0;
+    const double base = (double)((ngrp + num_sms - 1) / num_sms);
+    double best = base * 0.96;
+    int best_hops = 0;
+    std::vector<double> fin;
+    for (int R = 2; R <= 8; ++R) {
+        const int hops = (n_hops + R - 1) / R;
+        if (hops < 4) break;
+        const int nr = (n_hops + hops - 1) / hops, total = ngrp * nr, G = std::min(num_sms, total);
+        fin.assign(total, 0.0);
+        std::vector<double> cta(G, 0.0);
+        double span = 0.0;
+        for (int i = 0; i < total; ++i) {
+            const int r = i / ngrp, h0 = r * hops, len = std::min(hops, n_hops - h0);
+            double start = cta[i % G];
+            if (r > 0) start = std::max(start, fin[i - ngrp]);
+            fin[i] = start + (double)len / n_hops + 0.003;        // + state hand-over and pipeline refill of an item
+            cta[i % G] = fin[i];
+            span = std::max(span, fin[i]);
+        }
+        if (span < best) { best = span; best_hops = hops; }
+    }
+    return best_hops;
+}
+
+int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st, CUtensorMap* tmaps_device = nullptr, fe_state* sliced = nullptr) {
     if (prm.n_streams <= 0 || prm.n_hops <= 0) return FE_OK;
     const int vi = pick_variant(e, prm.n_streams);
     int rc = ensure_variant(e, vi);
@@ -340,7 +373,24 @@ int launch(fe_engine* e, fe::KParams prm, float* scratch, cudaStream_t st, CUten
     prm.scratch = scratch;
     prm.compression = e->cfg.compression;
     prm.prof = e->prof;
-    const int grid = (prm.n_streams + v.ops.S - 1) / v.ops.S;
+    int grid = (prm.n_streams + v.ops.S - 1) / v.ops.S;
+    prm.slice_hops = 0;
+    prm.slice_flags = nullptr;
+    if (sliced && prm.mode == fe::MODE_STREAM && !prm.dbg && e->hop_slicing && !v.ops.hop_ring) {      // (compiled into the variants without hop-tiled rings)
+        const int hops = plan_slices(grid, prm.n_hops, e->num_sms);
+        if (hops > 0) {
+            const size_t items = (size_t)grid * ((prm.n_hops + hops - 1) / hops);
+            if (sliced->flags_n < items) {
+                if (sliced->flags) { FE_CUDA(cudaStreamSynchronize(st)); FE_CUDA(cudaFree(sliced->flags)); sliced->flags = nullptr; sliced->flags_n = 0; }
+                FE_CUDA(cudaMalloc(&sliced->flags, items * sizeof(int)));
+                sliced->flags_n = items;
+            }
+            FE_CUDA(cudaMemsetAsync(sliced->flags, 0, items * sizeof(int), st));
+            prm.slice_hops = hops;
+            prm.slice_flags = sliced->flags;
+            grid = (int)std::min<size_t>((size_t)e->num_sms, items);
+        }
+    }
     // streaming launches of the variants whose rings are hop-tiled: the input hop arrives and the output hop leaves as 2-D TMA tiles
     // [S streams][hop tile] (cp.async.bulk.tensor); plain loads / stores when the caller's arrays are not 16-byte aligned / pitched
     // (single-hop launches keep the plain path: nothing to prefetch, and the descriptors would cost an upload per hop)
@@ -520,6 +570,7 @@ FE_API int fe_create(const fe_config* cfg, const float* canonical, size_t n_floa
     }
     if (const char* env = std::getenv("FE_STREAMS_PER_CTA")) e->forced_s = std::atoi(env);
     if (const char* env = std::getenv("FE_HOP_TMA")) e->hop_tma = std::atoi(env);
+    if (const char* env = std::getenv("FE_HOP_SLICING")) e->hop_slicing = std::atoi(env);
     if (const char* env = std::getenv("FE_OFFLINE_MODE")) e->offline_mode = std::max(0, std::min(2, std::atoi(env)));
     // Default arithmetic = results identical to the fp32 reference: the fp32-accurate tensor-core family where the model has one
     // (split-fp16 operands, three MMAs per product), else the fp32 FMA pipe.  The faster reduced-precision families are opt-in.
@@ -610,6 +661,7 @@ FE_API void fe_state_destroy(fe_state* s) {
     if (s->data && s->owns_data) cudaFree(s->data);
     if (s->scratch) cudaFree(s->scratch);
     if (s->tmaps) cudaFree(s->tmaps);
+    if (s->flags) cudaFree(s->flags);
     for (int i = 0; i < 2; ++i) {
         if (s->h_in[i]) cudaFree(s->h_in[i]);
         if (s->h_out[i]) cudaFree(s->h_out[i]);
@@ -657,7 +709,7 @@ FE_API int fe_stream_taps(fe_engine* e, fe_state* s, const float* wav_in, float*
     prm.state = s->data; prm.in = wav_in; prm.out = wav_out; prm.ld_in = ld_in; prm.ld_out = ld_out;
     prm.n_streams = s->n_streams; prm.n_hops = n_hops; prm.mode = fe::MODE_STREAM;
     prm.dbg = taps_device; prm.dbg_hop = tap_hop;
-    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream, s->tmaps);
+    return launch(e, prm, s->scratch, (cudaStream_t)cuda_stream, s->tmaps, s);
 }
 
 FE_API int fe_stream(fe_engine* e, fe_state* s, const float* wav_in, float* wav_out, int n_hops, long long ld_in,
@@ -869,6 +921,11 @@ FE_API int fe_stft_gemm(fe_engine* e, const float* wav, int B, long long ld, int
     return FE_OK;
 }
 
+FE_API int fe_set_hop_slicing(fe_engine* e, int on) {
+    if (!e) return fail(FE_ERR_ARG, "fe_set_hop_slicing: null engine");
+    e->hop_slicing = on ? 1 : 0;
+    return FE_OK;
+}
 FE_API int fe_set_offline_mode(fe_engine* e, int mode) {
     if (!e || mode < 0 || mode > 2) return fail(FE_ERR_ARG, "fe_set_offline_mode: mode must be 0 (automatic), 1 (sequential walk) or 2 (frame-parallel)");
     e->offline_mode = mode;

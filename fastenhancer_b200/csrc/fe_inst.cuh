@@ -89,6 +89,27 @@ template <int NT> __device__ __forceinline__ void bar_consumers() { asm volatile
 template <class P> struct GpuCtx {
     float* sm; const float* blob; KParams prm; int s0; float* gs; int cta, ncta;
     int tid; unsigned seq_base; uint32_t bars;     // bars: full[STAGES] then empty[STAGES], 8 bytes each
+    int h0, h1;             // hop range of the piece of work in progress (one item of a hop-sliced launch; Plan::SLICED variants only)
+    __device__ __forceinline__ int hbeg() const { return P::SLICED ? h0 : 0; }
+    __device__ __forceinline__ int hend() const { return P::SLICED ? h1 : prm.n_hops; }
+    __device__ __forceinline__ void begin_range(int a, int b) { if constexpr (P::SLICED) { h0 = a; h1 = b; } }
+    // hop-sliced launches: item `idx` (an earlier hop range of the same streams, possibly run by another CTA) has stored its state
+    __device__ __forceinline__ void wait_item(int idx) const {
+        if (tid == 0) {
+            const long long t0 = clock64();
+            int v = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prm.slice_flags + idx) : "memory");
+                if (v == 0 && clock64() - t0 > 20000000000LL) __trap();          // bounded: a scheduling bug is an error, not a hang
+            } while (v == 0);
+        }
+        bar_consumers<P::NT>();
+    }
+    __device__ __forceinline__ void signal_item(int idx) const {
+        __threadfence();
+        bar_consumers<P::NT>();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prm.slice_flags + idx), "r"(1) : "memory");
+    }
     int ci0, nci;           // weight chunks of one iteration: [ci0, ci0 + nci) (the whole frame, or one stage of the frame-parallel schedule)
     // ---- hop tiles by TMA (HOP_RING variants, prm.hop_tma): hop_full mbarrier behind the accumulator barrier ----
     // the thread that issues the hop tiles: first lane of the LAST consumer warp (warp 0 issues the MMAs and is the critical one)
@@ -354,6 +375,14 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
                 iters = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
                 c0 = Frame<P>::tp_ci0(prm); c1 = Frame<P>::tp_ci1(prm);
             }
+            if (P::SLICED && prm.slice_hops > 0 && prm.mode == MODE_STREAM) {      // hop-sliced launch: the hops of this CTA's items (Frame::run)
+                const int ngrp = (prm.n_streams + P::S - 1) / P::S, nrange = (prm.n_hops + prm.slice_hops - 1) / prm.slice_hops;
+                iters = 0;
+                for (int item = blockIdx.x; item < ngrp * nrange; item += gridDim.x) {
+                    const int h0 = (item / ngrp) * prm.slice_hops;
+                    iters += (h0 + prm.slice_hops < prm.n_hops ? h0 + prm.slice_hops : prm.n_hops) - h0;
+                }
+            }
             for (int hop = 0; hop < iters; ++hop) {
                 for (int ci = c0; ci < c1; ++ci, ++seq) {
                     const unsigned stage = seq % P::STAGES, use = seq / P::STAGES;
@@ -372,6 +401,7 @@ __global__ void __launch_bounds__(P::NTHREADS, 1) fe_fused_kernel(const KParams 
     if constexpr (!P::TC) { x.ci0 = Frame<P>::tp_ci0(prm); x.nci = Frame<P>::tp_ci1(prm) - x.ci0; }
     x.gs = prm.scratch + (size_t)blockIdx.x * P::GS_TOTAL;
     x.tid = threadIdx.x; x.seq_base = 0; x.bars = bars; x.t_last = clock64(); x.cur_phase = 0;
+    x.h0 = 0; x.h1 = prm.n_hops;
     x.tmem = 0; x.acc_bar = bars + 8u * (2 * P::STAGES); x.acc_uses = 0;
     if constexpr (P::TC) x.tmem = *tmem_slot;
     Frame<P>::run(x);

@@ -40,6 +40,8 @@ inline f2 ld2(const float* p) { f2 v; std::memcpy(&v, p, 8); return v; }
 inline void st4(float* p, f4 v) { std::memcpy(p, &v, 16); }
 inline void st2(float* p, f2 v) { std::memcpy(p, &v, 8); }
 inline float ldg(const float* p) { return *p; }
+inline float ld_state(const float* p) { return *p; }
+inline f4 ld_state4(const float* p) { return ld4(p); }
 inline f2 ldg2(const float* p) { return ld2(p); }
 inline f4 ldg4(const float* p) { return ld4(p); }
 inline float fe_exp(float x) { return expf(x); }
@@ -65,6 +67,10 @@ FE_DEV f2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 FE_DEV void st4(float* p, f4 v) { *reinterpret_cast<float4*>(p) = v; }
 FE_DEV void st2(float* p, f2 v) { *reinterpret_cast<float2*>(p) = v; }
 FE_DEV float ldg(const float* p) { return __ldg(p); }
+// recurrent / overlap state at the start of a piece of work: it may have been written by ANOTHER CTA earlier in the same launch
+// (hop-sliced launches), so these loads bypass L1 and never use the non-coherent path
+FE_DEV float ld_state(const float* p) { return __ldcg(p); }
+FE_DEV float4 ld_state4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 FE_DEV f2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 FE_DEV f4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 FE_DEV float fe_exp(float x) { return __expf(x); }
@@ -928,7 +934,33 @@ template <class P> struct Frame {
         return next < C::K ? TP_CI_BLK0 + next * P::BLK_CHUNKS + P::Gru::NCHUNK : P::NCHUNK_FRAME;
     }
 
+    // Hop-sliced streaming launches (KParams::slice_hops > 0): the launch is cut into items (hop range r, stream group g), range-major,
+    // dealt round-robin to a persistent grid; an item starts when the previous range of its streams has been stored (a flag per item,
+    // release / acquire at GPU scope).  With more stream groups than SMs this evens out the last wave: 256 groups on 148 SMs take
+    // 1.77 instead of 2 rounds with four ranges.  (A launch with at most one group per SM gains nothing: its chains are the critical path.)
+    // Compiled into the variants without hop-tiled rings (Plan::SLICED: M / L, the configs that run one or two streams per CTA and so
+    // have the most groups); the others keep the hop range of a launch a compile-time fact.
     template <class X> FE_DEV static void run(X& x) {
+        const KParams& prm = x.prm;
+        if (P::SLICED && prm.slice_hops > 0 && prm.mode == MODE_STREAM) {
+            const int ngrp = (prm.n_streams + S - 1) / S, nrange = (prm.n_hops + prm.slice_hops - 1) / prm.slice_hops;
+            for (int item = x.cta; item < ngrp * nrange; item += x.ncta) {
+                const int r = item / ngrp, g = item % ngrp;
+                x.s0 = g * S;
+                x.gs = prm.scratch + (size_t)g * P::GS_TOTAL;
+                const int h0 = r * prm.slice_hops, h1 = h0 + prm.slice_hops < prm.n_hops ? h0 + prm.slice_hops : prm.n_hops;
+                if (r > 0) x.wait_item(item - ngrp);
+                x.begin_range(h0, h1);
+                run_range(x);
+                x.signal_item(item);
+            }
+            return;
+        }
+        x.begin_range(0, prm.n_hops);
+        run_range(x);
+    }
+    // hops x.hbeg() .. x.hend() - 1 of the streams x.s0 .. x.s0 + S - 1
+    template <class X> FE_DEV static void run_range(X& x) {
         const KParams& prm = x.prm;
         float* sm = x.sm;
         // ---- one-time init: zero the activation area, load overlap state ----
@@ -955,10 +987,10 @@ template <class P> struct Frame {
                     int gs = x.s0 + s;
                     float a = 0.f, b = 0.f;
                     if (gs < prm.n_streams) {
-                        a = prm.state[st_cache(prm, 0, gs) + i]; b = prm.state[st_cache(prm, 1, gs) + i];
+                        a = ld_state(prm.state + st_cache(prm, 0, gs) + i); b = ld_state(prm.state + st_cache(prm, 1, gs) + i);
                     }
-                    sm[P::SM_TIN + P::ring_off(s, (H + i) & NMASK)] = a;
-                    sm[P::SM_OLA + P::ring_off(s, i)] = b;
+                    sm[P::SM_TIN + P::ring_off(s, (x.hbeg() * H + H + i) & NMASK)] = a;
+                    sm[P::SM_OLA + P::ring_off(s, (x.hbeg() * H + i) & NMASK)] = b;
                 }
             });
         }
@@ -975,7 +1007,7 @@ template <class P> struct Frame {
                         for (int k = 0; k < C::K; ++k) {
                             float v[4] = {0.f, 0.f, 0.f, 0.f};
                             if (live && 4 * g < C2) {
-                                const f4 t = ldg4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * g);
+                                const f4 t = ld_state4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * g);
                                 v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                             }
                             x.tmem_st4(tid, P::TM_H + k * P::C2P + 4 * g, v);
@@ -1014,14 +1046,14 @@ template <class P> struct Frame {
                     const int s = idx / (C::K * P::C2P * F2), r = idx % (C::K * P::C2P * F2);
                     const int k = r / (P::C2P * F2), c = (r / F2) % P::C2P, f = r % F2, gs = x.s0 + s;
                     float v = 0.f;
-                    if (c < C2 && gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
+                    if (c < C2 && gs < prm.n_streams) v = ld_state(prm.state + st_h(prm, k, gs) + f * C2 + c);
                     sm[P::SM_HST + k * P::XTS + rf_off(c, s, f)] = v;
                 }
             });
         }
         const bool hop_tma = P::HOP_RING && prm.hop_tma;          // streaming launches: hop tiles move by TMA
-        if (hop_tma) x.hop_prefetch(0);                           // the rings are initialised: the tile of hop 0 may land
-        for (int hop = 0; hop < prm.n_hops; ++hop) {
+        if (hop_tma) x.hop_prefetch(x.hbeg());                        // the rings are initialised: the tile of the first hop may land
+        for (int hop = x.hbeg(); hop < x.hend(); ++hop) {
             frame(x, hop);
             x.next_frame();
         }
@@ -1054,7 +1086,7 @@ template <class P> struct Frame {
             });
         }
         if (prm.mode == MODE_STREAM || prm.mode >= MODE_STFT) {
-            const int n = prm.n_hops;
+            const int n = x.hend();
             x.phase(PH_STATE, [&](int tid) {
                 for (int idx = tid; idx < S * C::CL; idx += NT) {
                     int s = idx / C::CL, i = idx % C::CL;
@@ -1254,7 +1286,7 @@ template <class P> struct Frame {
                         const int s = idx / (NC4 * F2), r = idx % (NC4 * F2);
                         const int f = (r % 8) + 8 * (r / (8 * NC4)), c4 = (r / 8) % NC4, gs = x.s0 + s;
                         f4 v = mk4(0.f, 0.f, 0.f, 0.f);
-                        if (4 * c4 < C2 && gs < prm.n_streams) v = ldg4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * c4);
+                        if (4 * c4 < C2 && gs < prm.n_streams) v = ld_state4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * c4);
                         st4(H + rf_off(4 * c4, s, f), v);
                     }
                 });
@@ -1876,7 +1908,7 @@ template <class P> struct Frame {
             });
             back_end(x, hop, false);
             return;
-        } else if (mode != MODE_SPEC && !(ovl && hop > 0) && tp != 2) {
+        } else if (mode != MODE_SPEC && !(ovl && hop > x.hbeg()) && tp != 2) {
             if (P::HOP_RING && mode != MODE_OFFLINE && !prm.hop_tma) x.phase(PH_LOAD, [&](int tid) { fill_hop(x, hop, tid, NT); });
             x.phase(PH_WINDOW, [&](int tid) {
                 if (P::HOP_RING && prm.hop_tma) x.hop_wait(hop);
@@ -2042,7 +2074,7 @@ template <class P> struct Frame {
                     for (int idx = tid; idx < S * C2 * F2; idx += NT) {
                         int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
                         float v = 0.f;
-                        if (!x_only && gs < prm.n_streams) v = prm.state[st_h(prm, k, gs) + f * C2 + c];
+                        if (!x_only && gs < prm.n_streams) v = ld_state(prm.state + st_h(prm, k, gs) + f * C2 + c);
                         HB[c * PR + s * F2P + f] = v;
                     }
                 });
@@ -2404,7 +2436,7 @@ template <class P> struct Frame {
             TcEpiAct epi{MASK, aux + A.convt_b, nullptr, false, false};     // the mask is not a conv input: no halo
             x.phase(PH_CONVT, [&](int tid) {
                 // overlapped schedule without TMA: the next hop's tile is filled here, a barrier ahead of the phase that windows it
-                if (P::HOP_RING && ovl && !prm.hop_tma && hop + 1 < prm.n_hops) fill_hop(x, hop + 1, tid, NT);
+                if (P::HOP_RING && ovl && !prm.hop_tma && hop + 1 < x.hend()) fill_hop(x, hop + 1, tid, NT);
                 const auto a0 = x.make_desc(W0 + S * 4, SLABF);
                 tc_layer<typename P::TConvT>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ACT1);
             });
@@ -2473,7 +2505,7 @@ template <class P> struct Frame {
         if (ovl) {
             // back end of this hop on threads 0 .. NT/2 - 1, front end of the next hop (if any) on the others, stage by stage
             constexpr int NH = NT / 2;
-            const bool next = hop + 1 < prm.n_hops;
+            const bool next = hop + 1 < x.hend();
             const float* tw = aux + A.tw;
             float* F0 = sm + P::SM_FF;
             float* F1 = F0 + S * N;

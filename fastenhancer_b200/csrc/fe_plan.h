@@ -404,6 +404,7 @@ struct Plan {
 #define FE_HOP_RING 1
 #endif
     static constexpr bool HOP_RING = TC && FE_HOP_RING && C::N_FFT % C::HOP == 0;
+    static constexpr bool SLICED = !HOP_RING;          // hop-sliced streaming launches (fe_kernel.cuh::Frame::run) are compiled in
     static constexpr int HT = C::HOP > 256 ? 256 : C::HOP;
     static_assert(!HOP_RING || (C::HOP % HT == 0 && (HT * 4) % 16 == 0), "hop tile");
     static constexpr int SM_TIN = round_up(SM_SPEC + SPECF, 32);      // 128-byte aligned (TMA destination)
@@ -558,6 +559,9 @@ struct KParams {
     int hop_tma;              // streaming launches of HOP_RING variants: the input hop arrives / the output hop leaves as 2-D TMA tiles
     const void* tmaps;        // ... described by two CUtensorMap (input, output) in global memory (device; 64-byte aligned)
     float compression;
+    // ---- hop-sliced streaming launches: items (hop range, stream group) on a persistent grid (fe_kernel.cuh::run) ----
+    int slice_hops;           // hops per range; 0 = one CTA per stream group walks all hops
+    int* slice_flags;         // [ranges][groups] item-done flags (zeroed before the launch)
     // ---- frame-parallel offline schedule (MODE_OFFLINE, fp32 family; fe_api.cu::offline_tp): the CTAs take groups of S FRAMES (slot =
     //      frame q = group * S + s of the n_streams * n_hops frames; utterance q / n_hops, frame q % n_hops) instead of S streams ----
     int tp_stage;             // 0 = off; 1 = stage A: front end, encoder, rf_pre, input half of GRU 0; 2 = stage B of block tp_blk: rnn_fc,

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
     "fe_state_create_on", "fe_state_planes", "fe_microbench_fma", "fe_fold_device", "fe_create_from_device",
-    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode", "fe_stft_gemm",
+    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode", "fe_stft_gemm", "fe_set_hop_slicing",
 )
 
 #: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
@@ -99,6 +99,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_set_precision.argtypes = [vp, ip]
     lib.fe_get_precision.argtypes = [vp]
     lib.fe_set_offline_mode.argtypes = [vp, ip]
+    lib.fe_set_hop_slicing.argtypes = [vp, ip]
     lib.fe_stft_gemm.argtypes = [vp, fp, ip, ll, ip, fp, ip, vp]
     _lib = lib
     return lib
@@ -273,6 +274,10 @@ class Engine:
         if precision not in PRECISION_MODES:
             raise ValueError(f"precision must be one of {sorted(PRECISION_MODES)}")
         _check(self._lib.fe_set_precision(self._h, PRECISION_MODES[precision]), "fe_set_precision")
+
+    def set_hop_slicing(self, on: bool) -> None:
+        """Multi-round streaming launches cut into hop ranges on a persistent grid (default on; results are bit-identical)."""
+        _check(self._lib.fe_set_hop_slicing(self._h, 1 if on else 0), "fe_set_hop_slicing")
 
     def set_offline_mode(self, mode: str) -> None:
         """Schedule of ``offline`` (``Model.forward``): 'auto', 'walk' (one CTA per group of utterances steps through the frames) or

@@ -165,6 +165,12 @@ int fe_set_precision(fe_engine* e, int mode);
 int fe_get_precision(fe_engine* e);               /* 0 TF32, 1 fp32 FMA pipe, 2 fp16, 3 bf16 conv section, 4 fp32x3 */
 
 /* Introspection used by the host wrapper, tests and bench. */
+/* Hop-sliced streaming launches (default on): when fe_stream has more stream groups than the GPU has SMs, the launch is cut into
+ * hop ranges and the items (range, stream group) run on one persistent CTA per SM, the state of a group handed from range to range
+ * through global memory -- the last round of CTAs no longer leaves SMs idle (256 groups on 148 SMs: 1.77 instead of 2 rounds).
+ * Available in the kernel variants without hop-tiled rings (M / L: the configs with one or two streams per CTA).
+ * Results are bit-identical to the unsliced launch. */
+int fe_set_hop_slicing(fe_engine* e, int on);
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
 int fe_set_streams_per_cta(fe_engine* e, int s);                /* force a variant (0 = automatic) */
 long long fe_kernel_launches(fe_engine* e);                     /* fused-kernel launches issued so far */

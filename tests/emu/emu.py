@@ -40,7 +40,7 @@ def _load():
         _lib = ctypes.CDLL(build())
         fp = ctypes.POINTER(ctypes.c_float)
         _lib.fee_run.argtypes = [ctypes.c_int] * 10 + [fp, ctypes.c_int, fp, fp, fp, fp] + [ctypes.c_int] * 3 + \
-            [ctypes.c_longlong] * 2 + [fp, ctypes.c_int, ctypes.c_float]
+            [ctypes.c_longlong] * 2 + [fp, ctypes.c_int, ctypes.c_float, ctypes.c_int]
         _lib.fee_tap_total.argtypes = [ctypes.c_int] * 8
         _lib.fee_offline_tp.argtypes = [ctypes.c_int] * 9 + [fp, fp, fp, fp] + [ctypes.c_int] * 3 + [ctypes.c_float]
     return _lib
@@ -75,10 +75,10 @@ def to_canonical(cfg, planes):
 
 
 def run(cfg, S, canonical, mode, state_native, inp, out, spec_out=None, n_streams=1, n_hops=1, L=0, ld_in=0, ld_out=0,
-        dbg=None, dbg_hop=-1, tc=False):
+        dbg=None, dbg_hop=-1, tc=False, slice_hops=0):
     lib = _load()
     rc = lib.fee_run(*_shape(cfg), S, int(tc), _p(np.ascontiguousarray(canonical, np.float32)), mode, _p(state_native), _p(inp), _p(out),
-                     _p(spec_out), n_streams, n_hops, L, ld_in, ld_out, _p(dbg), dbg_hop, cfg.input_compression)
+                     _p(spec_out), n_streams, n_hops, L, ld_in, ld_out, _p(dbg), dbg_hop, cfg.input_compression, slice_hops)
     if rc != 0:
         raise RuntimeError(f"fee_run failed rc={rc}")
 

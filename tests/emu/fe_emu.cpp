@@ -20,6 +20,12 @@ namespace fe {
 template <class P> struct EmuCtx {
     float* sm; const float* blob; KParams prm; int s0; float* gs; int cta, ncta = 1;
     long frames_done = 0;
+    int h0 = 0, h1 = 0;
+    int hbeg() const { return P::SLICED ? h0 : 0; }
+    int hend() const { return P::SLICED ? h1 : prm.n_hops; }
+    void begin_range(int a, int b) { h0 = a; h1 = b; hops_loaded = a; }
+    void wait_item(int) const {}        // hop-sliced launches: the emulation runs the items in order on one CTA
+    void signal_item(int) const {}
     const int* table;
     const float* acquire(int ci, int expect_floats) const {
         if (ci < 0 || ci >= P::NCHUNK_FRAME) throw std::runtime_error("emu: chunk index out of range");
@@ -155,7 +161,8 @@ template <class P> int run_variant(const float* canonical, KParams prm) {
     std::vector<float> blob = pack_blob<P>(canonical);
     constexpr auto A = P::make_aux();
     int grid = (prm.n_streams + P::S - 1) / P::S;
-    std::vector<float> sm(P::SM_TOTAL), gs((size_t)P::GS_TOTAL);
+    std::vector<float> sm(P::SM_TOTAL), gs((size_t)P::GS_TOTAL * (P::SLICED && prm.slice_hops > 0 ? grid : 1));
+    if (P::SLICED && prm.slice_hops > 0) { prm.scratch = gs.data(); grid = 1; }        // one emulated CTA takes every item, in order
     for (int cta = 0; cta < grid; ++cta) {
         // poison shared memory so that reads of never-written locations show up
         for (auto& v : sm) v = std::nanf("");
@@ -296,13 +303,13 @@ FE_GROUPS(X)
 extern "C" int fee_run(int n_fft, int hop, int c1, int n_enc, int c2, int f2, int n_blocks, int n_heads, int S, int tc,
                        const float* canonical, int mode, float* state, const float* in, float* out, float* spec_out,
                        int n_streams, int n_hops, int L, long long ld_in, long long ld_out, float* dbg, int dbg_hop,
-                       float compression)
+                       float compression, int slice_hops)
 {
     fe::ShapeKey key{n_fft, hop, c1, n_enc, c2, f2, n_blocks, n_heads};
     fe::KParams prm{};
     prm.state = state; prm.in = in; prm.out = out; prm.spec_out = spec_out; prm.dbg = dbg;
     prm.ld_in = ld_in; prm.ld_out = ld_out; prm.n_streams = n_streams; prm.n_hops = n_hops; prm.mode = mode; prm.L = L;
-    prm.dbg_hop = dbg_hop; prm.compression = compression;
+    prm.dbg_hop = dbg_hop; prm.compression = compression; prm.slice_hops = slice_hops;
     try {
 #define X(g) { const int rc = fee_run_g##g(&key, S, tc, canonical, &prm); if (rc != -1) return rc; }
         FE_GROUPS(X)

@@ -101,6 +101,25 @@ def test_every_variant_matches_oracle(name, canonical, engines, precision):
         eng.set_streams_per_cta(0)
 
 
+@pytest.mark.parametrize("name,B,nh", [("16k_m", 330, 16), ("16k_l", 200, 9), ("48k_m", 170, 10), ("48k_l", 160, 8), ("16k_b", 640, 24)])
+def test_hop_sliced_launch_is_bit_identical(name, B, nh, engines, precision):
+    """More stream groups than SMs: fe_stream cuts the launch into hop ranges on a persistent grid (items wait for the previous range
+    of their streams; state through global memory).  Output and final state must equal the unsliced launch bit for bit."""
+    cfg, eng = PRESETS[name], engines(name)
+    H = cfg.hop_size
+    x = torch.from_numpy(synthetic_noisy(B, nh * H, cfg.sample_rate)).cuda()
+    out = []
+    try:
+        for on in (False, True):
+            eng.set_hop_slicing(on)
+            st = eng.new_state(B)
+            y = torch.cat([eng.stream(st, x[:, :(nh - 3) * H].contiguous()), eng.stream(st, x[:, (nh - 3) * H:].contiguous())], dim=1)
+            out.append((y, st.export()))
+    finally:
+        eng.set_hop_slicing(True)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("name", ["16k_t", "16k_b", "16k_m", "48k_l"])
 def test_hop_by_hop_equals_one_launch_bit_exact(name, engines):
     """1 launch of n hops == n launches of 1 hop: the state round trip through HBM loses nothing."""
