@@ -494,6 +494,9 @@ FE_DEV void tc_stream(X& x, int tid, int ci0, Issue issue) {
     x.sub_end(tid, PH_TC_MMA);
 }
 
+#ifndef FE_SKIP_IDLE_WARPS
+#define FE_SKIP_IDLE_WARPS 1
+#endif
 // every consumer thread owns accumulator row m (TMEM lane) and half of the NG channel groups
 // ALLROWS: epi(gp, g, v, valid) runs for every lane, rows past the last position included (valid = false): needed when the
 // epilogue contains warp-collective tcgen05.st, which all 32 lanes must execute.
@@ -506,6 +509,10 @@ FE_DEV void tc_epilogue(X& x, int tid, Epi epi) {
     const int half = (tid >> 7) & 1, m = (((tid >> 5) & 3) << 5) + (tid & 31);
 #pragma unroll
     for (int mt = 0; mt < L::NMT; ++mt) {
+        // a warp whose 32 accumulator rows all lie past the last position has nothing to do (warp-uniform, so the collective TMEM
+        // accesses of the epilogue stay converged): the RNNFormer tiles carry 16 .. 96 live rows of 128, and their epilogues are
+        // throughput-bound (MUFU / ALU), so the idle warps' garbage work was stealing issue slots from the live ones
+        if (FE_SKIP_IDLE_WARPS && mt * 128 + (((tid >> 5) & 3) << 5) >= L::NPOS) continue;
         float v[GH][4];
 #pragma unroll
         for (int i = 0; i < GH; ++i) {
@@ -1372,6 +1379,7 @@ template <class P> struct Frame {
                     constexpr int GH = (NGX + 1) / 2, GB = 3;
                     constexpr bool EVEN = (NGX % 2 == 0);
                     const int half = (tid >> 7) & 1;
+                    if (!FE_SKIP_IDLE_WARPS || (((tid >> 5) & 3) << 5) < P::RSLOTS)           // (warps whose rows all lie past the last position: see tc_epilogue)
 #pragma unroll
                     for (int i0 = 0; i0 < GH; i0 += GB) {
                         float vr[GB][4], vz[GB][4], vx[GB][4], vh[GB][4], vo[GB][4];
