@@ -104,6 +104,14 @@ def host_info():
 def workload_config(args, cfg, n_hops, world):
     """the `config` object: identical in both arms (the reference arm runs a bounded SAMPLE of it, described under `sample`)."""
     size = args.preset.split("_")[1].upper()
+    if args.config == 1:       # BASELINE config 1: offline Model.forward on whole utterances (n_hops = frames of one utterance, 1 + L // hop)
+        L = int(args.seconds * cfg.sample_rate)
+        return {"workload": f"FastEnhancer_{size} {cfg.sample_rate // 1000} kHz offline Model.forward(noisy [{args.streams}, {L}]) -> wav, "
+                            f"{n_hops} frames per utterance, fp32 audio in/out, random-init weights",
+                "baseline_config": args.config, "baseline_config_text": CONFIGS[args.config][3], "preset": args.preset,
+                "streams_per_gpu": args.streams, "streams_total": args.streams * world, "hops_per_step": n_hops,
+                "frames_per_step": args.streams * world * n_hops, "parallelism": f"utterances sharded x{world}, no data-path collective",
+                "l2": "L2 flushed between steps (a 256 MB buffer is written): the utterance itself is 0.6 MB"}
     return {"workload": f"FastEnhancer_{size} {cfg.sample_rate // 1000} kHz streaming wav2wav, {args.streams} streams/GPU x {args.seconds:g} s "
                         f"({n_hops} hops of {cfg.hop_size}), fp32 audio in/out, random-init folded weights",
             "baseline_config": args.config, "baseline_config_text": CONFIGS[args.config][3], "preset": args.preset,
@@ -230,6 +238,44 @@ def reference_cpu_rate(ref, cfg, n_streams, hops, threads):
     return n_streams * hops / dt, dt
 
 
+def run_reference_offline(args, cfg, threads):
+    """BASELINE config 1 on the reference: its own Model.forward (models/fastenhancer/default/model.py:711-735, unmodified sources,
+    PyTorch CPU, all threads) on the same [B, 10 s] batch of utterances."""
+    import torch
+    ref = ReferenceTorch(cfg)
+    B, L, H = args.streams * max(1, args.gpus), int(args.seconds * cfg.sample_rate), cfg.hop_size
+    wav = torch.from_numpy(synthetic_noisy(B, L, cfg.sample_rate))
+    T = 1 + L // H
+    times, extras = [], {}
+    with torch.no_grad():
+        torch.set_num_threads(threads)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            ref.offline(wav)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        torch.set_num_threads(1)
+        ref.offline(wav)
+        t0 = time.perf_counter()
+        ref.offline(wav)
+        dt1 = time.perf_counter() - t0
+        extras["offline_1thread"] = {"ms": dt1 * 1e3, "rtf": dt1 / (B * args.seconds), "frames_per_s": B * T / dt1}
+    value = float(np.mean([B * T / t for t in times]))
+    how = "the reference's own Model.forward (models/fastenhancer/default/model.py:711-735), unmodified sources, PyTorch CPU"
+    line = {
+        "impl": "reference", "metric": "frames_per_second", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": float(np.mean(times) / (B * args.seconds)),
+        "config": workload_config(args, cfg, T, max(1, args.gpus)),
+        "sample": {"hops_per_step": T, "frames_per_step": B * T, "of_hops": T, "note": "the whole workload, every step"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": f"{B} utterance(s) of {args.seconds:g} s per step; {how}"},
+        "host": host_info(), "reference_paths": extras,
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, cfg, canon, rank, world):
     """Reference arm: the reference's own implementation of the path on the host cores, all threads, bounded sample of the same workload."""
     if rank != 0:
@@ -239,6 +285,8 @@ def run_reference(args, cfg, canon, rank, world):
     n_streams = args.streams * max(1, args.gpus)          # the whole job of the N-GPU arm (weak scaling)
     _, n_hops_full = workload(cfg, args.seconds)
     extras = {}
+    if args.config == 1:
+        return run_reference_offline(args, cfg, threads)
     try:
         ref = ReferenceTorch(cfg)
         kind = "reference"
@@ -390,7 +438,7 @@ def reference_shaped_calls(args, cfg, dev, x_host, n_hops, precision):
         frames = B * (1 + L // H)
         out[f"model_forward_offline_batch{B}"] = {
             "value": frames / dt, "unit": "frames/s", "ms": dt * 1e3, "rtf": dt / (B * args.seconds), "h2d_bytes": wav_h.numel() * 4,
-            "d2h_bytes": out_h.numel() * 4, "fused_kernel_launches": launches,
+            "d2h_bytes": out_h.numel() * 4, "kernel_launches": launches,
             "schedule": "sequential walk (one CTA per group of utterances)" if launches == 1 else
                         "frame-parallel (stage A, GRU scan + stage B per block, overlap-add)",
             "api": "Model.forward(noisy [B, L]) -> wav (spec_hat stays on the device, as in scripts/test_pytorch.py:34-37)"}
@@ -492,19 +540,45 @@ def main():
     x = x_host.to(dev)                      # inputs resident in HBM before the timed region
     y = torch.empty_like(x)
     state = eng.new_state(B)
+    # BASELINE config 1 is the OFFLINE call: Model.forward on whole utterances (fe_offline; few long utterances run the frame-parallel
+    # schedule).  Its working set (0.6 MB per utterance) fits the L2, so the L2 is flushed between steps; the flush is outside the events.
+    offline = args.config == 1
+    L_off = int(args.seconds * cfg.sample_rate)
+    if offline:
+        n_hops = 1 + L_off // H                     # frames of one utterance
+        x_off = x[:, :L_off].contiguous()
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def step(engine, st):
+        if offline:
+            engine.offline(x_off, want_spec=True)
+        else:
+            engine.stream(st, x, out=y)
 
     def timed(engine, st, steps):
+        if offline:
+            total = 0.0
+            for _ in range(steps):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(engine, st)
+                e1.record()
+                e1.synchronize()
+                total += e0.elapsed_time(e1)
+            barrier()
+            return max_over_ranks(total) / steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            engine.stream(st, x, out=y)
+            step(engine, st)
         e1.record()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
 
     # ---------------- device-resident throughput (`value`) ----------------
     for _ in range(args.warmup):
-        eng.stream(state, x, out=y)
+        step(eng, state)
     barrier()
     sampler = ClockSampler(local_rank).start()
     launches0 = eng.kernel_launches
@@ -515,20 +589,40 @@ def main():
     value = frames_step / (ms_step * 1e-3)
 
     # ---------------- end to end through the C ABI's host-buffer call (`e2e`) ----------------
-    e2e_state = eng.new_state(B)
-    e2e_state.reserve_host(64)
-    for _ in range(2):
-        eng.stream_host(e2e_state, x_host, out=y_host)
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(3, args.steps // 2)
-    for _ in range(e2e_steps):
-        eng.stream_host(e2e_state, x_host, out=y_host)     # returns after the last D2H copy completed
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    barrier()
+    if offline:
+        xo_host = x_host[:, :L_off].contiguous().pin_memory()
+        yo_host = torch.empty(B, H * (L_off // H)).pin_memory()
+
+        def e2e_step():
+            wav, _spec = eng.offline(xo_host.to(dev, non_blocking=True), want_spec=True)
+            yo_host.copy_(wav, non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        barrier()
+        io_bytes, out_bytes = B * L_off * 4, B * H * (L_off // H) * 4
+        e2e_api = "Engine.offline (fe_offline) as Model.forward calls it: pinned host wav -> device, enhanced wav -> pinned host, synchronous"
+    else:
+        e2e_state = eng.new_state(B)
+        e2e_state.reserve_host(64)
+        for _ in range(2):
+            eng.stream_host(e2e_state, x_host, out=y_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.stream_host(e2e_state, x_host, out=y_host)     # returns after the last D2H copy completed
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        barrier()
+        io_bytes = out_bytes = B * n_hops * H * 4
+        e2e_api = "fe_stream_host via Engine.stream_host (pinned host buffers, copies pipelined with the kernel)"
     e2e_value = frames_step / e2e_s
-    io_bytes = B * n_hops * H * 4
 
     # ---------------- NCCL scatter / gather of a batch held on rank 0 (reported separately) ----------------
     scatter = None
@@ -562,7 +656,7 @@ def main():
                 continue              # this model has no kernels of that family
             st_o = eng_o.new_state(B)
             for _ in range(2):
-                eng_o.stream(st_o, x, out=y)
+                step(eng_o, st_o)
             barrier()
             other_ms[other] = timed(eng_o, st_o, max(3, args.steps // 3))
             del eng_o, st_o
@@ -599,9 +693,10 @@ def main():
             if precision == "fp32x3":
                 roofline["note"] = ("achieved counts ALGORITHMIC flops; the split-fp16 family executes 3 tensor-core MACs per algorithmic MAC, "
                                     "so the tensor pipe does 3x this work")
-        roofline["kernel"] = "fe_fused_kernel (one persistent launch per step)"
-        roofline["hbm"] = {"achieved_gbs": 2 * io_bytes / t_launch / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                           "frac": 2 * io_bytes / t_launch / 1e9 / peaks["hbm_gbs"]}
+        roofline["kernel"] = "fe_fused_kernel (one persistent launch per step)" if launches == args.steps else \
+            f"fe_fused_kernel stages + fe_gru_scan_kernel + fe_overlap_add_kernel ({launches // max(1, args.steps)} launches per step: frame-parallel offline schedule)"
+        roofline["hbm"] = {"achieved_gbs": (io_bytes + out_bytes) / t_launch / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                           "frac": (io_bytes + out_bytes) / t_launch / 1e9 / peaks["hbm_gbs"]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
@@ -624,12 +719,12 @@ def main():
             "metric": "frames_per_second", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE[precision], "data": "synthetic",
-            "rtf": (ms_step * 1e-3) / (n_hops * H / cfg.sample_rate),
+            "rtf": (ms_step * 1e-3) / (args.seconds if offline else n_hops * H / cfg.sample_rate),
             "config": workload_config(args, cfg, n_hops, world),
             "impl_config": {"precision": precision, "streams_per_cta": eng.streams_per_cta(B)},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
-                    "ms_per_step": e2e_s * 1e3, "api": "fe_stream_host via Engine.stream_host (pinned host buffers, copies pipelined with the kernel)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": e2e_s * 1e3, "api": e2e_api},
             "e2e_reference_shaped_calls": calls, "spec2spec_rtf": s2s, "latency_sweep": sweep, "scatter_gather": scatter,
             "variants": {precision: {"value": value, "ms_per_step": ms_step},
                          **{o: {"value": frames_step / (ms * 1e-3), "ms_per_step": ms} for o, ms in other_ms.items()},

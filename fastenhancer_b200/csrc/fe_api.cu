@@ -497,7 +497,7 @@ int offline_tp(fe_engine* e, const float* wav, int B, int L, float* wav_out, flo
     mark();
     stage(1, 0);
     for (int k = 0; k < c.n_blocks; ++k) {
-        if (rc == FE_OK && ce == cudaSuccess) rc = gru_scan(c, k, prm.tp_gx, buf + n_scr + n_gx, e->canon_dev, B, T, st);
+        if (rc == FE_OK && ce == cudaSuccess) { rc = gru_scan(c, k, prm.tp_gx, buf + n_scr + n_gx, e->canon_dev, B, T, st); e->launches.fetch_add(1, std::memory_order_relaxed); }
         mark();
         stage(2, k);
     }
@@ -506,6 +506,7 @@ int offline_tp(fe_engine* e, const float* wav, int B, int L, float* wav_out, flo
         fe_overlap_add_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(prm.tp_frames, v.blob + v.ops.aux_window_sq, wav_out, B, T,
                                                                                                 c.n_fft, c.hop);
         ce = cudaGetLastError();
+        e->launches.fetch_add(1, std::memory_order_relaxed);
     }
     cudaFreeAsync(buf, st);
     if (timing && !evs.empty()) {

@@ -173,7 +173,7 @@ int fe_get_precision(fe_engine* e);               /* 0 TF32, 1 fp32 FMA pipe, 2 
 int fe_set_hop_slicing(fe_engine* e, int on);
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
 int fe_set_streams_per_cta(fe_engine* e, int s);                /* force a variant (0 = automatic) */
-long long fe_kernel_launches(fe_engine* e);                     /* fused-kernel launches issued so far */
+long long fe_kernel_launches(fe_engine* e);                     /* kernels of this library launched so far (fused kernel, GRU scan, overlap-add) */
 int fe_tap_floats(fe_engine* e);
 /* Test hook: like fe_stream, additionally dumps the per-stage tensors of stream 0 at hop `tap_hop`
  * (layout of oracle/fe_oracle.c::core) into taps_device [fe_tap_floats]. */

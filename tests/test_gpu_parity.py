@@ -181,7 +181,7 @@ def test_offline_schedules_agree_and_match_reference_golden(name, golden, canoni
         assert rms(out[mode][0] - g["offline_wav"]) < TOL["fp32"]["wav"], mode
         sp = out[mode][1][:, :, g["offline_spec_frames"]] if "offline_spec_frames" in g.files else out[mode][1]
         assert np.abs(sp - g["offline_spec"]).max() < TOL["fp32"]["spec_abs"] * max(1.0, np.abs(g["offline_spec"]).max()), mode
-    assert out["walk"][2] == 1 and out["frame_parallel"][2] == cfg.rf_blocks + 1        # fused-kernel launches: 1 vs stage A + one stage B per block
+    assert out["walk"][2] == 1 and out["frame_parallel"][2] == 2 * cfg.rf_blocks + 2   # launches: 1 vs stage A + (scan + stage B) per block + overlap-add
     assert rms(out["walk"][0] - out["frame_parallel"][0]) < 2e-6
     assert np.abs(out["walk"][1] - out["frame_parallel"][1]).max() < 2e-5 * max(1.0, np.abs(out["walk"][1]).max())
 
@@ -203,7 +203,7 @@ def test_offline_frame_parallel_long_utterance(name, B, seconds, canonical):
     eng.set_offline_mode("auto")                                  # few utterances: automatic mode picks the same schedule
     n0 = eng.kernel_launches
     wav2, _ = eng.offline(torch.from_numpy(x).cuda())
-    assert eng.kernel_launches - n0 == cfg.rf_blocks + 1 and torch.equal(wav, wav2)
+    assert eng.kernel_launches - n0 == 2 * cfg.rf_blocks + 2 and torch.equal(wav, wav2)
 
 
 def test_offline_frame_parallel_needs_accurate_mode(canonical):
