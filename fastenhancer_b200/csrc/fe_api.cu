@@ -156,15 +156,17 @@ fe_gru_scan_kernel(const float* __restrict__ gx, float* __restrict__ hseq, const
     const int u = blockIdx.x / F2, f = blockIdx.x % F2;
     const float* g0 = gx + (((size_t)u * T) * F2 + f) * GROW;              // + t * F2 * GROW
     const size_t gstep = (size_t)F2 * GROW, hstep = (size_t)F2 * C2;
-    auto issue = [&](int t) {          // every thread commits one (possibly empty) group per call: the wait below counts groups
-        if (t < T)
-            for (int i = tid; i < GROW / 4; i += NTH)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&gbuf[t % NSTG][4 * i])),
-                             "l"(g0 + (size_t)t * gstep + 4 * i) : "memory");
+    static_assert(GROW / 4 <= NTH, "one 16-byte piece per thread and step");
+    const float* gsrc = g0 + 4 * tid;                                       // this thread's piece of a step (threads < GROW / 4)
+    const bool piece = tid < GROW / 4;
+    const uint32_t gdst = (uint32_t)__cvta_generic_to_shared(&gbuf[0][0]) + 16u * tid;
+    // every thread commits one (possibly empty) group per step: the waits below count groups
+    auto issue = [&](int t, int slot) {
+        if (piece && t < T) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(gdst + (uint32_t)(slot * GROW * 4)), "l"(gsrc + (size_t)t * gstep) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
-    for (int t = 0; t < NSTG; ++t) issue(t);
+    for (int t = 0; t < NSTG; ++t) issue(t, t);
     float wr[CQ], wz[CQ], wn[CQ];
 #pragma unroll
     for (int i = 0; i < CQ; ++i) {
@@ -178,33 +180,42 @@ fe_gru_scan_kernel(const float* __restrict__ gx, float* __restrict__ hseq, const
     for (int i = tid; i < 2 * HP; i += NTH) (&hbuf[0][0])[i] = 0.f;
     asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 1) : "memory");      // step 0 has landed
     if (NTH > 32) __syncthreads(); else __syncwarp();
-    float* h0 = hseq + (((size_t)u * T) * F2 + f) * C2 + jj;
+    float* hout = hseq + (((size_t)u * T) * F2 + f) * C2 + jj;
     float hj = 0.f;                // h[j] of this thread's channel (lanes q == 0)
-    for (int t = 0; t < T; ++t) {
-        if (t > 0) issue(t - 1 + NSTG);         // the slot of step t - 1 is free: every thread passed the barrier that ended it
-        const float* hb = hbuf[t & 1];
-        float ar0 = 0.f, az0 = 0.f, an0 = 0.f, ar1 = 0.f, az1 = 0.f, an1 = 0.f;
+    // NSTG steps per trip: the ring slot (t % NSTG) and the h buffer (t & 1) of every step are compile-time facts
+    for (int t0 = 0; t0 < T; t0 += NSTG) {
 #pragma unroll
-        for (int i = 0; i + 1 < CQ; i += 2) {
-            const float2 hv = *reinterpret_cast<const float2*>(hb + c0 + i);
-            ar0 = fmaf(wr[i], hv.x, ar0); az0 = fmaf(wz[i], hv.x, az0); an0 = fmaf(wn[i], hv.x, an0);
-            ar1 = fmaf(wr[i + 1], hv.y, ar1); az1 = fmaf(wz[i + 1], hv.y, az1); an1 = fmaf(wn[i + 1], hv.y, an1);
-        }
-        if (CQ & 1) { const float hv = hb[c0 + CQ - 1]; ar0 = fmaf(wr[CQ - 1], hv, ar0); az0 = fmaf(wz[CQ - 1], hv, az0); an0 = fmaf(wn[CQ - 1], hv, an0); }
-        float ar = ar0 + ar1, az = az0 + az1, an = an0 + an1;
+        for (int d = 0; d < NSTG; ++d) {
+            const int t = t0 + d;
+            if (t < T) {       // uniform
+                if (t > 0) issue(t - 1 + NSTG, (d + NSTG - 1) % NSTG);   // the slot of step t - 1 is free: every thread passed the barrier that ended it
+                const float* hb = hbuf[d & 1];
+                const float* gb = gbuf[d];
+                const float gr = gb[jj], gz = gb[C2 + jj], gn = gb[2 * C2 + jj];
+                float ar0 = 0.f, az0 = 0.f, an0 = 0.f, ar1 = 0.f, az1 = 0.f, an1 = 0.f;
 #pragma unroll
-        for (int o = 1; o < Q; o <<= 1) {
-            ar += __shfl_xor_sync(0xffffffffu, ar, o); az += __shfl_xor_sync(0xffffffffu, az, o); an += __shfl_xor_sync(0xffffffffu, an, o);
+                for (int i = 0; i + 1 < CQ; i += 2) {
+                    const float2 hv = *reinterpret_cast<const float2*>(hb + c0 + i);
+                    ar0 = fmaf(wr[i], hv.x, ar0); az0 = fmaf(wz[i], hv.x, az0); an0 = fmaf(wn[i], hv.x, an0);
+                    ar1 = fmaf(wr[i + 1], hv.y, ar1); az1 = fmaf(wz[i + 1], hv.y, az1); an1 = fmaf(wn[i + 1], hv.y, an1);
+                }
+                if (CQ & 1) { const float hv = hb[c0 + CQ - 1]; ar0 = fmaf(wr[CQ - 1], hv, ar0); az0 = fmaf(wz[CQ - 1], hv, az0); an0 = fmaf(wn[CQ - 1], hv, an0); }
+                float ar = ar0 + ar1, az = az0 + az1, an = an0 + an1;
+#pragma unroll
+                for (int o = 1; o < Q; o <<= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, o); az += __shfl_xor_sync(0xffffffffu, az, o); an += __shfl_xor_sync(0xffffffffu, an, o);
+                }
+                if (q == 0) {
+                    const float r = fe::sigmoid_acc(gr + br + ar), z = fe::sigmoid_acc(gz + bz + az);
+                    const float n = fe::tanh_acc(gn + bin + r * (an + bhn));
+                    hj = (1.0f - z) * n + z * hj;
+                    if (live) { hbuf[(d + 1) & 1][j] = hj; *hout = hj; }
+                }
+                hout += hstep;
+                asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");  // step t + 1 has landed (this thread's piece; the barrier publishes all)
+                if (NTH > 32) __syncthreads(); else __syncwarp();
+            }
         }
-        if (q == 0) {
-            const float* gb = gbuf[t % NSTG];
-            const float r = fe::sigmoid_acc(gb[jj] + br + ar), z = fe::sigmoid_acc(gb[C2 + jj] + bz + az);
-            const float n = fe::tanh_acc(gb[2 * C2 + jj] + bin + r * (an + bhn));
-            hj = (1.0f - z) * n + z * hj;
-            if (live) { hbuf[(t + 1) & 1][j] = hj; h0[(size_t)t * hstep] = hj; }
-        }
-        asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");  // step t + 1 has landed (this thread's pieces; the barrier publishes all)
-        if (NTH > 32) __syncthreads(); else __syncwarp();
     }
 }
 
