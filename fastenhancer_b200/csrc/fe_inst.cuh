@@ -295,6 +295,13 @@ template <class P> struct GpuCtx {
     __device__ __forceinline__ void tmem_st2_row(int /*row*/, int col, const float* v) const { tmem_st2(0, col, v); }
     // same for callers that know their row instead of their thread id (the row must be the calling thread's own lane)
     __device__ __forceinline__ void tmem_st4_row(int /*row*/, int col, const float* v) const { tmem_st4(0, col, v); }
+    // 16-byte asynchronous global -> shared copies (cp.async, L2 only: the source may have been written by another CTA of this launch),
+    // one group per prefetch; async_wait_all before the phase barrier makes this thread's pieces visible to the CTA
+    __device__ __forceinline__ void async_copy16(float* dst, const float* src) const {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ void async_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void async_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void tmem_st_wait() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ void tmem_ld_wait() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
     // end of a phase: make generic-proxy shared-memory writes visible to the async proxy (MMA operand reads) and order

@@ -597,17 +597,23 @@ FE_DEV void tc_mmas(X& x, int tid, int ci, ADesc a_desc, int tapstride, int alo 
         }
     });
 }
-template <class L, class X, class ADesc, class Epi>
-FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi, int alo = 0) {
+// `post(tid)` runs on every consumer thread between the completion of the layer's MMAs and its epilogue: the operand buffers the
+// MMAs read are free from there on, so asynchronous copies (x.async_copy16: the next decoder stage's spilled skip tensor, the next
+// block's GRU state) can land in them while the epilogue runs.  The phase must end with x.async_wait_all() before its barrier.
+struct NoHook { FE_DEV void operator()(int) const {} };
+template <class L, class X, class ADesc, class Epi, class Post = NoHook>
+FE_DEV void tc_layer(X& x, int tid, int ci, ADesc a_desc, int tapstride, Epi epi, int alo = 0, Post post = Post{}) {
     tc_mmas<L, false>(x, tid, ci, a_desc, tapstride, alo);
+    post(tid);
     tc_epilogue<L>(x, tid, epi);
 }
 template <int W> struct WTag { static constexpr int value = W; };
 // RNNFormer layer (1x1, positions = S * F2): epi(position, first channel, values[W], WTag<W>) with W = 2 (M = 64 path) or 4
 // ALLROWS: see tc_epilogue (rows past the last position reach epi with valid = false).
-template <class L, bool M64, bool ALLROWS = false, class X, class ADesc, class Epi>
-FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi, int alo = 0) {
+template <class L, bool M64, bool ALLROWS = false, class X, class ADesc, class Epi, class Post = NoHook>
+FE_DEV void rf_layer(X& x, int tid, int ci, ADesc a_desc, Epi epi, int alo = 0, Post post = Post{}) {
     tc_mmas<L, M64>(x, tid, ci, a_desc, 0, alo);
+    post(tid);
     if constexpr (M64) tc_epilogue64<L>(x, tid, [&](int p, int c, const float* v) { epi(p, c, v, true, WTag<2>{}); });
     else if constexpr (ALLROWS) tc_epilogue<L, true>(x, tid, [&](int p, int g, const float* v, bool valid) { epi(p, 4 * g, v, valid, WTag<4>{}); });
     else tc_epilogue<L>(x, tid, [&](int p, int g, const float* v) { epi(p, 4 * g, v, true, WTag<4>{}); });
@@ -1263,6 +1269,26 @@ template <class P> struct Frame {
             });
             ci += P::LinPreT::NCHUNK;
         }
+        // Configs whose GRU state is not resident on chip (M / L) stage the state of block k from global memory into the scratch buffer
+        // HB every hop.  HB aliases the attention output, which is free once the MMAs of attn_fc (block k - 1) / rf_pre (block 0) have
+        // completed: the staging runs as 16-byte asynchronous copies (cp.async: the [F2][C2] -> GeoR transposition moves whole float4s)
+        // issued at that point, under the epilogue of that layer, instead of a phase of its own (8 % of a hop of M).
+        auto prefetch_h = [&](int tid, int k) {
+            if constexpr (!P::H_RES) {
+                float* H = AB + P::O_HB_T;
+                // one float4 = 4 channels of one (stream, frequency): 8 consecutive threads take 8 frequencies of the same channel
+                // group (conflict-free 16-byte shared-memory writes), the next 8 the next group (64 contiguous bytes per row of h)
+                constexpr int NC4 = C2P / 4;
+                static_assert(F2 % 8 == 0, "per-hop state staging assumes F2 % 8 == 0");
+                for (int idx = tid; idx < S * NC4 * F2; idx += NT) {
+                    const int s = idx / (NC4 * F2), r = idx % (NC4 * F2);
+                    const int f = (r % 8) + 8 * (r / (8 * NC4)), c4 = (r / 8) % NC4, gs = x.s0 + s;
+                    if (4 * c4 < C2 && gs < prm.n_streams) x.async_copy16(H + rf_off(4 * c4, s, f), prm.state + st_h(prm, k, gs) + f * C2 + 4 * c4);
+                    else st4(H + rf_off(4 * c4, s, f), mk4(0.f, 0.f, 0.f, 0.f));
+                }
+                x.async_commit();
+            }
+        };
         // ... then the 1x1 conv C1 -> C2 (+ folded BN) on the tensor cores
         x.phase(PH_RF_PRE, [&](int tid) {
             const auto a0 = x.make_desc(Y1, RSLABF);
@@ -1274,8 +1300,9 @@ template <class P> struct Frame {
 #pragma unroll
                 for (int e = 0; e < W; ++e) o[e] = v[e] + b[e];
                 store_x(p, c, o, valid, wt, WTag<1>{});
-            }, P::Y1T1);
+            }, P::Y1T1, [&](int t) { prefetch_h(t, 0); });
             if constexpr (P::H_TMEM) x.tmem_st_wait();
+            if constexpr (!P::H_RES) x.async_wait_all();
         });
         ci += P::TRfPre::NCHUNK;
         if (dbg) dump_rf(XR, TAP_RFPRE);
@@ -1283,21 +1310,6 @@ template <class P> struct Frame {
         for (int k = 0; k < C::K; ++k) {
             const auto ab = A.blk(k);
             float* H = P::H_RES ? x.sm + P::SM_HST + k * XTS : AB + P::O_HB_T;
-            if constexpr (!P::H_RES) {
-                x.phase(PH_HLOAD, [&](int tid) {
-                    // one float4 = 4 channels of one (stream, frequency): 8 consecutive threads take 8 frequencies of the same channel
-                    // group (conflict-free 16-byte shared-memory stores), the next 8 the next group (64 contiguous bytes per row of h)
-                    constexpr int NC4 = C2P / 4;
-                    static_assert(F2 % 8 == 0, "per-hop state staging assumes F2 % 8 == 0");
-                    for (int idx = tid; idx < S * NC4 * F2; idx += NT) {
-                        const int s = idx / (NC4 * F2), r = idx % (NC4 * F2);
-                        const int f = (r % 8) + 8 * (r / (8 * NC4)), c4 = (r / 8) % NC4, gs = x.s0 + s;
-                        f4 v = mk4(0.f, 0.f, 0.f, 0.f);
-                        if (4 * c4 < C2 && gs < prm.n_streams) v = ld_state4(prm.state + st_h(prm, k, gs) + f * C2 + 4 * c4);
-                        st4(H + rf_off(4 * c4, s, f), v);
-                    }
-                });
-            }
             // ---- fused GRU step: 6 weight sets -> accumulators R | Z | NX | NH (NPG columns each) ----
             x.phase(PH_GRU, [&](int tid) {
                 using L = typename P::TGru;
@@ -1670,8 +1682,9 @@ template <class P> struct Frame {
                             }
                         }
                     }
-                }, XTS);
+                }, XTS, [&](int t) { if (k + 1 < C::K) prefetch_h(t, k + 1); });      // the attention output has been read: stage the next block's state over it
                 if constexpr (P::H_TMEM) x.tmem_st_wait();
+                if constexpr (!P::H_RES) x.async_wait_all();
             });
             ci += P::TFc::NCHUNK;
             if (dbg) {
@@ -2287,6 +2300,19 @@ template <class P> struct Frame {
                     for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(sm + P::SM_SK + i * ACT + idx, ld4(x.gs + P::TP_O_SK + i * ACT + idx));
             });
         }
+        // Spilled skip tensors (configs whose skip tensors do not all fit shared memory) come back from the L2-resident scratch into W0
+        // as 16-byte asynchronous copies issued as soon as the MMAs of the layer that last read W0 have completed (rf_post for the
+        // deepest one, the k = 3 conv of the previous decoder stage for the others), under that layer's epilogue, instead of in a
+        // phase of their own.
+        auto prefetch_skip = [&](int tid, int sk) {
+            if constexpr (P::TC && P::SKIP_SMEM < P::NSK) {
+                if (sk >= P::SKIP_SMEM) {
+                    const float* gsrc = x.gs + (size_t)(sk - P::SKIP_SMEM) * ACT;
+                    for (int idx = tid * 4; idx < ACT; idx += NT * 4) x.async_copy16(W0 + idx, gsrc + idx);
+                }
+                x.async_commit();
+            }
+        };
         // ================= rf_post: Linear(F2->F1), 1x1 conv =================
         float* Zb = AB + P::O_Z;
         if constexpr (P::LIN_TC) {
@@ -2310,7 +2336,9 @@ template <class P> struct Frame {
             x.phase(PH_RF_POST, [&](int tid) {
                 zero_halo(W1, tid);          // W1 was FFT / RNNFormer scratch
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
-                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1,
+                                              [&](int t) { prefetch_skip(t, E); });      // Zb (in W0) has been read: the deepest skip tensor may land there
+                if constexpr (P::SKIP_SMEM < P::NSK) x.async_wait_all();
             });
             ci += P::TRfPost::NCHUNK;
         } else if constexpr (P::TC) {
@@ -2349,7 +2377,9 @@ template <class P> struct Frame {
             x.phase(PH_RF_POST, [&](int tid) {
                 zero_halo(W1, tid);          // W1 was FFT / RNNFormer scratch
                 const auto a0 = x.make_desc(Zb + S * 4, SLABF);
-                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1);
+                tc_layer<typename P::TRfPost>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi, P::ZB1,
+                                              [&](int t) { prefetch_skip(t, E); });      // Zb (in W0) has been read: the deepest skip tensor may land there
+                if constexpr (P::SKIP_SMEM < P::NSK) x.async_wait_all();
             });
             ci += P::TRfPost::NCHUNK;
         } else {
@@ -2376,10 +2406,12 @@ template <class P> struct Frame {
             if (sk < P::SKIP_SMEM) {
                 skip = sm + P::SM_SK + sk * ACT;
             } else {
-                const float* gsrc = x.gs + (size_t)(sk - P::SKIP_SMEM) * ACT;
-                x.phase(PH_SKIP_LOAD, [&](int tid) {
-                    for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(W0 + idx, ld4(gsrc + idx));
-                });
+                if constexpr (!P::TC) {          // (tensor-core variants: prefetched under the previous layer's epilogue, see prefetch_skip)
+                    const float* gsrc = x.gs + (size_t)(sk - P::SKIP_SMEM) * ACT;
+                    x.phase(PH_SKIP_LOAD, [&](int tid) {
+                        for (int idx = tid * 4; idx < ACT; idx += NT * 4) st4(W0 + idx, ld4(gsrc + idx));
+                    });
+                }
                 skip = W0;
             }
             const float* b1 = aux + (i < E ? A.dec1_b(i) : A.dp_b);
@@ -2399,7 +2431,9 @@ template <class P> struct Frame {
                     TcEpiAct epi2{W1, aux + A.dec2_b(i), nullptr, true, true};      // rf_post zeroed W1's halos this frame
                     x.phase(PH_DEC, [&](int tid) {
                         const auto a0 = x.make_desc(W0 + S * 4, SLABF);
-                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2, P::ACT1);
+                        tc_layer<typename P::TConv3>(x, tid, ci, [&](int j) { return x.desc_add(a0, 2 * j * SLABF); }, S, epi2, P::ACT1,
+                                                     [&](int t) { prefetch_skip(t, sk - 1); });      // W0 has been read: the next stage's skip tensor
+                        if constexpr (P::SKIP_SMEM < P::NSK) x.async_wait_all();
                     });
                     ci += P::TConv3::NCHUNK;
                     if (dbg) dump_geo1(W1, TAP_DEC + i * C1 * F1);

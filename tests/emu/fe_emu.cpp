@@ -140,6 +140,9 @@ template <class P> struct EmuCtx {
         for (int e = 0; e < 4; ++e) tmem[row * 512 + col + e] = v[e];
     }
     void tmem_st4_row(int row, int col, const float* v) { for (int e = 0; e < 4; ++e) tmem[row * 512 + col + e] = v[e]; }
+    void async_copy16(float* dst, const float* src) const { std::memcpy(dst, src, 16); }
+    void async_commit() const {}
+    void async_wait_all() const {}
     void tmem_st_wait() const {}
     void tmem_ld16(int tid, int col, float* v) const {      // tcgen05.ld.16x256b.x1
         const int q = (tid >> 5) & 3, t = tid & 31, l0 = 32 * q + t / 4, c = col + 2 * (t % 4);
