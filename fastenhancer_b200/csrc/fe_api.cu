@@ -280,21 +280,29 @@ struct fe_state {
 
 namespace {
 
+// Which streams-per-CTA variant serves `n_streams` streams fastest.  The chain per hop is mostly fixed latency, so a CTA with S streams
+// costs about r(S) = 1 / 1.35 / 2.4 (S = 1 / 2 / 4; measured: B 1.02-1.06 and M 1.37 for two streams, B f16 1.84 for four -- the upper
+// ends, so that ties go to the smaller, lower-latency variant) of a one-stream CTA, and the launch takes rounds(S) x r(S): whole rounds
+// of one CTA per SM, or -- where hop-sliced launches even out the last round (variants without hop-tiled rings) -- the fractional
+// number.  E.g. B: 100 streams -> S = 1 (one round either way), 200 or 256 -> S = 2 (one round instead of two), 4096 (f16) -> S = 4.
 int pick_variant(fe_engine* e, int n_streams) {
     // variants are sorted by (tc, S); only those of the engine's precision mode are eligible
-    int first = -1;
     if (e->forced_s > 0) {
         for (size_t i = 0; i < e->variants.size(); ++i)
             if (e->variants[i].ops.tc == e->tc && e->variants[i].ops.S == e->forced_s) return (int)i;
     }
-    // largest S that still gives most SMs a CTA; otherwise the smallest S
-    for (int i = (int)e->variants.size() - 1; i >= 0; --i) {
+    int best = -1;
+    double best_cost = 0.0;
+    for (size_t i = 0; i < e->variants.size(); ++i) {
         if (e->variants[i].ops.tc != e->tc) continue;
-        first = i;
         const int S = e->variants[i].ops.S;
-        if ((n_streams + S - 1) / S >= (e->num_sms * 4) / 5) return i;
+        const double groups = (double)((n_streams + S - 1) / S);
+        const bool sliced = e->hop_slicing && !e->variants[i].ops.hop_ring;
+        const double rounds = (sliced && groups > e->num_sms) ? 1.02 * groups / e->num_sms : std::ceil(groups / e->num_sms);
+        const double cost = rounds * (S == 1 ? 1.0 : (S == 2 ? 1.35 : 0.6 * S));
+        if (best < 0 || cost < best_cost - 1e-9) { best = (int)i; best_cost = cost; }
     }
-    return first;
+    return best;
 }
 
 int ensure_variant(fe_engine* e, int vi) {

@@ -120,6 +120,18 @@ def test_hop_sliced_launch_is_bit_identical(name, B, nh, engines, precision):
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
 
 
+def test_variant_choice_follows_the_round_model(canonical):
+    """streams-per-CTA variant per batch size: rounds of one CTA per SM x the cost of an S-stream CTA (fe_api.cu::pick_variant)."""
+    from fastenhancer_b200.engine import Engine
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    eng = Engine(PRESETS["16k_b"], canonical("16k_b"), "cuda:0")                    # fp32x3: S in {1, 2}
+    assert [eng.streams_per_cta(n) for n in (1, sms, sms + 1, 2 * sms, 4096)] == [1, 1, 2, 2, 2]
+    eng = Engine(PRESETS["16k_b"], canonical("16k_b"), "cuda:0", precision="f16")   # S in {1, 2, 4}
+    assert [eng.streams_per_cta(n) for n in (sms, 2 * sms, 4096)] == [1, 2, 4]
+    eng = Engine(PRESETS["16k_m"], canonical("16k_m"), "cuda:0", precision="bf16")  # S in {1, 2}, hop-sliced launches
+    assert [eng.streams_per_cta(n) for n in (sms, 256, 512)] == [1, 2, 2]
+
+
 @pytest.mark.parametrize("name", ["16k_t", "16k_b", "16k_m", "48k_l"])
 def test_hop_by_hop_equals_one_launch_bit_exact(name, engines):
     """1 launch of n hops == n launches of 1 hop: the state round trip through HBM loses nothing."""
