@@ -1326,6 +1326,19 @@ template <class P> struct Frame {
                         // one MMA per (input, k-step): h tiles first (k-step 0 overwrites all four accumulator blocks, zeroing NX), then x
                         const int inp = tile < L::NKS ? 1 : 0, j = tile % L::NKS;
                         const bool first = tile == 0;
+                        if constexpr (L::WIDE) {
+                            // 4 NPG > 256 columns: the first h tile writes [R | Z | NH], the first x tile is NX alone (accumulate = 0) + [R | Z]
+                            static_assert(!P::H_TMEM, "the wide merged form reads its A operands from shared memory");
+                            const auto a = x.desc_add(inp == 0 ? dx : dh, 2 * j * RSLABF);
+                            if (inp == 0 && j == 0) {
+                                x.template mma<M64>(tid, a, wd, NPG, 0, false, P::RSLOTS);
+                                x.template mma<M64>(tid, a, x.desc_add(wd, NPG * 4), 2 * NPG, NPG, true, P::RSLOTS);
+                            } else {
+                                const int r0 = inp == 1 ? NPG : 0;
+                                x.template mma<M64>(tid, a, x.desc_add(wd, r0 * 4), 3 * NPG, r0, !first, P::RSLOTS);
+                            }
+                            return;
+                        }
                         const int row0 = (inp == 1 && !first) ? NPG : 0;           // first weight row = first accumulator column
                         const int n = first ? 4 * NPG : 3 * NPG;
                         const auto wsub = x.desc_add(wd, row0 * 4);

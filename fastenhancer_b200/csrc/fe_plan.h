@@ -146,11 +146,11 @@ struct TcGemm {
 };
 
 // Fused GRU on the tensor cores.
-// MERGED (4 * NPG <= 256: T, B, S): the accumulator columns are [ NX | R | Z | NH ] and every (input, k-step) is ONE MMA with N = 3 NPG
+// MERGED (3 * NPG <= 256: T, B, S, M): the accumulator columns are [ NX | R | Z | NH ] and every (input, k-step) is ONE MMA with N = 3 NPG
 // on a tile [2][4 NPG][4] whose rows are [ W_in | W_r | W_z | W_hn ] (x tiles: W_hn rows zero, h tiles: W_in rows zero): the h tiles
 // come first -- k-step 0 with N = 4 NPG and accumulate = 0, which also zeroes NX -- then accumulate onto columns NPG .. 4 NPG - 1
 // (rows NPG ..), and the x tiles accumulate onto columns 0 .. 3 NPG - 1 (rows 0 ..).  Half the MMAs of the split form.
-// Split form (M, L): per (input x | h, k-step) one tile [ R|Z part: [2][2 NPG][4] | N part: [2][NPG][4] ], i.e. two MMAs: N = 2 NPG into
+// Split form (L): per (input x | h, k-step) one tile [ R|Z part: [2][2 NPG][4] | N part: [2][NPG][4] ], i.e. two MMAs: N = 2 NPG into
 // the R|Z accumulator columns (x and h accumulate together) and N = NPG into NX or NH; x tiles first; columns [ R | Z | NX | NH ].
 // KE = 16: fp16 operands (x and h as packed halves), tiles [2][rows][8 halves].
 template <int NPOS_, int C2_, int CHUNK_, int KE_ = 8, int PARTS_ = 1>
@@ -160,14 +160,18 @@ struct TcGru {
 #ifndef FE_GRU_MERGE
 #define FE_GRU_MERGE 1
 #endif
-    static constexpr bool MERGED = FE_GRU_MERGE && 4 * NPG <= 256;
+    static constexpr bool MERGED = FE_GRU_MERGE && 3 * NPG <= 256;
+    // WIDE (M: 3 NPG <= 256 < 4 NPG): no single MMA covers all four accumulator blocks, so the first h tile writes [ R | Z | NH ]
+    // (N = 3 NPG, accumulate = 0) and the first x tile is two MMAs -- NX alone with accumulate = 0, then [ R | Z ] accumulating --;
+    // every other tile is one N = 3 NPG MMA as in the narrow form: 2 NKS + 1 MMAs per block instead of the split form's 4 NKS.
+    static constexpr bool WIDE = MERGED && 4 * NPG > 256;
     static constexpr int NP = MERGED ? 4 * NPG : 2 * NPG;              // rows (LBO) of the tile / of its R|Z part
     static constexpr int NTILE = 2 * NKS;              // MERGED: h tiles, then x tiles; split: x tiles, then h tiles
     static constexpr int TILE1 = (MERGED ? 4 : 3) * NPG * 8;
     static constexpr int WLBO = NP * 4;
     static constexpr int TILE = TILE1 * PARTS;
     static constexpr int COL_NX = MERGED ? 0 : 2 * NPG, COL_R = MERGED ? NPG : 0, COL_Z = MERGED ? 2 * NPG : NPG, COL_NH = 3 * NPG;
-    static_assert(TILE <= CHUNK_ && NP <= 256, "GRU tile");
+    static_assert(TILE <= CHUNK_ && (MERGED ? 3 * NPG : NP) <= 256, "GRU tile");
     static constexpr int TPC = cmax(1, cmin(NTILE, CHUNK_ / TILE));
     static constexpr int NCHUNK = cdiv(NTILE, TPC);
     static constexpr int FLOATS = NTILE * TILE;
