@@ -2243,38 +2243,42 @@ template <class P> struct Frame {
 #pragma unroll
                             for (int d = 0; d < HD; ++d) { q[d] = qb[d * PR + i] * scale; o[d] = 0.f; }
                             float mx = -INFINITY, den = 0.f;
-                            if constexpr (F2 <= 48) {          // scores stay in registers between the two softmax passes
-                                float sc[F2];
+                            // Online softmax over chunks of 16 keys, four keys per shared-memory load: K and V are channel-major rows with
+                            // the positions contiguous, so one float4 feeds four multiply-adds (the scalar form issued one broadcast load per
+                            // multiply-add and, beyond 48 tokens, computed every score twice: 22 % of a hop of 48 kHz L).
+                            constexpr int CH = 16;
+#pragma unroll 1
+                            for (int j0 = 0; j0 < F2; j0 += CH) {
+                                float sc[CH], cm = mx;
 #pragma unroll
-                                for (int j = 0; j < F2; ++j) {
-                                    float a = 0.f;
+                                for (int jj = 0; jj < CH; jj += 4) {
+                                    if (j0 + jj < F2) {          // (F2 is a multiple of 4: whole float4 groups)
+                                        f4 a = mk4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
-                                    sc[j] = a;
-                                    mx = fmaxf(mx, a);
+                                        for (int d = 0; d < HD; ++d) {
+                                            const f4 kv = ld4(qb + (HD + d) * PR + j0 + jj);
+                                            a.x = fmaf(q[d], kv.x, a.x); a.y = fmaf(q[d], kv.y, a.y); a.z = fmaf(q[d], kv.z, a.z); a.w = fmaf(q[d], kv.w, a.w);
+                                        }
+                                        sc[jj] = a.x; sc[jj + 1] = a.y; sc[jj + 2] = a.z; sc[jj + 3] = a.w;
+                                        cm = fmaxf(fmaxf(cm, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+                                    }
                                 }
+                                const float corr = fe_exp(mx - cm);            // first chunk: exp(-inf) = 0 on zeros
+                                den *= corr;
 #pragma unroll
-                                for (int j = 0; j < F2; ++j) {
-                                    const float pj = fe_exp(sc[j] - mx);
-                                    den += pj;
+                                for (int d = 0; d < HD; ++d) o[d] *= corr;
+                                mx = cm;
 #pragma unroll
-                                    for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
-                                }
-                            } else {
-                                for (int j = 0; j < F2; ++j) {
-                                    float a = 0.f;
+                                for (int jj = 0; jj < CH; jj += 4) {
+                                    if (j0 + jj < F2) {
+                                        const float p0 = fe_exp(sc[jj] - mx), p1 = fe_exp(sc[jj + 1] - mx), p2 = fe_exp(sc[jj + 2] - mx), p3 = fe_exp(sc[jj + 3] - mx);
+                                        den += (p0 + p1) + (p2 + p3);
 #pragma unroll
-                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
-                                    mx = fmaxf(mx, a);
-                                }
-                                for (int j = 0; j < F2; ++j) {
-                                    float a = 0.f;
-#pragma unroll
-                                    for (int d = 0; d < HD; ++d) a = fmaf(q[d], qb[(HD + d) * PR + j], a);
-                                    const float pj = fe_exp(a - mx);
-                                    den += pj;
-#pragma unroll
-                                    for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, qb[(2 * HD + d) * PR + j], o[d]);
+                                        for (int d = 0; d < HD; ++d) {
+                                            const f4 vv = ld4(qb + (2 * HD + d) * PR + j0 + jj);
+                                            o[d] = fmaf(p3, vv.w, fmaf(p2, vv.z, fmaf(p1, vv.y, fmaf(p0, vv.x, o[d]))));
+                                        }
+                                    }
                                 }
                             }
                             const float inv = 1.0f / den;
