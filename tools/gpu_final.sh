@@ -6,3 +6,4 @@ echo "=== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q --maxfai
 echo "=== smoke"; timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee $OUT/smoke.txt
 echo "=== bench"; timeout 900 python bench.py 2>&1 | tail -1 | tee $OUT/bench.json | cut -c1-200
 echo "=== bench config 3"; timeout 900 python bench.py --config 3 --steps 5 2>&1 | tail -1 | tee $OUT/bench_config3.json | cut -c1-200
+echo "=== bench config 4 (default fp32 family)"; timeout 900 python bench.py --config 4 --steps 3 --no-cpu-baseline --no-extras 2>&1 | tail -1 | tee $OUT/bench_config4.json | cut -c1-200
