@@ -28,6 +28,14 @@ template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAG
 // Two streams per CTA for the larger configs (M in f16 / bf16, S in tf32 / bf16, 48 kHz B / S): the chain per hop is mostly fixed latency, so
 // the second stream costs ~40 % (M, 512 streams: 313 -> 215 us / hop, 1.64 -> 2.38 M frames/s) even though the skip tensors of M then
 // spill to the L2-resident scratch and the front / back end overlap no longer fits.
+// fp32 FMA family of the wide configs (M / L, one stream per CTA): register tiles of the RNNFormer layers sized so that every layer is one
+// pass with all eight warps busy -- rnn_fc / attn_fc / qkv with up to 12 channels per lane (8 left L's 96-channel linears with a
+// half-empty second pass), the fused GRU tile 4 positions x 4 (M: 5) channels per lane instead of 2 x 6 (13 instead of 6.5
+// multiply-adds per shared-memory load).  The tensor-core families of the same (config, S) do not use these fields.
+template <> struct Tune<C16M, 1> : TuneBase<C16M, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 5; };
+template <> struct Tune<C48M, 1> : TuneBase<C48M, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 5; };
+template <> struct Tune<C16L, 1> : TuneBase<C16L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 4; };
+template <> struct Tune<C48L, 1> : TuneBase<C48L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 4; };
 // B, 4 streams per CTA (throughput variant for thousands of streams: the RNNFormer tiles carry 96 of 128 rows instead of 48, the conv
 // section runs two M tiles per layer): the activations of four streams leave room for a 2 x 16 KB weight ring only.
 template <> struct Tune<C16B, 4> : TuneBase<C16B, 4> { static constexpr int CHUNK = 4096; };
