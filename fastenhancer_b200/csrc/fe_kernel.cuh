@@ -2106,7 +2106,9 @@ template <class P> struct Frame {
                 // GRU state h[k] of the CTA's streams -> HB (zero for the first offline / spec frame is the caller's job)
                 x.phase(PH_HLOAD, [&](int tid) {
                     for (int idx = tid; idx < S * C2 * F2; idx += NT) {
-                        int s = idx / (C2 * F2), r = idx % (C2 * F2), c = r / F2, f = r % F2, gs = x.s0 + s;
+                        // channel fastest: the [F2][C2] rows of the state are read coalesced (the transposing store pays an 8-way bank
+                        // conflict instead: position-fastest reads were 4-byte accesses C2 floats apart, 4.8 % of a hop of 48 kHz L)
+                        int s = idx / (C2 * F2), r = idx % (C2 * F2), f = r / C2, c = r % C2, gs = x.s0 + s;
                         float v = 0.f;
                         if (!x_only && gs < prm.n_streams) v = ld_state(prm.state + st_h(prm, k, gs) + f * C2 + c);
                         HB[c * PR + s * F2P + f] = v;
