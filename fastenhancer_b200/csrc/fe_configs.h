@@ -34,8 +34,11 @@ template <> struct Tune<C16T, 2> : TuneBase<C16T, 2> { static constexpr int STAG
 // multiply-adds per shared-memory load).  The tensor-core families of the same (config, S) do not use these fields.
 template <> struct Tune<C16M, 1> : TuneBase<C16M, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 5; };
 template <> struct Tune<C48M, 1> : TuneBase<C48M, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 5; };
-template <> struct Tune<C16L, 1> : TuneBase<C16L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 4; };
-template <> struct Tune<C48L, 1> : TuneBase<C48L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = 4; };
+#ifndef FE_L_CT_GRU
+#define FE_L_CT_GRU 4
+#endif
+template <> struct Tune<C16L, 1> : TuneBase<C16L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = FE_L_CT_GRU; };
+template <> struct Tune<C48L, 1> : TuneBase<C48L, 1> { static constexpr int CT_RF = 12, PT_GRU = 4, CT_GRU = FE_L_CT_GRU; };
 // B, 4 streams per CTA (throughput variant for thousands of streams: the RNNFormer tiles carry 96 of 128 rows instead of 48, the conv
 // section runs two M tiles per layer): the activations of four streams leave room for a 2 x 16 KB weight ring only.
 template <> struct Tune<C16B, 4> : TuneBase<C16B, 4> { static constexpr int CHUNK = 4096; };
