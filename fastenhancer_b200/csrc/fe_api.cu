@@ -941,6 +941,12 @@ FE_API int fe_stft_gemm(fe_engine* e, const float* wav, int B, long long ld, int
     return FE_OK;
 }
 
+// The slicing decision on its own (pure host arithmetic, no device needed): hops per range for a streaming launch of `n_groups` stream
+// groups x `n_hops` hops on `num_sms` SMs, 0 = do not slice.
+FE_API int fe_plan_hop_slices(int n_groups, int n_hops, int num_sms) {
+    if (n_groups <= 0 || n_hops <= 0 || num_sms <= 0) return 0;
+    return plan_slices(n_groups, n_hops, num_sms);
+}
 FE_API int fe_set_hop_slicing(fe_engine* e, int on) {
     if (!e) return fail(FE_ERR_ARG, "fe_set_hop_slicing: null engine");
     e->hop_slicing = on ? 1 : 0;

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fe_spec", "fe_stft", "fe_istft", "fe_offline", "fe_streams_per_cta", "fe_set_streams_per_cta", "fe_kernel_launches", "fe_tap_floats",
     "fe_stream_taps", "fe_profile_slots", "fe_set_profile", "fe_set_precision", "fe_get_precision", "fe_state_reserve_host",
     "fe_state_create_on", "fe_state_planes", "fe_microbench_fma", "fe_fold_device", "fe_create_from_device",
-    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode", "fe_stft_gemm", "fe_set_hop_slicing",
+    "fe_pcm16_to_float", "fe_resample_poly", "fe_float_to_pcm16", "fe_set_offline_mode", "fe_stft_gemm", "fe_set_hop_slicing", "fe_plan_hop_slices",
 )
 
 #: precision name -> fe_set_precision mode (include/fastenhancer_b200.h)
@@ -100,6 +100,7 @@ def load_library(build_if_missing: bool = True):
     lib.fe_get_precision.argtypes = [vp]
     lib.fe_set_offline_mode.argtypes = [vp, ip]
     lib.fe_set_hop_slicing.argtypes = [vp, ip]
+    lib.fe_plan_hop_slices.argtypes = [ip, ip, ip]
     lib.fe_stft_gemm.argtypes = [vp, fp, ip, ll, ip, fp, ip, vp]
     _lib = lib
     return lib

@@ -171,6 +171,7 @@ int fe_get_precision(fe_engine* e);               /* 0 TF32, 1 fp32 FMA pipe, 2 
  * Available in the kernel variants without hop-tiled rings (M / L: the configs with one or two streams per CTA).
  * Results are bit-identical to the unsliced launch. */
 int fe_set_hop_slicing(fe_engine* e, int on);
+int fe_plan_hop_slices(int n_groups, int n_hops, int num_sms);   /* hops per range the launch would use (0 = unsliced); no device needed */
 int fe_streams_per_cta(fe_engine* e, int n_streams);            /* kernel variant the engine would pick */
 int fe_set_streams_per_cta(fe_engine* e, int s);                /* force a variant (0 = automatic) */
 long long fe_kernel_launches(fe_engine* e);                     /* kernels of this library launched so far (fused kernel, GRU scan, overlap-add) */

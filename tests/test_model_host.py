@@ -54,3 +54,34 @@ def test_unsupported_kwargs_rejected():
     kw["mask"] = "sigmoid"
     with pytest.raises(ValueError):
         Model(**kw)
+
+
+def _makespan(n_groups, n_hops, num_sms, slice_hops):
+    """rounds of a full chain that a launch takes: items (range, group) dealt round-robin to min(SMs, items) persistent CTAs, an item
+    waits for the previous range of its group (the schedule of fe_kernel.cuh::Frame::run)."""
+    if slice_hops == 0:
+        return float(-(-n_groups // num_sms))
+    nr = -(-n_hops // slice_hops)
+    total, G = n_groups * nr, min(num_sms, n_groups * nr)
+    fin, cta = [0.0] * total, [0.0] * G
+    for i in range(total):
+        r = i // n_groups
+        start = max(cta[i % G], fin[i - n_groups] if r else 0.0)
+        fin[i] = start + min(slice_hops, n_hops - r * slice_hops) / n_hops
+        cta[i % G] = fin[i]
+    return max(fin)
+
+
+def test_hop_slice_plan_shortens_multi_round_launches():
+    """fe_plan_hop_slices (host arithmetic of the C ABI, no device): nothing to gain with at most one stream group per SM (the chains are
+    the critical path) or on short launches; multi-round launches get ranges of at least 4 hops that shorten the simulated schedule."""
+    from fastenhancer_b200.engine import load_library
+    lib = load_library()
+    assert lib.fe_plan_hop_slices(128, 626, 148) == 0 and lib.fe_plan_hop_slices(148, 626, 148) == 0      # one round either way
+    assert lib.fe_plan_hop_slices(256, 4, 148) == 0                                                        # too short to slice
+    for groups, hops in ((256, 626), (256, 64), (512, 1003), (200, 2405), (1024, 100)):
+        h = lib.fe_plan_hop_slices(groups, hops, 148)
+        assert h == 0 or h >= 4
+        if h:
+            assert _makespan(groups, hops, 148, h) < 0.97 * _makespan(groups, hops, 148, 0), (groups, hops, h)
+    assert lib.fe_plan_hop_slices(256, 626, 148) > 0 and lib.fe_plan_hop_slices(512, 1003, 148) > 0
